@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py - frames/s of one CADDY training step (forward + all losses + backward + gradient all-reduce + Adam).
+
+Workload (BASELINE.json configs[1]): BAIR 256x256, seq_len 16, batch 8 per GPU, full CADDY (E+R+A+D), ground-truth
+context 6 frames, L1 + VGG19-perceptual (3 resolutions) + states MSE + KL + smooth-MI losses, synthetic U[-1,1] frames,
+reference-default random init (no network for datasets / checkpoints).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # this implementation (hand-written sm_100a kernels)
+    python bench.py --impl reference --steps 2 --warmup 1         # the reference algorithm on the host CPU cores
+
+One JSON line on stdout (rank 0).  `value` = whole-job frames/s with inputs resident in HBM; `e2e` = the same step
+driven through the public API from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed region).
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config kind, reduced, H, W, S, B per GPU, T, gt_init)
+    "bair256_b8_t16": dict(config="bair", reduced=False, H=256, W=256, S=1, B=8, T=16, gt_init=6),
+    "bair64_b2_t4": dict(config="bair", reduced=False, H=64, W=64, S=1, B=2, T=4, gt_init=3),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pvg_b200", choices=["pvg_b200", "reference"])
+    ap.add_argument("--workload", default="bair256_b8_t16", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=16, help="frames (B=1 x T) of the CPU baseline sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured (bf16 cuBLAS, sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+def synthetic_batch(w, seed=0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.rand((w["B"], w["T"], 3 * w["S"], w["H"], w["W"]), generator=g) * 2.0 - 1.0
+    return (obs, torch.zeros((w["B"], w["T"]), dtype=torch.int32), torch.zeros((w["B"], w["T"])),
+            torch.zeros((w["B"], w["T"]), dtype=torch.bool))
+
+
+def cpu_reference_step_time(w, frames, steps, warmup):
+    """The reference algorithm (CPU oracle port: oracle/caddy_oracle.py, pinned against the unmodified reference) on
+    all host cores: forward + all losses + backward + Adam on a B=1 slice of the workload."""
+    import torch
+    from oracle import caddy_oracle as O
+    from oracle.cases import build_config
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = build_config(dict(config=w["config"], H=w["H"], W=w["W"], S=w["S"]))
+    t = max(3, min(w["T"], frames))
+    sd = O.make_weights(cfg, 0, w["reduced"])
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))
+                  and "centroid" not in k else v.clone()) for k, v in sd.items()}
+    train = [v for v in params.values() if v.requires_grad]
+    m = [torch.zeros_like(p) for p in train]
+    v2 = [torch.zeros_like(p) for p in train]
+    vgg_sd = O.make_vgg_weights()
+    mi = O.MutualInformation(cfg["data"]["actions_count"], cfg["training"]["mutual_information_estimation_alpha"])
+    bt = synthetic_batch(dict(w, B=1, T=t))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        total, _, _ = O.compute_losses(params, vgg_sd, cfg, mi, bt, min(w["gt_init"], t - 1), 1.0)
+        for p in train:
+            p.grad = None
+        total.backward()
+        with torch.no_grad():
+            live = [(p, p.grad, a, b) for p, a, b in zip(train, m, v2) if p.grad is not None]
+            O.adam_step([x[0] for x in live], [x[1] for x in live], [x[2] for x in live], [x[3] for x in live], s + 1, 4e-4, 1e-6)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return dict(value=t / mean, unit="frames/s", cores=cores, kind="port",
+                sample=f"B=1 x T={t} of {w['H']}x{w['W']} (one sequence of the batch), {len(times)} timed step(s), "
+                       f"{mean:.2f} s/step, torch CPU fp32, {cores} threads"), mean
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, mean = cpu_reference_step_time(w, args.cpu_sample_frames, max(1, args.steps), max(0, args.warmup))
+    line = dict(impl="reference", metric="frames/sec (train step)", value=cb["value"], unit="frames/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=mean * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, note="reference algorithm on host CPU cores; bounded sample: " + cb["sample"]),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    from oracle.cases import build_config            # config dict only (plain data; no oracle compute on this path)
+    from playablevideogeneration_b200 import _lib, ops
+    from playablevideogeneration_b200.caddy import Model
+    from playablevideogeneration_b200.training.step import TrainStep
+    from playablevideogeneration_b200.vgg import Vgg19
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    ops.set_precision(args.precision)
+
+    cfg = build_config(dict(config=w["config"], H=w["H"], W=w["W"], S=w["S"]))
+    torch.manual_seed(0); random.seed(0)
+    model = Model(cfg, reduced=w["reduced"]).to(dev)
+    vgg = Vgg19()
+    g = torch.Generator().manual_seed(1234)
+    with torch.no_grad():                                # He-init stand-in for the ImageNet weights (no network)
+        for conv in vgg.convs.values():
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (conv.weight.shape[1] * 9)) ** 0.5)
+            conv.bias.copy_(torch.randn(conv.bias.shape, generator=g) * 0.05)
+    step = TrainStep(cfg, model, vgg, process_group=pg)
+    host = synthetic_batch(w, seed=rank)
+    host = tuple(t.pin_memory() for t in host)
+    resident = tuple(t.to(dev) for t in host)
+    frames_per_step = w["B"] * w["T"] * world
+    torch.manual_seed(100 + rank); random.seed(100 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step.step(resident, w["gt_init"], 1.0)
+    # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ops.conv_profile = []
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step.step(resident, w["gt_init"], 1.0)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count - launches0
+    prof, ops.conv_profile = ops.conv_profile, None
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    # ---- timed region 2: end to end through the public API from pinned host memory ---------------------------------
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e2.record()
+    loss_host = 0.0
+    for _ in range(args.steps):
+        batch = tuple(t.to(dev, non_blocking=True) for t in host)          # H2D of this step's inputs
+        total, _ = step.step(batch, w["gt_init"], 1.0)
+        loss_host = float(total.cpu()[0])                                  # D2H of the step's result
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv) from CUDA events recorded around its launches --
+    peaks = load_peaks()
+    roof = None
+    if prof:
+        tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+        flops = sum(f for _, _, f in prof)
+        ach = flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        roof = dict(bound="tensor", kernel="conv_umma_kernel (tcgen05 kind::tf32" + (", 3 MMAs per k-step" if args.precision == "tf32x3" else "") + ")",
+                    achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=None,
+                    launches_per_step=len(prof) / args.steps, avg_launch_us=tot_ms * 1e3 / len(prof),
+                    share_of_step=tot_ms / args.steps / ms_dev, peak_source=peaks["source"],
+                    note="achieved = algorithmic conv FLOPs (2*N*H*W*Cout*R*S*Cin, unpadded) / CUDA-event time of the launches; "
+                         "peak is the measured bf16 cuBLAS figure - kind::tf32 tops out at half of it, 3xTF32 at a sixth")
+    if rank != 0:
+        return
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_step_time(w, args.cpu_sample_frames, 1, 0)
+    line = dict(metric="frames/sec (train step, 256x256x3, seq=16)", value=frames_per_step / (ms_dev * 1e-3), unit="frames/s",
+                n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype={"tf32x3": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "tf32": "tf32",
+                                         "fp32": "f32"}[args.precision],
+                data="synthetic", impl="pvg_b200",
+                config=dict(workload=args.workload, per_gpu_batch=w["B"], seq_len=w["T"], frame=f"{w['H']}x{w['W']}x3",
+                            gt_init=w["gt_init"], parallelism=f"dp{world}", precision=args.precision,
+                            l2="inputs (100.7 MB/step) and per-step activations (>10 GB) exceed the 126 MB L2; no explicit flush"),
+                e2e=dict(value=frames_per_step / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d * world,
+                         d2h_bytes_per_step=8 * world, ms_per_step=ms_e2e, last_loss=loss_host),
+                gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu_base)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+/* pvg_b200.h - C ABI of the B200-native CADDY hot path (libpvg_b200.so).
+ *
+ * The reference (willi-menapace/PlayableVideoGeneration) has no native/FFI layer: every op on its hot path is a
+ * torch.nn / torch.nn.functional call.  Each entry point below therefore replaces a *library op
+ * call site* of the reference; the file:line next to it is that call site.  The Python host side
+ * (playablevideogeneration_b200/ops.py) binds these with ctypes and wraps them in torch.autograd.Function.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers into caller-owned storage (the callee never allocates, frees or retains);
+ *   - activations are NHWC fp32 ("channels_last" physical layout of a logical NCHW tensor);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and re-entrant per stream;
+ *   - return 0 on success, negative on error; pvg_last_error() returns the message of the last failure
+ *     on the calling thread;
+ *   - "lo" companions: in the fp32-equivalent 3xTF32 mode (nprod == 3) a tensor-core operand X is consumed as
+ *     X_hi + X_lo with X_lo = X - tf32(X); pvg_split_tf32 produces X_lo.
+ */
+#ifndef PVG_B200_H_
+#define PVG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVG_ACT_NONE    0
+#define PVG_ACT_LRELU   1   /* leaky_relu(slope)  - model/layers/residual_block.py:30, same_block.py:33, up_block.py:40 */
+#define PVG_ACT_RELU    2   /* torchvision VGG19 features, model/layers/vgg.py:16 */
+#define PVG_ACT_TANH    3   /* model/layers/final_block.py:27 */
+#define PVG_ACT_SIGMOID 4   /* model/main_model/representation_network.py:55 */
+
+#define PVG_ALGO_AUTO 0
+#define PVG_ALGO_SIMT 1     /* fp32 CUDA-core implicit GEMM (any shape) */
+#define PVG_ALGO_UMMA 2     /* tcgen05 / TMEM / TMA implicit GEMM (Cin % 32 == 0) */
+
+typedef struct pvg_conv_desc {
+  int32_t N, H, W;          /* output == input spatial size (all convs on the path are stride 1, "same" padding) */
+  int32_t Cin;              /* physical channels of x (== K per tap) */
+  int32_t Cout;             /* physical channels of y */
+  int32_t R, S, pad;        /* kernel height/width and zero padding (3,3,1 | 1,1,0 | 7,7,3) */
+  int32_t act;              /* PVG_ACT_* fused into the epilogue (after bias) */
+  float   slope;            /* leaky slope for PVG_ACT_LRELU */
+  int32_t algo;             /* PVG_ALGO_* */
+  int32_t nprod;            /* 1 = single TF32 product, 3 = 3xTF32 (fp32-equivalent); SIMT ignores it */
+} pvg_conv_desc;
+
+const char* pvg_last_error(void);
+int pvg_version(void);
+/* 1 if the current device is sm_100 (tcgen05 path usable) */
+int pvg_has_umma(void);
+
+/* ---- convolution: replaces nn.Conv2d forward (cuDNN) at residual_block.py:52,57,63, same_block.py:38,
+ *      up_block.py:37, final_block.py:26, convolutional_lstm_cell.py:92-95, representation_network.py:41,
+ *      model.py:413, vgg.py:48-52 ------------------------------------------------------------------------------ */
+/* w: [Cout][R][S][Cin] (K-major pack from pvg_pack_conv_weight); w_lo may be NULL when nprod == 1 / SIMT.
+ * y[n,h,w,co] = act(bias[co] + sum_{r,s,ci} x[n,h+r-pad,w+s-pad,ci] * w[co,r,s,ci]).   bias may be NULL. */
+int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+                   const float* bias, float* y, void* stream);
+/* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinP] (zero padded to CinP >= Cin) and data-gradient pack
+ * [CinP][R][S][Cout] with flipped taps (dgrad = pvg_conv2d_fwd(dy, bwd pack)).  *_lo = w - tf32(w); *_hi = tf32(w)
+ * when round_hi != 0 (tensor-core consumers) else w (SIMT consumers); any output pointer may be NULL. */
+int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinP, int round_hi,
+                         float* fwd_hi, float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream);
+/* weight gradient (cudnnConvolutionBackwardFilter): dw_oihw[co][ci][r][s] += sum_pixels dy * x ; x has CinP
+ * physical channels of which the first Cin are real.  dw must be zero-initialised by the caller. */
+int pvg_conv2d_wgrad(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* dy, float* dw_oihw,
+                     void* stream);
+/* out[c] = sum over M rows of x[M][C]  (bias gradient); scratch: double[C] */
+int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* out, void* stream);
+/* hi != NULL: hi = rna_tf32(x), lo = x - hi.  hi == NULL: lo = x - trunc_tf32(x) (x itself then serves as the hi
+ * operand; valid when the tensor core truncates raw fp32 inputs - probed at start-up by the host side). */
+int pvg_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* g = dy * act'(y) for an activation fused in a conv epilogue (y is the activation OUTPUT) */
+int pvg_act_bwd(const float* dy, const float* y, int act, float slope, float* g, int64_t n, void* stream);
+
+/* ---- BatchNorm2d (training: per-call batch statistics; eval: running statistics), optionally preceded by
+ *      avg_pool2d(2) and followed by (+residual) and an activation.  Replaces F.avg_pool2d + nn.BatchNorm2d +
+ *      LeakyReLU at residual_block.py:53-55,58,66-68, same_block.py:40-45, up_block.py:38-40,
+ *      representation_network.py:42-44, conv_dynamics_network.py:41-45.
+ *      `groups`: the batch dim is split in `groups` equal chunks with independent statistics (one reference
+ *      BatchNorm call per chunk) - lets time steps be batched without changing the reference's semantics. ------- */
+/* sums: double[groups][2][C], zero-initialised by caller: sum and sum of squares per channel */
+int pvg_bn_stats(const float* x, int N, int HW, int C, int groups, double* sums, void* stream);
+/* y = avg_pool2d(x, 2) (H, W even) and the statistics of y */
+int pvg_pool2_stats(const float* x, int N, int H, int W, int C, float* y, int groups, double* sums, void* stream);
+/* mean/invstd: float[groups][C]; running stats updated group after group with `momentum` (unbiased variance),
+ * exactly as `groups` successive nn.BatchNorm2d training calls would. count = elements per channel per group. */
+int pvg_bn_finalize(const double* sums, int64_t count, int groups, int C, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* invstd, void* stream);
+/* eval mode: mean = running_mean, invstd = rsqrt(running_var + eps) */
+int pvg_bn_eval_prepare(const float* running_mean, const float* running_var, int C, float eps,
+                        float* mean, float* invstd, void* stream);
+/* y = act((x - mean) * invstd * weight + bias (+ residual)) ; weight/bias may be NULL (affine=False) */
+int pvg_bn_apply(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
+                 const float* weight, const float* bias, const float* residual, int act, float slope,
+                 float* y, void* stream);
+/* backward pass 1: with g = dy * act'(y): sums2 (double[groups][2][C], zeroed) += (sum g, sum g * xhat) */
+int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, int HW, int C, int groups,
+                      const float* mean, const float* invstd, int act, float slope, double* sums2, void* stream);
+/* backward pass 2: dx = weight*invstd*(g - sum_g/M - xhat*sum_gx/M).  g_out (optional) receives g (gradient of the
+ * residual branch).  unpool != 0: x/dy are at (H/2,W/2) and dx is written at (H,W) as 0.25*dx (avg_pool2d backward).
+ * eval != 0: statistics are constants: dx = weight*invstd*g. */
+int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
+                     const float* mean, const float* invstd, const float* weight, int act, float slope,
+                     const double* sums2, int eval, int unpool, float* dx, float* g_out, void* stream);
+/* dweight[c] = sum_groups sum_gx ; dbias[c] = sum_groups sum_g */
+int pvg_bn_bwd_params(const double* sums2, int groups, int C, float* dweight, float* dbias, void* stream);
+
+/* ---- resampling: F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) at up_block.py:35,43;
+ *      F.interpolate(size, 'bilinear') of the ground truth at losses.py:92,450; nn.MaxPool2d(2) of VGG19 -------- */
+int pvg_upsample2x_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream);
+int pvg_upsample2x_bwd(const float* dy, int N, int H, int W, int C, float* dx, void* stream);   /* H,W = input size */
+int pvg_resize_bilinear(const float* x, int N, int H, int W, int C, float* y, int OH, int OW, void* stream);
+int pvg_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream);
+/* dx = (x is the first arg-max of its 2x2 window) ? dy : 0, times relu'(x) when relu_mask != 0 */
+int pvg_maxpool2_bwd(const float* dy, const float* x, const float* y, int N, int H, int W, int C, int relu_mask,
+                     float* dx, void* stream);
+
+/* ---- ConvLSTM cell point-wise part, convolutional_lstm_cell.py:92-101.  gates: [M][4][C] pre-activations in the
+ *      order input, forget, output, cell. ------------------------------------------------------------------------ */
+int pvg_lstm_fwd(const float* gates, const float* c_prev, int64_t M, int C, float* c_new, float* h_new, void* stream);
+int pvg_lstm_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc_new,
+                 int64_t M, int C, float* dgates, float* dc_prev, void* stream);
+
+/* ---- losses: nn.L1Loss (losses.py:59,118), |a-b|.mean(dim=[1,2,3]) per VGG level (losses.py:465) ------------- */
+/* out[n] = mean_i |a[n,i] - b[n,i]| ; out must be zeroed by the caller */
+int pvg_absdiff_mean_fwd(const float* a, const float* b, int N, int64_t count, double* out, void* stream);
+/* db[n,i] = -sign(a-b) * gout[n] / count */
+int pvg_absdiff_mean_bwd(const float* a, const float* b, const float* gout, int N, int64_t count, float* db,
+                         void* stream);
+
+/* ---- optimiser: torch.optim.Adam(lr, weight_decay) as configured at training/trainer.py:36 -------------------- */
+int pvg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVG_B200_H_ */

@@ -1,0 +1,401 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05) for sm_100a.
+//
+//   GEMM view      M = N*H*W output pixels (128 per CTA: a tn x th x tw patch), N = Cout (BN per CTA),
+//                  K = R*S*Cin walked tap by tap in 32-channel (128-byte) chunks.
+//   A operand      NHWC activations.  One 4-D TMA box {32 ch, tw, th, tn} per (tap, chunk) lands the shifted patch in
+//                  shared memory as 128 rows x 128 B with the 128-byte swizzle; the conv zero padding IS the TMA
+//                  out-of-bounds fill (negative / past-the-end coordinates), so there is no im2col buffer and no
+//                  boundary code in the main loop.
+//   B operand      weights packed [Cout][R][S][Cin] (K-major), 2-D TMA box {32, BN}, same swizzle.
+//   MMA            tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8, fp32 accumulators in TMEM (BN columns),
+//                  issued by one thread.  NPROD=3 runs the error-compensated split
+//                  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (fp32-equivalent accuracy at 3 MMAs per k-step).
+//   pipeline       warp 0: TMA producer; warp 1: MMA issuer (+TMEM alloc); warps 2-5: epilogue.  smem ring of STAGES
+//                  {A[,A_lo],B[,B_lo]} slots with full/empty mbarriers; tcgen05.commit releases slots and publishes the
+//                  accumulator.
+//   epilogue       tcgen05.ld 32 lanes x 16 columns per warp-instruction -> +bias -> activation -> NHWC global stores
+//                  (each thread owns one output pixel and writes its channels contiguously).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pvg {
+
+int conv2d_fwd_simt(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row (1024 B) swizzle atoms stacked along M/N.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 1024 B between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc_tf32() {
+  return (1u << 4)                 // D format: F32
+         | (2u << 7)               // A format: TF32
+         | (2u << 10)              // B format: TF32
+         | ((uint32_t)(BN >> 3) << 17)   // N >> 3
+         | ((uint32_t)(128 >> 4) << 24); // M >> 4 ; A and B K-major (bits 15, 16 = 0)
+}
+
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kChunk = 32;                 // channels per K chunk (128 B of fp32)
+constexpr int kABytes = kTileM * 128;      // 16 KB per A plane per stage
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BN, int NPROD>
+struct Cfg {
+  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "need at least a double buffer");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+};
+
+struct ConvParams {
+  int N, H, W, Cin, Cout, R, S, pad, act;
+  float slope;
+  int tw, th, tn;               // M-tile patch (tw*th*tn == 128)
+  int tiles_w, tiles_h, tiles_n;
+  const float* bias;
+  float* y;
+};
+
+template <int BN, int NPROD>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const ConvParams p) {
+  using C = Cfg<BN, NPROD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* acc_bar = empty_bar + C::kStages;
+  uint32_t* tmem_slot = (uint32_t*)(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+  const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+  const int tile_n = t;
+  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
+  const int co0 = blockIdx.y * BN;
+  const int chunks = p.Cin / kChunk;
+  const int k_iters = p.R * p.S * chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    if (NPROD == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int k = 0; k < k_iters; ++k) {
+        const int tap = k / chunks, cc = k - tap * chunks;
+        const int r = tap / p.S, s = tap - r * p.S;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = stage_base + stage * C::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        tma_load_4d(st, &tmA, &full_bar[stage], cc * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+        tma_load_2d(st + C::kPlanes * kABytes, &tmB, &full_bar[stage], k * kChunk, co0);
+        if (NPROD == 3) {
+          tma_load_4d(st + kABytes, &tmAlo, &full_bar[stage], cc * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma_load_2d(st + 2 * kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * kChunk, co0);
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32<BN>();
+      int stage = 0; uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
+        const uint32_t a_hi = st, a_lo = st + kABytes;
+        const uint32_t b_hi = st + C::kPlanes * kABytes, b_lo = b_hi + C::kBBytes;
+        if (NPROD == 3) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_lo + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, accumulate);
+            accumulate = 1;
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_lo + ks * 32), idesc, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&empty_bar[stage]);     // slot reusable once these MMAs have read it
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_bar);                 // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int wi = row % p.tw;
+    const int hi = (row / p.tw) % p.th;
+    const int ni = row / (p.tw * p.th);
+    const int ow = w0 + wi, oh = h0 + hi, on = n0 + ni;
+    const bool valid = ow < p.W && oh < p.H && on < p.N;
+    float* yrow = p.y + (((int64_t)on * p.H + oh) * p.W + ow) * p.Cout;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const bool vec_ok = (p.Cout % 4) == 0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      const int co = co0 + c;
+      if (!valid || co >= p.Cout) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float b = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
+        v[j] = act_fwd(v[j] + b, p.act, p.slope);
+      }
+      if (vec_ok && co + 16 <= p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (co + j < p.Cout) yrow[co + j] = v[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, C::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int encode_act_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, int tw, int th, int tn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return -3; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r)); return -3; }
+  return 0;
+}
+
+static int encode_w_map(CUtensorMap* m, const float* w, int Cout, int K, int bn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return -3; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); return -3; }
+  return 0;
+}
+
+// choose the 128-pixel patch (tw, th, tn) that wastes the fewest MMA rows
+static void choose_patch(int N, int H, int W, int* tw, int* th, int* tn) {
+  static const int cand[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {4, 32, 1}, {64, 2, 1}, {128, 1, 1}, {16, 4, 2},
+                                {8, 8, 2},  {4, 16, 2}, {16, 2, 4}, {8, 4, 4},  {4, 8, 4},  {4, 4, 8},   {8, 2, 8},
+                                {2, 8, 8},  {2, 2, 32}, {4, 2, 16}, {2, 4, 16}, {1, 1, 128}, {2, 1, 64}, {1, 2, 64}};
+  double best = -1;
+  for (auto& c : cand) {
+    int64_t tiles = (int64_t)ceil_div(W, c[0]) * ceil_div(H, c[1]) * ceil_div(N, c[2]);
+    double util = (double)N * H * W / ((double)tiles * 128.0);
+    if (util > best + 1e-9) { best = util; *tw = c[0]; *th = c[1]; *tn = c[2]; }
+  }
+}
+
+template <int BN, int NPROD>
+static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+                       const float* bias, float* y, cudaStream_t st) {
+  using C = Cfg<BN, NPROD>;
+  ConvParams p;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y;
+  choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
+  p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  const int K = d->R * d->S * d->Cin;
+  int rc;
+  if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
+  if ((rc = encode_w_map(&tmB, w, d->Cout, K, BN))) return rc;
+  if (NPROD == 3) {
+    if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, BN))) return rc;
+  } else {
+    tmAlo = tmA; tmBlo = tmB;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PVG_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)ceil_div(d->Cout, BN));
+  conv_umma_kernel<BN, NPROD><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmAlo, tmB, tmBlo, p);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+template <int NPROD>
+static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+                       const float* bias, float* y, cudaStream_t st) {
+  const int co = d->Cout;
+  if (co <= 16) return launch_umma<16, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (co <= 32) return launch_umma<32, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (co <= 64) return launch_umma<64, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (co <= 80) return launch_umma<80, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (NPROD == 1 && co % 256 == 0) return launch_umma<256, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  return launch_umma<128, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+}
+
+}  // namespace pvg
+
+using namespace pvg;
+
+extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+                              const float* bias, float* y, void* stream) {
+  PVG_CHECK_ARG(d && x && w && y, "null argument");
+  PVG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "empty problem");
+  PVG_CHECK_ARG(d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "only odd 'same' kernels are supported");
+  cudaStream_t st = (cudaStream_t)stream;
+  int algo = d->algo;
+  const bool umma_ok = (d->Cin % kChunk) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
+  if (algo == PVG_ALGO_AUTO) algo = (umma_ok && pvg_has_umma()) ? PVG_ALGO_UMMA : PVG_ALGO_SIMT;
+  if (algo == PVG_ALGO_SIMT) return conv2d_fwd_simt(d, x, w, bias, y, st);
+  PVG_CHECK_ARG(umma_ok, "tensor-core path needs Cin % 32 == 0 and 16-byte aligned operands");
+  if (d->nprod == 3) {
+    PVG_CHECK_ARG(x_lo && w_lo, "nprod == 3 needs x_lo and w_lo");
+    return dispatch_bn<3>(d, x, x_lo, w, w_lo, bias, y, st);
+  }
+  return dispatch_bn<1>(d, x, nullptr, w, nullptr, bias, y, st);
+}

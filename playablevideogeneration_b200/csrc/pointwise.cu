@@ -1,0 +1,792 @@
+// HBM-bound kernels of the CADDY hot path: BatchNorm (training/eval, forward/backward, optional fused avg-pool and
+// residual/activation), bilinear resampling, max-pool, ConvLSTM point-wise cell, L1-type reductions, Adam, TF32 split,
+// weight packing.  All tensors NHWC fp32.  Every kernel is a coalesced, float4-vectorised (when C % 4 == 0)
+// grid-stride loop sized in multiples of the SM count; reductions accumulate in fp64 and finish with one atomic per
+// CTA and channel.
+#include "common.cuh"
+
+namespace pvg {
+
+thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// small generic vector helpers: V = 4 (float4) or 1 (scalar) channel units
+// ---------------------------------------------------------------------------------------------------------------
+template <int V> struct Vec;
+template <> struct Vec<4> {
+  float v[4];
+  __device__ static Vec load(const float* p) { float4 t = ldg4(p); return Vec{{t.x, t.y, t.z, t.w}}; }
+  __device__ void store(float* p) const { stg4(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <> struct Vec<1> {
+  float v[1];
+  __device__ static Vec load(const float* p) { return Vec{{__ldg(p)}}; }
+  __device__ void store(float* p) const { *p = v[0]; }
+};
+
+constexpr int kRedThreads = 256;
+
+// Per-channel reduction of K quantities over the rows of one batch group.  `f(row, unit, acc)` adds the
+// contributions of one V-wide channel unit of one row into acc[K][V] (doubles).
+template <int V, int K, class F>
+__device__ void channel_reduce(int64_t row_begin, int64_t row_end, int C, double* out /*[K][C]*/, F f) {
+  const int U = C / V;
+  const int lanes = kRedThreads / U;       // >= 1 (checked on the host)
+  const int unit = threadIdx.x % U;
+  const int lane = threadIdx.x / U;
+  double acc[K][V];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[k][j] = 0.0;
+  if (lane < lanes) {
+    for (int64_t r = row_begin + (int64_t)blockIdx.x * lanes + lane; r < row_end; r += (int64_t)gridDim.x * lanes)
+      f(r, unit, acc);
+  }
+  // sum over lanes in shared memory, one (k, j) slice at a time to bound the footprint at 2 KB
+  __shared__ double slice[kRedThreads];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      slice[threadIdx.x] = (lane < lanes) ? acc[k][j] : 0.0;
+      __syncthreads();
+      if (threadIdx.x < U) {
+        double s = 0.0;
+        for (int l = 0; l < lanes; ++l) s += slice[l * U + threadIdx.x];
+        atomicAdd(&out[(size_t)k * C + threadIdx.x * V + j], s);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BatchNorm statistics
+// ---------------------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(const float* __restrict__ x, int64_t rows_per_group,
+                                                               int C, double* __restrict__ sums) {
+  const int g = blockIdx.y;
+  const int64_t r0 = (int64_t)g * rows_per_group;
+  channel_reduce<V, 2>(r0, r0 + rows_per_group, C, sums + (size_t)g * 2 * C,
+                       [&](int64_t r, int unit, double (*acc)[V]) {
+                         Vec<V> t = Vec<V>::load(x + r * C + unit * V);
+#pragma unroll
+                         for (int j = 0; j < V; ++j) { acc[0][j] += t.v[j]; acc[1][j] += (double)t.v[j] * t.v[j]; }
+                       });
+}
+
+template <int V>
+__global__ void __launch_bounds__(kRedThreads) pool2_stats_kernel(const float* __restrict__ x, int H, int W, int C,
+                                                                  int64_t rows_per_group, float* __restrict__ y,
+                                                                  double* __restrict__ sums) {
+  const int g = blockIdx.y;
+  const int OH = H / 2, OW = W / 2;
+  const int64_t r0 = (int64_t)g * rows_per_group;
+  channel_reduce<V, 2>(r0, r0 + rows_per_group, C, sums + (size_t)g * 2 * C,
+                       [&](int64_t r, int unit, double (*acc)[V]) {
+                         int ow = (int)(r % OW);
+                         int64_t t = r / OW;
+                         int oh = (int)(t % OH);
+                         int64_t n = t / OH;
+                         const float* p = x + ((n * H + 2 * oh) * W + 2 * ow) * C + unit * V;
+                         Vec<V> a = Vec<V>::load(p), b = Vec<V>::load(p + C);
+                         Vec<V> c = Vec<V>::load(p + (int64_t)W * C), d = Vec<V>::load(p + (int64_t)W * C + C);
+                         Vec<V> o;
+#pragma unroll
+                         for (int j = 0; j < V; ++j) {
+                           o.v[j] = (a.v[j] + b.v[j] + c.v[j] + d.v[j]) * 0.25f;
+                           acc[0][j] += o.v[j];
+                           acc[1][j] += (double)o.v[j] * o.v[j];
+                         }
+                         o.store(y + r * C + unit * V);
+                       });
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int groups, int C, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* __restrict__ mean,
+                                   float* __restrict__ invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+  for (int g = 0; g < groups; ++g) {
+    double s = sums[((size_t)g * 2 + 0) * C + c], ss = sums[((size_t)g * 2 + 1) * C + c];
+    double m = s / count;
+    double var = ss / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[(size_t)g * C + c] = (float)m;
+    invstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * (float)m;
+    rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
+}
+
+__global__ void bn_eval_prepare_kernel(const float* rm, const float* rv, int C, float eps, float* mean, float* invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  invstd[c] = 1.f / sqrtf(rv[c] + eps);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, int64_t M, int64_t rows_per_group,
+                                                       int C, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, const float* __restrict__ weight,
+                                                       const float* __restrict__ bias, const float* __restrict__ residual,
+                                                       int act, float slope, float* __restrict__ y) {
+  const int U = C / V;
+  const int64_t total = M * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / U;
+    int c = (int)(i % U) * V;
+    int g = (int)(r / rows_per_group);
+    Vec<V> t = Vec<V>::load(x + r * C + c), o;
+    Vec<V> res;
+    if (residual) res = Vec<V>::load(residual + r * C + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float w = weight ? __ldg(weight + c + j) : 1.f, b = bias ? __ldg(bias + c + j) : 0.f;
+      float v = (t.v[j] - __ldg(mean + (size_t)g * C + c + j)) * __ldg(invstd + (size_t)g * C + c + j) * w + b;
+      if (residual) v += res.v[j];
+      o.v[j] = act_fwd(v, act, slope);
+    }
+    o.store(y + r * C + c);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                                    const float* __restrict__ x, int64_t rows_per_group,
+                                                                    int C, const float* __restrict__ mean,
+                                                                    const float* __restrict__ invstd, int act, float slope,
+                                                                    double* __restrict__ sums2) {
+  const int g = blockIdx.y;
+  const int64_t r0 = (int64_t)g * rows_per_group;
+  channel_reduce<V, 2>(r0, r0 + rows_per_group, C, sums2 + (size_t)g * 2 * C,
+                       [&](int64_t r, int unit, double (*acc)[V]) {
+                         int c = unit * V;
+                         Vec<V> d = Vec<V>::load(dy + r * C + c), xv = Vec<V>::load(x + r * C + c), yv;
+                         if (act != PVG_ACT_NONE) yv = Vec<V>::load(y + r * C + c);
+#pragma unroll
+                         for (int j = 0; j < V; ++j) {
+                           float gg = d.v[j] * (act != PVG_ACT_NONE ? act_bwd_from_out(yv.v[j], act, slope) : 1.f);
+                           float xhat = (xv.v[j] - __ldg(mean + (size_t)g * C + c + j)) * __ldg(invstd + (size_t)g * C + c + j);
+                           acc[0][j] += gg;
+                           acc[1][j] += (double)gg * xhat;
+                         }
+                       });
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                           const float* __restrict__ x, int64_t M, int64_t rows_per_group,
+                                                           int OH, int OW, int C, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ weight,
+                                                           int act, float slope, const double* __restrict__ sums2, int eval,
+                                                           int unpool, float* __restrict__ dx, float* __restrict__ g_out) {
+  const int U = C / V;
+  const int64_t total = M * U;
+  const double inv_count = 1.0 / (double)rows_per_group;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / U;
+    int c = (int)(i % U) * V;
+    int g = (int)(r / rows_per_group);
+    Vec<V> d = Vec<V>::load(dy + r * C + c), xv = Vec<V>::load(x + r * C + c), yv, o, go;
+    if (act != PVG_ACT_NONE) yv = Vec<V>::load(y + r * C + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float gg = d.v[j] * (act != PVG_ACT_NONE ? act_bwd_from_out(yv.v[j], act, slope) : 1.f);
+      go.v[j] = gg;
+      float is = __ldg(invstd + (size_t)g * C + c + j);
+      float w = weight ? __ldg(weight + c + j) : 1.f;
+      float val;
+      if (eval) {
+        val = w * is * gg;
+      } else {
+        float xhat = (xv.v[j] - __ldg(mean + (size_t)g * C + c + j)) * is;
+        float sg = (float)(sums2[((size_t)g * 2 + 0) * C + c + j] * inv_count);
+        float sgx = (float)(sums2[((size_t)g * 2 + 1) * C + c + j] * inv_count);
+        val = w * is * (gg - sg - xhat * sgx);
+      }
+      o.v[j] = val;
+    }
+    if (g_out) go.store(g_out + r * C + c);
+    if (!unpool) {
+      o.store(dx + r * C + c);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] *= 0.25f;
+      int ow = (int)(r % OW);
+      int64_t t = r / OW;
+      int oh = (int)(t % OH);
+      int64_t n = t / OH;
+      const int W = OW * 2, H = OH * 2;
+      float* p = dx + ((n * H + 2 * oh) * W + 2 * ow) * C + c;
+      o.store(p); o.store(p + C); o.store(p + (int64_t)W * C); o.store(p + (int64_t)W * C + C);
+    }
+  }
+}
+
+__global__ void bn_bwd_params_kernel(const double* sums2, int groups, int C, float* dweight, float* dbias) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int g = 0; g < groups; ++g) { sg += sums2[((size_t)g * 2 + 0) * C + c]; sgx += sums2[((size_t)g * 2 + 1) * C + c]; }
+  if (dweight) dweight[c] = (float)sgx;
+  if (dbias) dbias[c] = (float)sg;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// resampling
+// ---------------------------------------------------------------------------------------------------------------
+struct Lerp { int i0, i1; float l; };
+// PyTorch area_pixel_compute_source_index(align_corners=False) + clamp to 0, as used by upsample_bilinear2d
+__device__ __forceinline__ Lerp src_index(int dst, float scale, int in_size) {
+  float s = scale * (dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  int i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  Lerp r;
+  r.i0 = i0;
+  r.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  r.l = s - (float)i0;
+  return r;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                                              float* __restrict__ y, int OH, int OW, float sh, float sw) {
+  const int U = C / V;
+  const int64_t total = (int64_t)N * OH * OW * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % U) * V;
+    int64_t r = i / U;
+    int ox = (int)(r % OW); r /= OW;
+    int oy = (int)(r % OH);
+    int64_t n = r / OH;
+    Lerp ly = src_index(oy, sh, H), lx = src_index(ox, sw, W);
+    const float* b = x + n * H * W * C + c;
+    Vec<V> v00 = Vec<V>::load(b + ((int64_t)ly.i0 * W + lx.i0) * C), v01 = Vec<V>::load(b + ((int64_t)ly.i0 * W + lx.i1) * C);
+    Vec<V> v10 = Vec<V>::load(b + ((int64_t)ly.i1 * W + lx.i0) * C), v11 = Vec<V>::load(b + ((int64_t)ly.i1 * W + lx.i1) * C);
+    Vec<V> o;
+    float w0y = 1.f - ly.l, w1y = ly.l, w0x = 1.f - lx.l, w1x = lx.l;
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      o.v[j] = w0y * (w0x * v00.v[j] + w1x * v01.v[j]) + w1y * (w0x * v10.v[j] + w1x * v11.v[j]);
+    o.store(y + i * V);
+  }
+}
+
+// gradient of the x2 bilinear upsample: gather form (each input pixel visits the <= 4x4 outputs that read it)
+template <int V>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float* __restrict__ dy, int N, int H, int W, int C,
+                                                             float* __restrict__ dx) {
+  const int U = C / V;
+  const int OH = 2 * H, OW = 2 * W;
+  const int64_t total = (int64_t)N * H * W * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % U) * V;
+    int64_t r = i / U;
+    int ix = (int)(r % W); r /= W;
+    int iy = (int)(r % H);
+    int64_t n = r / H;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int oy = 2 * iy - 1; oy <= 2 * iy + 2; ++oy) {
+      if (oy < 0 || oy >= OH) continue;
+      Lerp ly = src_index(oy, 0.5f, H);
+      float wy = (ly.i0 == iy ? 1.f - ly.l : 0.f) + (ly.i1 == iy ? ly.l : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = 2 * ix - 1; ox <= 2 * ix + 2; ++ox) {
+        if (ox < 0 || ox >= OW) continue;
+        Lerp lx = src_index(ox, 0.5f, W);
+        float wx = (lx.i0 == ix ? 1.f - lx.l : 0.f) + (lx.i1 == ix ? lx.l : 0.f);
+        if (wx == 0.f) continue;
+        Vec<V> d = Vec<V>::load(dy + ((n * OH + oy) * OW + ox) * C + c);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += wy * wx * d.v[j];
+      }
+    }
+    Vec<V> o;
+#pragma unroll
+    for (int j = 0; j < V; ++j) o.v[j] = acc[j];
+    o.store(dx + i * V);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                                           float* __restrict__ y) {
+  const int U = C / V, OH = H / 2, OW = W / 2;
+  const int64_t total = (int64_t)N * OH * OW * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % U) * V;
+    int64_t r = i / U;
+    int ox = (int)(r % OW); r /= OW;
+    int oy = (int)(r % OH);
+    int64_t n = r / OH;
+    const float* p = x + ((n * H + 2 * oy) * W + 2 * ox) * C + c;
+    Vec<V> a = Vec<V>::load(p), b = Vec<V>::load(p + C), cc = Vec<V>::load(p + (int64_t)W * C), d = Vec<V>::load(p + (int64_t)W * C + C), o;
+#pragma unroll
+    for (int j = 0; j < V; ++j) o.v[j] = fmaxf(fmaxf(a.v[j], b.v[j]), fmaxf(cc.v[j], d.v[j]));
+    o.store(y + i * V);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ y, int N, int H, int W, int C,
+                                                           int relu_mask, float* __restrict__ dx) {
+  const int U = C / V, OH = H / 2, OW = W / 2;
+  const int64_t total = (int64_t)N * OH * OW * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % U) * V;
+    int64_t r = i / U;
+    int ox = (int)(r % OW); r /= OW;
+    int oy = (int)(r % OH);
+    int64_t n = r / OH;
+    int64_t base = ((n * H + 2 * oy) * W + 2 * ox) * C + c;
+    int64_t off[4] = {0, C, (int64_t)W * C, (int64_t)W * C + C};
+    Vec<V> m = Vec<V>::load(y + i * V), d = Vec<V>::load(dy + i * V);
+    Vec<V> in[4], out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) in[k] = Vec<V>::load(x + base + off[k]);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      bool taken = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bool hit = !taken && in[k].v[j] == m.v[j];
+        taken = taken || hit;
+        float gval = hit ? d.v[j] : 0.f;
+        if (relu_mask && !(in[k].v[j] > 0.f)) gval = 0.f;
+        out[k].v[j] = gval;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k].store(dx + base + off[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ConvLSTM cell point-wise part
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+template <int V>
+__global__ void __launch_bounds__(256) lstm_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                       int64_t M, int C, float* __restrict__ c_new, float* __restrict__ h_new) {
+  const int U = C / V;
+  const int64_t total = M * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / U;
+    int c = (int)(i % U) * V;
+    const float* gp = gates + r * 4 * C + c;
+    Vec<V> gi = Vec<V>::load(gp), gf = Vec<V>::load(gp + C), go = Vec<V>::load(gp + 2 * C), gc = Vec<V>::load(gp + 3 * C);
+    Vec<V> cp = Vec<V>::load(c_prev + r * C + c), cn, hn;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float ii = sigmoidf_(gi.v[j]), ff = sigmoidf_(gf.v[j]), oo = sigmoidf_(go.v[j]), cc = tanhf(gc.v[j]);
+      cn.v[j] = ff * cp.v[j] + ii * cc;
+      hn.v[j] = oo * tanhf(cn.v[j]);
+    }
+    cn.store(c_new + r * C + c);
+    hn.store(h_new + r * C + c);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                       const float* __restrict__ c_new, const float* __restrict__ dh,
+                                                       const float* __restrict__ dc_new, int64_t M, int C,
+                                                       float* __restrict__ dgates, float* __restrict__ dc_prev) {
+  const int U = C / V;
+  const int64_t total = M * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / U;
+    int c = (int)(i % U) * V;
+    const float* gp = gates + r * 4 * C + c;
+    Vec<V> gi = Vec<V>::load(gp), gf = Vec<V>::load(gp + C), go = Vec<V>::load(gp + 2 * C), gc = Vec<V>::load(gp + 3 * C);
+    Vec<V> cp = Vec<V>::load(c_prev + r * C + c), cn = Vec<V>::load(c_new + r * C + c);
+    Vec<V> dhv, dcn, di, df, dog, dg, dcp;
+    if (dh) dhv = Vec<V>::load(dh + r * C + c);
+    if (dc_new) dcn = Vec<V>::load(dc_new + r * C + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float ii = sigmoidf_(gi.v[j]), ff = sigmoidf_(gf.v[j]), oo = sigmoidf_(go.v[j]), cc = tanhf(gc.v[j]);
+      float tc = tanhf(cn.v[j]);
+      float dhj = dh ? dhv.v[j] : 0.f;
+      float dc = (dc_new ? dcn.v[j] : 0.f) + dhj * oo * (1.f - tc * tc);
+      dog.v[j] = dhj * tc * oo * (1.f - oo);
+      di.v[j] = dc * cc * ii * (1.f - ii);
+      df.v[j] = dc * cp.v[j] * ff * (1.f - ff);
+      dg.v[j] = dc * ii * (1.f - cc * cc);
+      dcp.v[j] = dc * ff;
+    }
+    float* dp = dgates + r * 4 * C + c;
+    di.store(dp); df.store(dp + C); dog.store(dp + 2 * C); dg.store(dp + 3 * C);
+    dcp.store(dc_prev + r * C + c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// L1-type reductions
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absdiff_mean_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               int64_t count, double* __restrict__ out) {
+  const int n = blockIdx.y;
+  const float* pa = a + (int64_t)n * count;
+  const float* pb = b + (int64_t)n * count;
+  double acc = 0.0;
+  const bool vec = (count % 4 == 0) && ((((uintptr_t)pa | (uintptr_t)pb) & 15) == 0);
+  if (vec) {
+    int64_t q = count / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 x = ldg4(pa + 4 * i), y = ldg4(pb + 4 * i);
+      float s = fabsf(x.x - y.x) + fabsf(x.y - y.y) + fabsf(x.z - y.z) + fabsf(x.w - y.w);
+      acc += s;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+      acc += fabsf(__ldg(pa + i) - __ldg(pb + i));
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out + n, red[0] / (double)count);
+}
+
+__global__ void __launch_bounds__(256) absdiff_mean_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               const float* __restrict__ gout, int64_t count,
+                                                               float* __restrict__ db) {
+  const int n = blockIdx.y;
+  const float g = __ldg(gout + n) / (float)count;
+  const float* pa = a + (int64_t)n * count;
+  const float* pb = b + (int64_t)n * count;
+  float* pd = db + (int64_t)n * count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = __ldg(pa + i) - __ldg(pb + i);
+    pd[i] = d > 0.f ? -g : (d < 0.f ? g : 0.f);      // d|a-b|/db = -sign(a-b)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------------------------------------------
+// hi != NULL: hi = rna_tf32(x), lo = x - hi (robust to any tensor-core input rounding).
+// hi == NULL: lo = x - trunc_tf32(x); valid when the tensor core truncates raw fp32 operands, x itself is then "hi".
+__device__ __forceinline__ float tf32_part(float v, bool rna) {
+  return rna ? tf32_hi(v) : __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                         float* __restrict__ lo, int64_t n) {
+  const bool rna = hi != nullptr;
+  int64_t q = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = ldg4(x + 4 * i);
+    float4 h = make_float4(tf32_part(v.x, rna), tf32_part(v.y, rna), tf32_part(v.z, rna), tf32_part(v.w, rna));
+    if (hi) stg4(hi + 4 * i, h);
+    stg4(lo + 4 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+  }
+  for (int64_t i = q * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float h = tf32_part(x[i], rna);
+    if (hi) hi[i] = h;
+    lo[i] = x[i] - h;
+  }
+}
+
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act,
+                                                      float slope, float* __restrict__ g, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    g[i] = __ldg(dy + i) * act_bwd_from_out(__ldg(y + i), act, slope);
+}
+
+template <int V>
+__global__ void __launch_bounds__(kRedThreads) channel_sum_kernel(const float* __restrict__ x, int64_t M, int C,
+                                                                  double* __restrict__ out) {
+  channel_reduce<V, 1>(0, M, C, out, [&](int64_t r, int unit, double (*acc)[V]) {
+    Vec<V> t = Vec<V>::load(x + r * C + unit * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[0][j] += t.v[j];
+  });
+}
+__global__ void cast_d2f_kernel(const double* in, float* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+// OIHW -> [Cout][R][S][CinP] (+lo) and [CinP][R][S][Cout] with flipped taps (+lo)
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S,
+                                                          int CinP, int round_hi, float* fwd_hi, float* fwd_lo,
+                                                          float* bwd_hi, float* bwd_lo) {
+  const int64_t total = (int64_t)Cout * R * S * CinP;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ci = (int)(i % CinP);
+    int64_t t = i / CinP;
+    int s = (int)(t % S); t /= S;
+    int r = (int)(t % R);
+    int co = (int)(t / R);
+    float v = ci < Cin ? __ldg(w + (((int64_t)co * Cin + ci) * R + r) * S + s) : 0.f;
+    float hi = tf32_hi(v);
+    float h = round_hi ? hi : v;          // SIMT consumers want the full fp32 value, tensor-core consumers tf32(v)
+    if (fwd_hi) fwd_hi[i] = h;
+    if (fwd_lo) fwd_lo[i] = v - hi;
+    int64_t j = (((int64_t)ci * R + (R - 1 - r)) * S + (S - 1 - s)) * Cout + co;
+    if (bwd_hi) bwd_hi[j] = h;
+    if (bwd_lo) bwd_lo[j] = v - hi;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                   float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * grad_scale + wd * pi;
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace pvg
+
+using namespace pvg;
+
+#define DISPATCH_V(C, ...)                     \
+  if ((C) % 4 == 0) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; }
+
+static int red_grid_x(int64_t rows, int lanes, int groups) {
+  int64_t want = ceil_div64(rows, (int64_t)lanes * 16);
+  int64_t cap = (int64_t)kSMs * 4 / (groups > 0 ? groups : 1);
+  if (cap < 1) cap = 1;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+extern "C" {
+
+const char* pvg_last_error(void) { return pvg::g_last_error.c_str(); }
+int pvg_version(void) { return 100; }
+
+int pvg_has_umma(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+int pvg_bn_stats(const float* x, int N, int HW, int C, int groups, double* sums, void* stream) {
+  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  int U = (C % 4 == 0) ? C / 4 : C;
+  PVG_CHECK_ARG(U >= 1 && U <= kRedThreads, "unsupported channel count");
+  int64_t rpg = (int64_t)(N / groups) * HW;
+  dim3 grid(red_grid_x(rpg, kRedThreads / U, groups), groups);
+  DISPATCH_V(C, (bn_stats_kernel<V><<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(x, rpg, C, sums)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_pool2_stats(const float* x, int N, int H, int W, int C, float* y, int groups, double* sums, void* stream) {
+  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  PVG_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "avg_pool2d(2) needs even H, W");
+  int U = (C % 4 == 0) ? C / 4 : C;
+  PVG_CHECK_ARG(U >= 1 && U <= kRedThreads, "unsupported channel count");
+  int64_t rpg = (int64_t)(N / groups) * (H / 2) * (W / 2);
+  dim3 grid(red_grid_x(rpg, kRedThreads / U, groups), groups);
+  DISPATCH_V(C, (pool2_stats_kernel<V><<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(x, H, W, C, rpg, y, sums)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_bn_finalize(const double* sums, int64_t count, int groups, int C, float eps, float momentum, float* running_mean,
+                    float* running_var, float* mean, float* invstd, void* stream) {
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)count, groups, C, eps, momentum,
+                                                                         running_mean, running_var, mean, invstd);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_bn_eval_prepare(const float* running_mean, const float* running_var, int C, float eps, float* mean, float* invstd,
+                        void* stream) {
+  bn_eval_prepare_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, C, eps, mean, invstd);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_bn_apply(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
+                 const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
+                 void* stream) {
+  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
+  DISPATCH_V(C, (bn_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+                    x, M, rpg, C, mean, invstd, weight, bias, residual, act, slope, y)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, int HW, int C, int groups, const float* mean,
+                      const float* invstd, int act, float slope, double* sums2, void* stream) {
+  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  int U = (C % 4 == 0) ? C / 4 : C;
+  PVG_CHECK_ARG(U >= 1 && U <= kRedThreads, "unsupported channel count");
+  int64_t rpg = (int64_t)(N / groups) * HW;
+  dim3 grid(red_grid_x(rpg, kRedThreads / U, groups), groups);
+  DISPATCH_V(C, (bn_bwd_reduce_kernel<V><<<grid, kRedThreads, 0, (cudaStream_t)stream>>>(dy, y, x, rpg, C, mean, invstd, act,
+                                                                                         slope, sums2)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
+                     const float* mean, const float* invstd, const float* weight, int act, float slope, const double* sums2,
+                     int eval, int unpool, float* dx, float* g_out, void* stream) {
+  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  int OH = unpool ? H / 2 : H, OW = unpool ? W / 2 : W;
+  int64_t M = (int64_t)N * OH * OW, rpg = (int64_t)(N / groups) * OH * OW;
+  DISPATCH_V(C, (bn_bwd_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+                    dy, y, x, M, rpg, OH, OW, C, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_bn_bwd_params(const double* sums2, int groups, int C, float* dweight, float* dbias, void* stream) {
+  bn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums2, groups, C, dweight, dbias);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_upsample2x_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream) {
+  return pvg_resize_bilinear(x, N, H, W, C, y, 2 * H, 2 * W, stream);
+}
+
+int pvg_upsample2x_bwd(const float* dy, int N, int H, int W, int C, float* dx, void* stream) {
+  int64_t total = (int64_t)N * H * W * C;
+  DISPATCH_V(C, (upsample2x_bwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(dy, N, H, W, C, dx)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_resize_bilinear(const float* x, int N, int H, int W, int C, float* y, int OH, int OW, void* stream) {
+  int64_t total = (int64_t)N * OH * OW * C;
+  float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
+  DISPATCH_V(C, (resize_bilinear_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y, OH,
+                                                                                                    OW, sh, sw)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream) {
+  PVG_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "max_pool2d(2) needs even H, W");
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
+  DISPATCH_V(C, (maxpool2_fwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_maxpool2_bwd(const float* dy, const float* x, const float* y, int N, int H, int W, int C, int relu_mask, float* dx,
+                     void* stream) {
+  PVG_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "max_pool2d(2) needs even H, W");
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
+  DISPATCH_V(C, (maxpool2_bwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, y, N, H, W, C,
+                                                                                                 relu_mask, dx)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_lstm_fwd(const float* gates, const float* c_prev, int64_t M, int C, float* c_new, float* h_new, void* stream) {
+  DISPATCH_V(C, (lstm_fwd_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, M, C, c_new,
+                                                                                               h_new)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_lstm_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc_new, int64_t M,
+                 int C, float* dgates, float* dc_prev, void* stream) {
+  DISPATCH_V(C, (lstm_bwd_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, dh,
+                                                                                               dc_new, M, C, dgates, dc_prev)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_absdiff_mean_fwd(const float* a, const float* b, int N, int64_t count, double* out, void* stream) {
+  int gx = (int)ceil_div64(count, 256 * 16);
+  int cap = kSMs * 8 / (N > 0 ? N : 1);
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  absdiff_mean_fwd_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(a, b, count, out);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_absdiff_mean_bwd(const float* a, const float* b, const float* gout, int N, int64_t count, float* db, void* stream) {
+  int gx = (int)ceil_div64(count, 256 * 8);
+  int cap = kSMs * 8 / (N > 0 ? N : 1);
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  absdiff_mean_bwd_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(a, b, gout, count, db);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  PVG_CHECK_ARG((((uintptr_t)x | (uintptr_t)lo | (uintptr_t)hi) & 15) == 0, "pointers must be 16-byte aligned");
+  split_tf32_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_act_bwd(const float* dy, const float* y, int act, float slope, float* g, int64_t n, void* stream) {
+  act_bwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, n);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* out, void* stream) {
+  int U = (C % 4 == 0) ? C / 4 : C;
+  PVG_CHECK_ARG(U >= 1 && U <= kRedThreads, "unsupported channel count");
+  PVG_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * C, (cudaStream_t)stream));
+  int gx = red_grid_x(M, kRedThreads / U, 1);
+  DISPATCH_V(C, (channel_sum_kernel<V><<<gx, kRedThreads, 0, (cudaStream_t)stream>>>(x, M, C, scratch)));
+  PVG_LAUNCH_OK();
+  cast_d2f_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(scratch, out, C);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinP, int round_hi, float* fwd_hi,
+                         float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream) {
+  PVG_CHECK_ARG(CinP >= Cin, "CinP < Cin");
+  int64_t total = (int64_t)Cout * R * S * CinP;
+  pack_weight_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, R, S, CinP, round_hi, fwd_hi,
+                                                                          fwd_lo, bwd_hi, bwd_lo);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float grad_scale, void* stream) {
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                                bc2_sqrt, grad_scale);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,507 @@
+"""torch.autograd.Function wrappers over the C ABI (include/pvg_b200.h).
+
+Tensors are logical NCHW with *channels_last* strides, i.e. physically NHWC fp32 - the layout every kernel uses - so
+the reference's NCHW-indexed glue (slicing, stacking, the 20-tuple the trainer unpacks) keeps working unchanged.
+PyTorch is used for storage, streams and the autograd tape only; every op below launches hand-written sm_100a
+kernels and raises if the extension is missing or the tensor is not on a CUDA device (no CPU / eager fallback).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ALGO_SIMT, ALGO_UMMA, ConvDesc, call
+
+Tensor = torch.Tensor
+
+# ---------------------------------------------------------------------------------------------------------------
+# precision mode of the tensor-core convolutions
+#   "tf32x3": error-compensated 3xTF32, fp32-equivalent (default: meets the loss <= 1e-5 rel parity tolerance)
+#   "tf32"  : one TF32 product (what cuDNN does by default for the reference on Ampere+ GPUs)
+#   "fp32"  : force the CUDA-core fp32 path everywhere (debug / cross-check)
+# ---------------------------------------------------------------------------------------------------------------
+_precision = "tf32x3"
+_tf32_truncates: Optional[bool] = None     # does tcgen05 kind::tf32 truncate raw fp32 operands? (probed lazily)
+
+
+def set_precision(mode: str) -> None:
+    global _precision
+    if mode not in ("tf32x3", "tf32", "fp32"):
+        raise ValueError(f"unknown precision mode {mode!r}")
+    _precision = mode
+
+
+def get_precision() -> str:
+    return _precision
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check_cuda(t: Tensor) -> None:
+    if not t.is_cuda:
+        raise _lib.PvgError("pvg_b200 ops run on CUDA tensors only (no CPU fallback exists for the CADDY hot path)")
+    if t.dtype != torch.float32:
+        raise _lib.PvgError(f"pvg_b200 ops take float32 tensors, got {t.dtype}")
+
+
+def nhwc_strides(shape: Sequence[int]) -> Tuple[int, int, int, int]:
+    n, c, h, w = shape
+    return (h * w * c, 1, w * c, c)
+
+
+def empty_nhwc(shape: Sequence[int], device, zero: bool = False) -> Tensor:
+    t = torch.empty_strided(tuple(shape), nhwc_strides(shape), dtype=torch.float32, device=device)
+    return t.zero_() if zero else t
+
+
+def nhwc(x: Tensor) -> Tensor:
+    """Returns x itself when it already is physically NHWC-dense, else a packed copy."""
+    _check_cuda(x)
+    want = nhwc_strides(x.shape)
+    ok = all(s == w or d == 1 for s, w, d in zip(x.stride(), want, x.shape))
+    if ok:
+        return x
+    out = empty_nhwc(x.shape, x.device)
+    out.copy_(x)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------------------------
+weights_epoch = 0      # bumped by optimisers that update parameters through raw pointers (no autograd version bump)
+
+
+def invalidate_weight_cache() -> None:
+    global weights_epoch
+    weights_epoch += 1
+
+
+def _get_packs(weight: Tensor, cin_p: int, round_hi: bool) -> Tensor:
+    """Packed (+tf32-split) copies of a conv weight: rows 0/1 = forward hi/lo [Cout][R][S][CinP], rows 2/3 = data-gradient
+    hi/lo [CinP][R][S][Cout] (flipped taps).  Cached ON the tensor object (so a recycled allocation can never alias a
+    stale pack) and rebuilt when the tensor's autograd version or the global weights epoch moves."""
+    cache = getattr(weight, "_pvg_packs", None)
+    if cache is None:
+        cache = {}
+        try:
+            weight._pvg_packs = cache
+        except Exception:
+            pass
+    key = (cin_p, round_hi)
+    hit = cache.get(key)
+    ver = (weight._version, weights_epoch)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    cout, cin, r, s = weight.shape
+    w = weight.detach().contiguous()
+    bufs = torch.empty((4, cout * r * s * cin_p), dtype=torch.float32, device=weight.device)
+    call("pvg_pack_conv_weight", w.data_ptr(), cout, cin, r, s, cin_p, 1 if round_hi else 0,
+         bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), _stream())
+    cache[key] = (ver, bufs)
+    return bufs
+
+
+def _conv_algo(cin_phys: int) -> Tuple[int, int]:
+    """(algo, nprod) for a conv whose A operand has cin_phys physical channels."""
+    if _precision == "fp32" or cin_phys % 32 != 0:
+        return ALGO_SIMT, 1
+    return ALGO_UMMA, (3 if _precision == "tf32x3" else 1)
+
+
+def tf32_truncates() -> bool:
+    """Probes (once) whether tcgen05 kind::tf32 truncates or rounds raw fp32 operands: one conv on crafted inputs."""
+    global _tf32_truncates
+    if _tf32_truncates is None:
+        dev = torch.device("cuda")
+        x = empty_nhwc((1, 32, 8, 16), dev, zero=True)
+        x[0, 0, 0, 0] = 1.0 + 2.0 ** -11 + 2.0 ** -13           # trunc -> 1.0 ; round-to-nearest -> 1 + 2^-10
+        w = torch.zeros((16, 32, 1, 1), device=dev)
+        w[0, 0, 0, 0] = 1.0
+        packs = _get_packs(w, 32, True)
+        y = empty_nhwc((1, 16, 8, 16), dev)
+        _run_conv(x, None, packs[0], None, None, y, 1, 0, ACT_NONE, 0.0, ALGO_UMMA, 1)
+        v = float(y[0, 0, 0, 0])
+        if v == 1.0:
+            _tf32_truncates = True
+        elif v == 1.0 + 2.0 ** -10:
+            _tf32_truncates = False
+        else:
+            raise _lib.PvgError(f"tf32 probe returned {v!r}: the tensor-core conv path is broken")
+    return _tf32_truncates
+
+
+conv_profile = None     # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per tensor-core conv launch
+
+
+def _run_conv(x, x_lo, w, w_lo, bias, y, ksize, pad, act, slope, algo, nprod, alg_flops=0.0):
+    n, cin, h, wd = x.shape
+    d = ConvDesc(n, h, wd, cin, y.shape[1], ksize, ksize, pad, act, float(slope), algo, nprod)
+    prof = conv_profile is not None and algo == ALGO_UMMA
+    if prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    call("pvg_conv2d_fwd", d, x.data_ptr(), _p(x_lo), w.data_ptr(), _p(w_lo), _p(bias), y.data_ptr(), _stream())
+    if prof:
+        e1.record()
+        conv_profile.append((e0, e1, alg_flops))
+
+
+def _split(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """(hi, lo) operands of the 3xTF32 product for an activation tensor."""
+    lo = torch.empty_like(x)
+    if tf32_truncates():
+        call("pvg_split_tf32", x.data_ptr(), None, lo.data_ptr(), x.numel(), _stream())
+        return x, lo
+    hi = torch.empty_like(x)
+    call("pvg_split_tf32", x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
+    return hi, lo
+
+
+def _conv_forward(x: Tensor, packs: Tensor, which: int, cout: int, ksize: int, bias, act: int, slope: float,
+                  algo: int, nprod: int, alg_flops: float = 0.0) -> Tensor:
+    n, cin, h, w = x.shape
+    y = empty_nhwc((n, cout, h, w), x.device)
+    if algo == ALGO_UMMA and nprod == 3:
+        hi, lo = _split(x)
+        _run_conv(hi, lo, packs[which], packs[which + 1], bias, y, ksize, (ksize - 1) // 2, act, slope, algo, nprod, alg_flops)
+    else:
+        _run_conv(x, None, packs[which], None, bias, y, ksize, (ksize - 1) // 2, act, slope, algo, nprod, alg_flops)
+    return y
+
+
+class Conv2dFn(torch.autograd.Function):
+    """nn.Conv2d(stride 1, 'same' padding) (+ bias) (+ activation) - reference call sites listed in pvg_b200.h.
+    ``weight`` is the reference's OIHW parameter; its input-channel count may be smaller than x's physical channel
+    count (zero-padded concat buffers)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, slope):
+        x = nhwc(x)
+        _check_cuda(weight)
+        cout, cin_log, r, s = weight.shape
+        cin_p = x.shape[1]
+        if cin_log > cin_p or r != s:
+            raise _lib.PvgError(f"conv weight {tuple(weight.shape)} does not fit input with {cin_p} channels")
+        algo, nprod = _conv_algo(cin_p)
+        packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
+        b = bias.detach().contiguous() if bias is not None else None
+        flops = 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * cout * r * s * cin_log
+        y = _conv_forward(x, packs, 0, cout, r, b, act, slope, algo, nprod, flops)
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.meta = (act, slope, bias is not None, cin_log)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        act, slope, has_bias, cin_log = ctx.meta
+        cout, _, r, s = weight.shape
+        n, cin_p, h, w = x.shape
+        dy = nhwc(dy)
+        if act != ACT_NONE:
+            g = torch.empty_like(dy)
+            call("pvg_act_bwd", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), dy.numel(), _stream())
+        else:
+            g = dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            algo, nprod = _conv_algo(cout)
+            packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
+            # data gradient = "same" convolution of g with the tap-flipped, transposed pack [CinP][R][S][Cout]
+            dx = _conv_forward(g, packs, 2, cin_p, r, None, ACT_NONE, 0.0, algo, nprod, 2.0 * n * h * w * cout * r * s * cin_log)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+            d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, 1)
+            call("pvg_conv2d_wgrad", d, cin_log, x.data_ptr(), g.data_ptr(), dw.data_ptr(), _stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty((cout,), dtype=torch.float32, device=dy.device)
+            scratch = torch.empty((cout,), dtype=torch.float64, device=dy.device)
+            call("pvg_channel_sum", g.data_ptr(), n * h * w, cout, scratch.data_ptr(), db.data_ptr(), _stream())
+        return dx, dw, db, None, None
+
+
+def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0) -> Tensor:
+    return Conv2dFn.apply(x, weight, bias, act, slope)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# [avg_pool2d(2)] -> BatchNorm2d -> (+ residual) -> activation
+# ---------------------------------------------------------------------------------------------------------------
+class PoolBNActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, pool, act, slope, eps, momentum,
+                groups):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        dev = x.device
+        st = _stream()
+        if residual is not None:
+            residual = nhwc(residual)
+        oh, ow = (h // 2, w // 2) if pool else (h, w)
+        mean = torch.empty((groups, c), dtype=torch.float32, device=dev)
+        invstd = torch.empty((groups, c), dtype=torch.float32, device=dev)
+        sums = torch.zeros((groups, 2, c), dtype=torch.float64, device=dev) if (training or pool) else None
+        if pool:
+            xp = empty_nhwc((n, c, oh, ow), dev)
+            call("pvg_pool2_stats", x.data_ptr(), n, h, w, c, xp.data_ptr(), groups, sums.data_ptr(), st)
+        else:
+            xp = x
+            if training:
+                call("pvg_bn_stats", x.data_ptr(), n, h * w, c, groups, sums.data_ptr(), st)
+        if training:
+            call("pvg_bn_finalize", sums.data_ptr(), (n // groups) * oh * ow, groups, c, float(eps), float(momentum),
+                 _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), st)
+        else:
+            if groups != 1:
+                raise _lib.PvgError("grouped statistics only exist in training mode")
+            call("pvg_bn_eval_prepare", running_mean.data_ptr(), running_var.data_ptr(), c, float(eps), mean.data_ptr(),
+                 invstd.data_ptr(), st)
+        y = empty_nhwc((n, c, oh, ow), dev)
+        wd = weight.detach() if weight is not None else None
+        bd = bias.detach() if bias is not None else None
+        call("pvg_bn_apply", xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(), invstd.data_ptr(), _p(wd), _p(bd),
+             _p(residual), act, float(slope), y.data_ptr(), st)
+        ctx.save_for_backward(xp, weight, mean, invstd, y if act != ACT_NONE else None)
+        ctx.meta = (training, pool, act, slope, groups, residual is not None, (n, c, h, w))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, weight, mean, invstd, y = ctx.saved_tensors
+        training, pool, act, slope, groups, has_res, (n, c, h, w) = ctx.meta
+        dy = nhwc(dy)
+        dev = dy.device
+        st = _stream()
+        oh, ow = (h // 2, w // 2) if pool else (h, w)
+        sums2 = torch.zeros((groups, 2, c), dtype=torch.float64, device=dev)
+        need_params = weight is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        if training or need_params:
+            call("pvg_bn_bwd_reduce", dy.data_ptr(), _p(y), xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(),
+                 invstd.data_ptr(), act, float(slope), sums2.data_ptr(), st)
+        dx = empty_nhwc((n, c, h, w), dev) if ctx.needs_input_grad[0] else None
+        g_out = empty_nhwc((n, c, oh, ow), dev) if (has_res and ctx.needs_input_grad[3]) else None
+        if dx is not None or g_out is not None:
+            if dx is None:        # only the residual gradient is wanted
+                dx_buf = empty_nhwc((n, c, h, w), dev)
+            else:
+                dx_buf = dx
+            call("pvg_bn_bwd_apply", dy.data_ptr(), _p(y), xp.data_ptr(), n, h, w, c, groups, mean.data_ptr(),
+                 invstd.data_ptr(), _p(weight.detach() if weight is not None else None), act, float(slope),
+                 sums2.data_ptr(), 0 if training else 1, 1 if pool else 0, dx_buf.data_ptr(), _p(g_out), st)
+        dweight = dbias = None
+        if need_params:
+            dweight = torch.empty((c,), dtype=torch.float32, device=dev)
+            dbias = torch.empty((c,), dtype=torch.float32, device=dev)
+            call("pvg_bn_bwd_params", sums2.data_ptr(), groups, c, dweight.data_ptr(), dbias.data_ptr(), st)
+        return (dx, dweight, dbias, g_out) + (None,) * 9
+
+
+def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, groups=1):
+    """``bn`` is an nn.BatchNorm2d used purely as the parameter/buffer container (reference state_dict names)."""
+    training = bn.training
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(groups)
+    return PoolBNActFn.apply(x, bn.weight, bias_or_none(bn), residual, bn.running_mean, bn.running_var, training, pool, act,
+                             slope, bn.eps, bn.momentum if bn.momentum is not None else 0.1, groups)
+
+
+def bias_or_none(m):
+    return getattr(m, "bias", None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# resampling
+# ---------------------------------------------------------------------------------------------------------------
+class Upsample2xFn(torch.autograd.Function):
+    """F.interpolate(scale_factor=2, mode='bilinear', align_corners=False), model/layers/up_block.py:35,43."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc((n, c, 2 * h, 2 * w), x.device)
+        call("pvg_upsample2x_fwd", x.data_ptr(), n, h, w, c, y.data_ptr(), _stream())
+        ctx.shape = (n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w = ctx.shape
+        dy = nhwc(dy)
+        dx = empty_nhwc((n, c, h, w), dy.device)
+        call("pvg_upsample2x_bwd", dy.data_ptr(), n, h, w, c, dx.data_ptr(), _stream())
+        return dx
+
+
+def upsample2x(x: Tensor) -> Tensor:
+    return Upsample2xFn.apply(x)
+
+
+def resize_bilinear(x: Tensor, size: Tuple[int, int]) -> Tensor:
+    """F.interpolate(x, size, mode='bilinear') of a tensor that needs no gradient (ground truth, losses.py:92,450)."""
+    x = nhwc(x.detach())
+    n, c, h, w = x.shape
+    y = empty_nhwc((n, c, size[0], size[1]), x.device)
+    call("pvg_resize_bilinear", x.data_ptr(), n, h, w, c, y.data_ptr(), size[0], size[1], _stream())
+    return y
+
+
+class MaxPool2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(2, 2) of torchvision VGG19 (model/layers/vgg.py:16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc((n, c, h // 2, w // 2), x.device)
+        call("pvg_maxpool2_fwd", x.data_ptr(), n, h, w, c, y.data_ptr(), _stream())
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = nhwc(dy)
+        dx = empty_nhwc((n, c, h, w), dy.device)
+        if (h % 2) or (w % 2):
+            dx.zero_()
+        call("pvg_maxpool2_bwd", dy.data_ptr(), x.data_ptr(), y.data_ptr(), n, h, w, c, 0, dx.data_ptr(), _stream())
+        return dx
+
+
+def maxpool2(x: Tensor) -> Tensor:
+    return MaxPool2Fn.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ConvLSTM cell (point-wise part) and the channel concat that feeds the gate convolution
+# ---------------------------------------------------------------------------------------------------------------
+class LSTMCellFn(torch.autograd.Function):
+    """convolutional_lstm_cell.py:92-101 given the 4C gate pre-activations (order input, forget, output, cell)."""
+
+    @staticmethod
+    def forward(ctx, gates, c_prev):
+        gates, c_prev = nhwc(gates), nhwc(c_prev)
+        n, c, h, w = c_prev.shape
+        c_new, h_new = empty_nhwc((n, c, h, w), gates.device), empty_nhwc((n, c, h, w), gates.device)
+        call("pvg_lstm_fwd", gates.data_ptr(), c_prev.data_ptr(), n * h * w, c, c_new.data_ptr(), h_new.data_ptr(), _stream())
+        ctx.save_for_backward(gates, c_prev, c_new)
+        return h_new, c_new
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        gates, c_prev, c_new = ctx.saved_tensors
+        n, c, h, w = c_prev.shape
+        dh = nhwc(dh) if dh is not None else None
+        dc = nhwc(dc) if dc is not None else None
+        dgates, dc_prev = torch.empty_like(gates), torch.empty_like(c_prev)
+        call("pvg_lstm_bwd", gates.data_ptr(), c_prev.data_ptr(), c_new.data_ptr(), _p(dh), _p(dc), n * h * w, c,
+             dgates.data_ptr(), dc_prev.data_ptr(), _stream())
+        return dgates, dc_prev
+
+
+def lstm_cell(gates: Tensor, c_prev: Tensor) -> Tuple[Tensor, Tensor]:
+    return LSTMCellFn.apply(gates, c_prev)
+
+
+class ConcatPadFn(torch.autograd.Function):
+    """Channel concat of 4-D maps and 2-D (N, C) vectors broadcast over H x W (conv_dynamics_network.py:64-109,
+    convolutional_lstm_cell.py:35-75), zero-padded to ``c_pad`` physical channels so the result is a legal
+    tensor-core A operand (K chunks of 32 channels)."""
+
+    @staticmethod
+    def forward(ctx, c_pad, *parts):
+        ref = next(p for p in parts if p.dim() == 4)
+        n, _, h, w = ref.shape
+        out = empty_nhwc((n, c_pad, h, w), ref.device)
+        off = 0
+        spans = []
+        for p in parts:
+            c = p.shape[1]
+            if p.dim() == 4:
+                out[:, off:off + c].copy_(p)
+            else:
+                out[:, off:off + c].copy_(p.detach()[:, :, None, None].expand(n, c, h, w))
+            spans.append((off, c, p.dim()))
+            off += c
+        if off > c_pad:
+            raise _lib.PvgError("concat wider than its padded size")
+        if off < c_pad:
+            out[:, off:].zero_()
+        ctx.spans = spans
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = []
+        for i, (off, c, dim) in enumerate(ctx.spans):
+            if not ctx.needs_input_grad[i + 1]:
+                grads.append(None)
+            elif dim == 4:
+                grads.append(dout[:, off:off + c])
+            else:
+                grads.append(dout[:, off:off + c].sum(dim=(2, 3)))
+        return (None,) + tuple(grads)
+
+
+def concat_pad(parts: Sequence[Tensor], multiple: int = 32) -> Tensor:
+    total = sum(p.shape[1] for p in parts)
+    c_pad = (total + multiple - 1) // multiple * multiple
+    return ConcatPadFn.apply(c_pad, *parts)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------------------
+class AbsDiffMeanFn(torch.autograd.Function):
+    """out[n] = mean |a[n] - b[n]| over everything but the first dim; gradient flows to ``b`` only
+    (a = detached ground-truth branch, losses.py:465 / nn.L1Loss at :118)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _check_cuda(a); _check_cuda(b)
+        if a.shape != b.shape:
+            raise _lib.PvgError(f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+        if a.dim() == 4:
+            a, b = nhwc(a), nhwc(b)           # same physical order on both sides; the mean is order independent
+        else:
+            a, b = a.contiguous(), b.contiguous()
+        n = a.shape[0]
+        count = a.numel() // n
+        out = torch.zeros((n,), dtype=torch.float64, device=a.device)
+        call("pvg_absdiff_mean_fwd", a.data_ptr(), b.data_ptr(), n, count, out.data_ptr(), _stream())
+        ctx.save_for_backward(a, b)
+        return out.float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        n = a.shape[0]
+        db = torch.empty_like(b)
+        g = gout.contiguous().float()
+        call("pvg_absdiff_mean_bwd", a.data_ptr(), b.data_ptr(), g.data_ptr(), n, a.numel() // n, db.data_ptr(), _stream())
+        return None, db
+
+
+def absdiff_mean(a: Tensor, b: Tensor) -> Tensor:
+    return AbsDiffMeanFn.apply(a.detach(), b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optimiser
+# ---------------------------------------------------------------------------------------------------------------
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+              eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    """In-place torch.optim.Adam update (L2-style weight decay) over flat fp32 buffers."""
+    call("pvg_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1),
+         float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())

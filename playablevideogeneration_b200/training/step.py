@@ -1,0 +1,192 @@
+"""One optimiser step of CADDY training on the pvg_b200 kernels: forward + every loss + backward + gradient
+all-reduce + Adam.  Mirrors ``Trainer.compute_losses`` / ``compute_losses_pretraining`` and the step at
+training/trainer.py:241-550,584-587 (same loss weights, same float64 accumulators, same ``loss_info`` keys for the
+quantities on the hot path) - with the trainer's ~50 per-scalar ``.item()`` host syncs replaced by ONE packed
+device->host copy, and all parameters / gradients / Adam moments living in flat arenas so that the optimiser is one
+kernel launch and data parallelism is one NCCL all-reduce per step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..vgg import Vgg19
+from . import losses as L
+
+
+class FlatArena:
+    """Moves every trainable parameter of ``module`` into one flat fp32 buffer (and its gradient into another)."""
+
+    ALIGN = 64
+
+    def __init__(self, module: nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        dev = self.params[0].device
+        self.flat = torch.zeros((total,), dtype=torch.float32, device=dev)
+        self.grad = torch.zeros((total,), dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                self.flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + p.numel()].view(p.shape)
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        self.offsets = offs
+        self.sizes = [(p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN for p in self.params]
+        # torch.optim.Adam skips parameters whose .grad is None (never reached by backward) and keeps a per-parameter
+        # step count; post-accumulate hooks record which parameters each backward reached.
+        self.touched = set()
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self.touched.add(i))
+        self.steps = [0] * len(self.params)
+
+    def zero_grad(self):
+        self.touched.clear()
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):          # re-attach (autograd may have replaced .grad objects)
+            g = self.grad[o:o + p.numel()].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g
+
+
+class TrainStep:
+    def __init__(self, config: dict, model: nn.Module, vgg: Optional[Vgg19] = None, process_group=None):
+        self.config = config
+        self.model = model
+        self.module = model.module if hasattr(model, "module") else model
+        tr = config["training"]
+        dev = next(self.module.parameters()).device
+        self.vgg = (vgg if vgg is not None else Vgg19()).to(dev)
+        self.perceptual_loss = L.ParallelPerceptualLoss(self.vgg)
+        self.observations_loss = L.ObservationsLoss()
+        self.states_loss = L.StatesLoss()
+        self.hidden_states_loss = L.HiddenStatesLoss()
+        self.entropy_loss = L.EntropyLogitLoss()
+        self.action_state_distribution_kl = L.KLGeneralGaussianDivergenceLoss()
+        self.action_directions_kl_gaussian_divergence_loss = L.KLGaussianDivergenceLoss()
+        if "smooth" in tr.get("trainer", ""):
+            self.mutual_information_loss = L.SmoothMutualInformationLoss(config).to(dev)
+        else:
+            self.mutual_information_loss = L.MutualInformationLoss()
+        self.mi_lambda = tr.get("action_mutual_information_entropy_lambda", 1.0)
+        self.arena = FlatArena(self.module)
+        self.exp_avg = torch.zeros_like(self.arena.flat)
+        self.exp_avg_sq = torch.zeros_like(self.arena.flat)
+        self.lr = tr["learning_rate"]
+        self.weight_decay = tr["weight_decay"]
+        self.lr_schedule = list(tr.get("lr_schedule", []))
+        self.lr_gamma = tr.get("lr_gamma", 1.0)
+        self.global_step = 0
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+
+    # ----------------------------------------------------------------------------------------------------------
+    def current_lr(self) -> float:
+        n = sum(1 for m in self.lr_schedule if self.global_step >= m)
+        return self.lr * (self.lr_gamma ** n)
+
+    def compute_losses(self, batch_tuple, ground_truth_observations_count: int, gumbel_temperature: float,
+                       pretraining: bool = False):
+        """-> (total_loss (1,) float64, loss_info {name: 0-dim tensor}, model results)."""
+        cfg = self.config
+        lw = cfg["training"]["loss_weights"]
+        sfx = "_pretraining" if pretraining else ""
+        observations = batch_tuple[0]
+        t = observations.shape[1]
+        if ground_truth_observations_count >= t:
+            ground_truth_observations_count = t - 1
+        if pretraining:
+            results = self.model(batch_tuple, pretraining=True, gumbel_temperature=gumbel_temperature)
+            (rec, pyr, rec_states, states, rec_hidden, hidden, selected, logits, samples, attention, dir_dist, sampled_dirs,
+             state_dist, sampled_states, variations, r_logits, r_dir_dist, r_sdirs, r_state_dist, r_sstates) = results
+        else:
+            results = self.model(batch_tuple, ground_truth_observations_count, gumbel_temperature=gumbel_temperature)
+            (rec, pyr, rec_states, states, hidden, selected, logits, samples, attention, rec_att, dir_dist, sampled_dirs,
+             state_dist, sampled_states, variations, r_logits, r_dir_dist, r_sdirs, r_state_dist, r_sstates) = results
+        dev = observations.device
+        perceptual = torch.zeros((1,), dtype=torch.float64, device=dev)
+        perceptual_term = torch.zeros((1,), dtype=torch.float64, device=dev)
+        rec_loss = torch.zeros((1,), dtype=torch.float64, device=dev)
+        info: Dict[str, torch.Tensor] = {}
+        lam_p = lw["perceptual_loss_lambda" + sfx]
+        for r, cur in enumerate(pyr):
+            p_tot, p_levels = self.perceptual_loss(observations, cur)
+            term = p_levels[0] * 0.0
+            for lv in p_levels:
+                term = term + lv * lam_p
+            o = self.observations_loss(observations, cur)
+            perceptual = perceptual + p_tot
+            perceptual_term = perceptual_term + term
+            rec_loss = rec_loss + o
+            info[f"perceptual_loss_r{r}"] = p_tot.detach()
+            info[f"observations_rec_loss_r{r}"] = o.detach()
+            for li, lv in enumerate(p_levels):
+                info[f"perceptual_loss_r{r}_l{li}"] = lv.detach()
+        n = len(pyr)
+        perceptual, perceptual_term, rec_loss = perceptual / n, perceptual_term / n, rec_loss / n
+        states_rec = self.states_loss(states.detach(), rec_states)
+        entropy = self.entropy_loss(logits)
+        kl_dir = self.action_directions_kl_gaussian_divergence_loss(dir_dist)
+        mi = self.mutual_information_loss(torch.softmax(logits, dim=-1), torch.softmax(r_logits, dim=-1), lamb=self.mi_lambda)
+        kl_state = self.action_state_distribution_kl(r_state_dist, state_dist.detach())
+        total = (lw["reconstruction_loss_lambda" + sfx] * rec_loss + perceptual_term
+                 + lw["states_rec_lambda" + sfx] * states_rec + lw["entropy_lambda" + sfx] * entropy
+                 + lw["action_directions_kl_lambda" + sfx] * kl_dir
+                 + lw["action_mutual_information_lambda" + sfx] * mi
+                 + lw["action_state_distribution_kl_lambda" + sfx] * kl_state)
+        if pretraining:
+            hid_rec = self.hidden_states_loss(hidden, rec_hidden.detach())
+            total = total + lw["hidden_states_rec_lambda_pretraining"] * hid_rec
+            info["hidden_states_rec_loss"] = hid_rec.detach()
+        info.update({
+            "avg_observations_rec_loss": rec_loss.detach()[0], "avg_perceptual_loss": perceptual.detach()[0],
+            "loss_component_perceptual_loss": perceptual_term.detach()[0], "states_rec_loss": states_rec.detach(),
+            "entropy_loss": entropy.detach(), "action_directions_kl_loss": kl_dir.detach(),
+            "action_mutual_information_loss": mi.detach(), "action_state_distribution_kl_loss": kl_state.detach(),
+            "total_loss": total.detach()[0]})
+        return total, info, results
+
+    @staticmethod
+    def fetch_info(info: Dict[str, torch.Tensor]) -> Dict[str, float]:
+        """ONE device->host copy for all logged scalars (the reference issues one .item() sync per scalar)."""
+        keys = list(info)
+        packed = torch.stack([info[k].reshape(()).double() for k in keys]).cpu()
+        return {k: float(v) for k, v in zip(keys, packed)}
+
+    def optimizer_step(self):
+        if self.pg is not None and self.world > 1:
+            torch.distributed.all_reduce(self.arena.grad, group=self.pg)       # one NCCL all-reduce over NVLink / NVSwitch
+        self.global_step += 1
+        a = self.arena
+        lr = self.current_lr()
+        # one launch per run of consecutive parameters that (a) received a gradient and (b) share a step count
+        # (in steady state: one or two launches for the whole model)
+        i, n = 0, len(a.params)
+        while i < n:
+            if i not in a.touched:
+                i += 1
+                continue
+            j = i
+            while j + 1 < n and (j + 1) in a.touched and a.steps[j + 1] == a.steps[i]:
+                j += 1
+            lo, hi = a.offsets[i], a.offsets[j] + a.sizes[j]
+            for k in range(i, j + 1):
+                a.steps[k] += 1
+            ops.adam_step(a.flat[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], a.steps[i], lr,
+                          weight_decay=self.weight_decay, grad_scale=1.0 / self.world)
+            i = j + 1
+        ops.invalidate_weight_cache()
+
+    def step(self, batch_tuple, ground_truth_observations_count: int, gumbel_temperature: float, pretraining: bool = False):
+        self.module.train()
+        total, info, _ = self.compute_losses(batch_tuple, ground_truth_observations_count, gumbel_temperature, pretraining)
+        self.arena.zero_grad()
+        total.backward()
+        self.optimizer_step()
+        return total.detach(), info

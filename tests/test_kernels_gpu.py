@@ -1,0 +1,295 @@
+"""Kernel-level parity (GPU): every C-ABI op against the same op in plain PyTorch fp32 on the CPU (what the oracle is
+built from).  Tolerances are written next to each check.  Runs on the B200 box: ``pytest -m gpu``."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from playablevideogeneration_b200 import ops
+    return ops
+
+
+def _log(name, **kw):
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "kernel_errors.jsonl"), "a") as f:
+            f.write(json.dumps(dict(name=name, **kw)) + "\n")
+    except Exception:
+        pass
+
+
+def _err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float()
+    return float((got - ref).abs().max()), float(ref.abs().max())
+
+
+def _close(name, got, ref, rel, abs_=0.0):
+    e, scale = _err(got, ref)
+    _log(name, max_abs_err=e, ref_absmax=scale, tol=rel * scale + abs_)
+    assert e <= rel * scale + abs_, f"{name}: max abs err {e:.3e} > {rel:g} * {scale:.3e} + {abs_:g}"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+# -----------------------------------------------------------------------------------------------------------------
+CONV_SIMT_SHAPES = [  # N, Cin, Cout, H, W, k, bias
+    (2, 3, 16, 20, 20, 3, False), (1, 12, 16, 12, 36, 3, False), (2, 16, 32, 16, 16, 1, False),
+    (2, 16, 16, 10, 14, 3, True), (1, 3, 64, 32, 32, 3, True), (2, 20, 3, 16, 16, 7, True)]
+
+
+@pytest.mark.parametrize("shape", CONV_SIMT_SHAPES)
+def test_conv_simt_forward(shape):
+    ops = _ops()
+    n, cin, cout, h, w, k, has_bias = shape
+    x, wt = _rand(n, cin, h, w, seed=1), _rand(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5)
+    b = _rand(cout, seed=3) if has_bias else None
+    ref = F.conv2d(x, wt, b, padding=k // 2)
+    ops.set_precision("fp32")
+    try:
+        got = ops.conv2d(x.to(DEV), wt.to(DEV), b.to(DEV) if has_bias else None)
+    finally:
+        ops.set_precision("tf32x3")
+    _close(f"conv_simt{shape}", got, ref, 2e-6, 1e-6)      # fp32 FMA chains of <= 1k terms, different summation order
+
+
+CONV_UMMA_SHAPES = [  # N, Cin_logical, Cin_physical, Cout, H, W, k, bias, act
+    (2, 32, 32, 64, 16, 16, 3, False, 0), (1, 64, 64, 65, 32, 32, 3, False, 0), (2, 128, 128, 128, 32, 32, 3, False, 0),
+    (2, 201, 224, 512, 8, 8, 3, True, 0), (3, 64, 64, 128, 12, 20, 1, False, 0), (1, 32, 32, 3, 64, 64, 7, True, 3),
+    (2, 64, 64, 64, 26, 20, 3, True, 2), (1, 128, 128, 3, 16, 16, 3, True, 3), (8, 256, 256, 256, 4, 4, 3, False, 0),
+    (1, 64, 64, 64, 128, 128, 3, True, 2), (2, 521, 544, 1024, 16, 16, 3, True, 0)]
+
+
+def _conv_case(shape, seed=0):
+    n, cin, cinp, cout, h, w, k, has_bias, act = shape
+    x = _rand(n, cinp, h, w, seed=seed + 1)
+    x[:, cin:] = 0
+    wt = _rand(cout, cin, k, k, seed=seed + 2, scale=(cin * k * k) ** -0.5)
+    b = _rand(cout, seed=seed + 3) if has_bias else None
+    ref = F.conv2d(x[:, :cin], wt, b, padding=k // 2)
+    if act == 2:
+        ref = F.relu(ref)
+    elif act == 3:
+        ref = torch.tanh(ref)
+    return x, wt, b, ref
+
+
+def test_tf32_probe_reports_rounding_mode():
+    ops = _ops()
+    trunc = ops.tf32_truncates()
+    _log("tf32_probe", truncates=bool(trunc))
+    assert trunc in (True, False)
+
+
+@pytest.mark.parametrize("shape", CONV_UMMA_SHAPES)
+def test_conv_umma_forward_tf32x3(shape):
+    """3xTF32 error-compensated tensor-core conv vs fp32 CPU: fp32-equivalent (tolerance 1e-5 of the output scale)."""
+    ops = _ops()
+    x, wt, b, ref = _conv_case(shape)
+    ops.set_precision("tf32x3")
+    got = ops.conv2d(x.to(DEV), wt.to(DEV), b.to(DEV) if b is not None else None, act=shape[8])
+    _close(f"conv_umma3{shape}", got, ref, 1e-5, 1e-6)
+
+
+@pytest.mark.parametrize("shape", CONV_UMMA_SHAPES[:5])
+def test_conv_umma_forward_tf32(shape):
+    """single TF32 product: 10-bit mantissa operands -> 2e-3 of the output scale."""
+    ops = _ops()
+    x, wt, b, ref = _conv_case(shape)
+    ops.set_precision("tf32")
+    try:
+        got = ops.conv2d(x.to(DEV), wt.to(DEV), b.to(DEV) if b is not None else None, act=shape[8])
+    finally:
+        ops.set_precision("tf32x3")
+    _close(f"conv_umma1{shape}", got, ref, 2e-3, 1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 16, 16, 3, True, 0), (2, 201, 224, 512, 8, 8, 3, True, 0),
+                                   (2, 3, 3, 16, 16, 16, 3, False, 0), (1, 64, 64, 65, 16, 16, 1, False, 0),
+                                   (2, 32, 32, 3, 16, 16, 7, True, 3), (2, 137, 160, 256, 16, 16, 3, False, 0)])
+def test_conv_backward(shape):
+    """dx (tensor-core dgrad with flipped packed weights or SIMT), dw (split-K wgrad), db vs torch autograd on CPU."""
+    ops = _ops()
+    n, cin, cinp, cout, h, w, k, has_bias, act = shape
+    x, wt, b, _ = _conv_case(shape, seed=10)
+    xr = x[:, :cin].clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if has_bias else None
+    ref = F.conv2d(xr, wr, br, padding=k // 2)
+    if act == 3:
+        ref = torch.tanh(ref)
+    gy = _rand(*ref.shape, seed=20)
+    ref.backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    wg = wt.to(DEV).requires_grad_(True)
+    bg = b.to(DEV).requires_grad_(True) if has_bias else None
+    out = ops.conv2d(xg, wg, bg, act=act)
+    out.backward(gy.to(DEV))
+    _close(f"conv_bwd_dx{shape}", xg.grad[:, :cin], xr.grad, 1e-5, 1e-6)
+    _close(f"conv_bwd_dw{shape}", wg.grad, wr.grad, 2e-5, 1e-6)
+    if has_bias:
+        _close(f"conv_bwd_db{shape}", bg.grad, br.grad, 1e-5, 1e-6)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [dict(c=16, pool=True, res=False, train=True, groups=1),
+                                 dict(c=65, pool=False, res=True, train=True, groups=1),
+                                 dict(c=128, pool=False, res=False, train=True, groups=3),
+                                 dict(c=64, pool=True, res=False, train=False, groups=1),
+                                 dict(c=256, pool=False, res=True, train=False, groups=1)])
+def test_pool_bn_act(cfg):
+    ops = _ops()
+    c, pool, use_res, train, groups = cfg["c"], cfg["pool"], cfg["res"], cfg["train"], cfg["groups"]
+    n, h, w = 6, 8, 12
+    x = _rand(n, c, h, w, seed=1).requires_grad_(True)
+    oh, ow = (h // 2, w // 2) if pool else (h, w)
+    res = _rand(n, c, oh, ow, seed=2).requires_grad_(True) if use_res else None
+    bn_ref = torch.nn.BatchNorm2d(c)
+    with torch.no_grad():
+        bn_ref.weight.copy_(1 + 0.1 * _rand(c, seed=3)); bn_ref.bias.copy_(0.1 * _rand(c, seed=4))
+        bn_ref.running_mean.copy_(0.1 * _rand(c, seed=5)); bn_ref.running_var.copy_(1 + 0.2 * torch.rand(c))
+    import copy
+    bn_gpu = copy.deepcopy(bn_ref).to(DEV)
+    bn_ref.train(train); bn_gpu.train(train)
+    xp = F.avg_pool2d(x, 2) if pool else x
+    outs = []
+    for g in range(groups):                       # reference semantics: one BatchNorm call per group, in order
+        sl = slice(g * n // groups, (g + 1) * n // groups)
+        outs.append(bn_ref(xp[sl]))
+    y = torch.cat(outs, 0)
+    if use_res:
+        y = y + res
+    ref = F.leaky_relu(y, 0.2)
+    gy = _rand(*ref.shape, seed=6)
+    ref.backward(gy)
+    xg = x.detach().to(DEV).requires_grad_(True)
+    rg = res.detach().to(DEV).requires_grad_(True) if use_res else None
+    got = ops.pool_bn_act(xg, bn_gpu, residual=rg, pool=pool, act=ops.ACT_LRELU, slope=0.2, groups=groups)
+    got.backward(gy.to(DEV))
+    tag = str(cfg)
+    _close("bn_fwd" + tag, got, ref, 2e-6, 2e-6)
+    _close("bn_dx" + tag, xg.grad, x.grad, 1e-5, 1e-6)
+    if use_res:
+        _close("bn_dres" + tag, rg.grad, res.grad, 1e-6, 1e-7)
+    _close("bn_dw" + tag, bn_gpu.weight.grad, bn_ref.weight.grad, 1e-5, 1e-5)
+    _close("bn_db" + tag, bn_gpu.bias.grad, bn_ref.bias.grad, 1e-5, 1e-5)
+    _close("bn_rm" + tag, bn_gpu.running_mean, bn_ref.running_mean, 1e-5, 1e-6)
+    _close("bn_rv" + tag, bn_gpu.running_var, bn_ref.running_var, 1e-5, 1e-6)
+    assert int(bn_gpu.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 5, 7), (1, 65, 8, 8), (3, 128, 16, 4)])
+def test_upsample2x(shape):
+    ops = _ops()
+    x = _rand(*shape, seed=1).requires_grad_(True)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear")
+    gy = _rand(*ref.shape, seed=2)
+    ref.backward(gy)
+    xg = x.detach().to(DEV).requires_grad_(True)
+    got = ops.upsample2x(xg)
+    got.backward(gy.to(DEV))
+    _close(f"up2x_fwd{shape}", got, ref, 1e-6, 1e-7)
+    _close(f"up2x_bwd{shape}", xg.grad, x.grad, 2e-6, 1e-7)
+
+
+@pytest.mark.parametrize("case", [((2, 3, 64, 64), (32, 32)), ((2, 3, 64, 64), (16, 16)), ((1, 3, 96, 64), (24, 16)),
+                                  ((1, 3, 30, 50), (17, 23))])
+def test_resize_bilinear(case):
+    ops = _ops()
+    shape, size = case
+    x = _rand(*shape, seed=1)
+    _close(f"resize{case}", ops.resize_bilinear(x.to(DEV), size), F.interpolate(x, size, mode="bilinear"), 1e-6, 1e-7)
+
+
+def test_maxpool2():
+    ops = _ops()
+    x = F.relu(_rand(2, 64, 12, 20, seed=1)).requires_grad_(True)      # many exact zeros -> ties, like VGG
+    ref = F.max_pool2d(x, 2)
+    gy = _rand(*ref.shape, seed=2)
+    ref.backward(gy)
+    xg = x.detach().to(DEV).requires_grad_(True)
+    got = ops.maxpool2(xg)
+    got.backward(gy.to(DEV))
+    _close("maxpool_fwd", got, ref, 0.0, 0.0)
+    nz = (x.detach() > 0)
+    _close("maxpool_bwd_nonzero", xg.grad.cpu() * nz, x.grad * nz, 0.0, 0.0)   # ties at 0 are killed by relu' anyway
+
+
+def test_lstm_cell():
+    ops = _ops()
+    n, c, h, w = 2, 32, 6, 5
+    gates = _rand(n, 4 * c, h, w, seed=1).requires_grad_(True)
+    cprev = _rand(n, c, h, w, seed=2).requires_grad_(True)
+    i, f, o, g = gates.chunk(4, dim=1)
+    cn = torch.sigmoid(f) * cprev + torch.sigmoid(i) * torch.tanh(g)
+    hn = torch.sigmoid(o) * torch.tanh(cn)
+    gh, gc = _rand(n, c, h, w, seed=3), _rand(n, c, h, w, seed=4)
+    (hn * gh + cn * gc).sum().backward()
+    gg = gates.detach().to(DEV).requires_grad_(True)
+    cg = cprev.detach().to(DEV).requires_grad_(True)
+    h2, c2 = ops.lstm_cell(gg, cg)
+    (h2 * gh.to(DEV) + c2 * gc.to(DEV)).sum().backward()
+    _close("lstm_h", h2, hn, 2e-6, 1e-6)
+    _close("lstm_c", c2, cn, 2e-6, 1e-6)
+    _close("lstm_dgates", gg.grad, gates.grad, 1e-5, 1e-6)
+    _close("lstm_dc", cg.grad, cprev.grad, 1e-5, 1e-6)
+
+
+def test_concat_pad():
+    ops = _ops()
+    a, v, hdd = _rand(2, 64, 4, 6, seed=1).requires_grad_(True), _rand(2, 9, seed=2).requires_grad_(True), _rand(2, 128, 4, 6, seed=3).requires_grad_(True)
+    ref = torch.cat([a, v[:, :, None, None].expand(-1, -1, 4, 6), hdd], dim=1)
+    gy = _rand(2, 224, 4, 6, seed=4)
+    (ref * gy[:, :201]).sum().backward()
+    ag, vg, hg = (t.detach().to(DEV).requires_grad_(True) for t in (a, v, hdd))
+    got = ops.concat_pad([ag, vg, hg])
+    assert got.shape == (2, 224, 4, 6) and float(got[:, 201:].abs().max()) == 0.0
+    (got * gy.to(DEV)).sum().backward()
+    _close("concat_fwd", got[:, :201], ref, 0.0, 0.0)
+    _close("concat_dv", vg.grad, v.grad, 1e-6, 1e-6)
+    _close("concat_da", ag.grad, a.grad, 0.0, 0.0)
+
+
+def test_absdiff_mean():
+    ops = _ops()
+    a, b = _rand(5, 64, 9, 7, seed=1), _rand(5, 64, 9, 7, seed=2).requires_grad_(True)
+    ref = (a - b).abs().mean(dim=[1, 2, 3])
+    gw = _rand(5, seed=3)
+    (ref * gw).sum().backward()
+    bg = b.detach().to(DEV).requires_grad_(True)
+    got = ops.absdiff_mean(a.to(DEV), bg)
+    (got * gw.to(DEV)).sum().backward()
+    _close("absdiff_fwd", got, ref, 1e-6, 0.0)
+    _close("absdiff_bwd", bg.grad, b.grad, 1e-6, 1e-9)
+
+
+def test_adam_matches_torch():
+    ops = _ops()
+    p0, steps = _rand(1000, seed=1), 3
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=4e-4, weight_decay=1e-6)
+    p = p0.to(DEV); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for s in range(1, steps + 1):
+        g = _rand(1000, seed=10 + s)
+        p_ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g.to(DEV), m, v, s, 4e-4, weight_decay=1e-6)
+    _close("adam", p, p_ref, 1e-6, 1e-7)
+
+
+def test_ops_refuse_cpu_tensors():
+    ops = _ops()
+    from playablevideogeneration_b200._lib import PvgError
+    with pytest.raises(PvgError):
+        ops.conv2d(torch.zeros(1, 32, 8, 8), torch.zeros(16, 32, 3, 3))
