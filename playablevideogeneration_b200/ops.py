@@ -7,6 +7,7 @@ kernels and raises if the extension is missing or the tensor is not on a CUDA de
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -22,7 +23,7 @@ Tensor = torch.Tensor
 #   "tf32"  : one TF32 product (what cuDNN does by default for the reference on Ampere+ GPUs)
 #   "fp32"  : force the CUDA-core fp32 path everywhere (debug / cross-check)
 # ---------------------------------------------------------------------------------------------------------------
-_precision = "tf32x3"
+_precision = os.environ.get("PVG_PRECISION", "tf32x3")
 _tf32_truncates: Optional[bool] = None     # does tcgen05 kind::tf32 truncate raw fp32 operands? (probed lazily)
 
 

@@ -1,0 +1,33 @@
+#!/bin/bash
+# Runs on the GPU box under gpurun: staged so that a hang in one stage cannot hide the others.
+# usage: tools/gpu_round.sh [stages...]   (default: all)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+OUT=gpurun_out
+stages="${@:-info kernels probe umma convbwd model_fp32 model smoke bench_small bench}"
+run() { # name timeout cmd...
+  local name=$1 t=$2; shift 2
+  echo "=== $name ===" | tee -a $OUT/summary.txt
+  timeout $t "$@" > $OUT/$name.log 2>&1
+  local rc=$?
+  echo "$name rc=$rc" | tee -a $OUT/summary.txt
+  tail -n 15 $OUT/$name.log | tee -a $OUT/summary.txt
+}
+for s in $stages; do
+case $s in
+  info) run info 60 bash -c 'nvidia-smi; nproc; free -g | head -2; python -c "import torch;print(torch.__version__, torch.cuda.get_device_name(0))"' ;;
+  kernels) run kernels 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "not umma and not probe and not conv_backward" -p no:cacheprovider ;;
+  probe) run probe 120 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "probe" -p no:cacheprovider ;;
+  umma) run umma 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma" -p no:cacheprovider ;;
+  convbwd) run convbwd 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv_backward" -p no:cacheprovider ;;
+  model_fp32) PVG_PRECISION=fp32 run model_fp32 900 python -m pytest tests/test_model_gpu.py -q -m gpu -p no:cacheprovider ;;
+  model) run model 900 python -m pytest tests/test_model_gpu.py -q -m gpu -p no:cacheprovider ;;
+  smoke) run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
+  bench_small) run bench_small 600 python bench.py --workload bair64_b2_t4 --steps 3 --warmup 3 --no-cpu-baseline ;;
+  bench) run bench 600 python bench.py --steps 3 --warmup 3 ;;
+  bench_ref) run bench_ref 900 python bench.py --impl reference --steps 1 --warmup 0 ;;
+  ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline ;;
+esac
+done
+cp $OUT/summary.txt $OUT/summary_$(date +%s).txt 2>/dev/null
+true
