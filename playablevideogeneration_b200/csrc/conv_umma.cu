@@ -15,6 +15,12 @@
 //                  accumulator.
 //   epilogue       tcgen05.ld 32 lanes x 16 columns per warp-instruction -> +bias -> activation -> NHWC global stores
 //                  (each thread owns one output pixel and writes its channels contiguously).
+//   split accum    (NPROD=3) The tensor core adds into its fp32 accumulator with truncation, so an accumulation chain of L
+//                  MMAs drifts by ~L * 2^-24 (measured on B200: 2.3e-5 at K = 4.7k).  To stay fp32-equivalent the main
+//                  term A_hi*B_hi is accumulated in TMEM for only kDrain k-iterations (32 MMAs), then drained by the
+//                  epilogue warps into fp32 REGISTER accumulators (round-to-nearest adds) while the MMA warp continues
+//                  into a second TMEM buffer (ping-pong, tfull/tempty mbarriers).  The two correction terms, 2^-11
+//                  smaller, accumulate in a third TMEM buffer for the whole K loop and are added once at the end.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -45,6 +51,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -132,10 +141,14 @@ struct Cfg {
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr bool kSplitAcc = NPROD == 3;               // see "split accum" in the header comment
+  static constexpr int kDrain = 8;                            // k-iterations (x4 MMAs) per TMEM accumulation chain
+  static constexpr int kAccCols = kSplitAcc ? 3 * BN : BN;    // [main0 | main1 | correction] or [acc]
+  static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
 };
 
 struct ConvParams {
@@ -157,8 +170,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* stage_base = smem;
   uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStageBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* acc_bar = empty_bar + C::kStages;
-  uint32_t* tmem_slot = (uint32_t*)(acc_bar + 1);
+  uint64_t* tfull_bar = empty_bar + C::kStages;      // [2] accumulator buffer ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator buffer drained, MMA may overwrite it
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -176,7 +190,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     if (NPROD == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(acc_bar, 1);
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 128); mbar_init(&tempty_bar[1], 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -209,32 +224,59 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32<BN>();
       int stage = 0; uint32_t phase = 0;
-      uint32_t accumulate = 0;
-      for (int k = 0; k < k_iters; ++k) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
-        const uint32_t a_hi = st, a_lo = st + kABytes;
-        const uint32_t b_hi = st + C::kPlanes * kABytes, b_lo = b_hi + C::kBBytes;
-        if (NPROD == 3) {
+      if constexpr (C::kSplitAcc) {
+        const uint32_t corr = tmem_acc + 2 * BN;
+        uint32_t corr_acc = 0;
+        const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
+        int k = 0;
+        for (int per = 0; per < periods; ++per) {
+          const int b = per & 1;
+          mbar_wait(&tempty_bar[b], ((per >> 1) & 1) ^ 1);       // epilogue finished draining this buffer
+          tc_fence_after();
+          const uint32_t main_acc = tmem_acc + b * BN;
+          const int k_end = min(k + C::kDrain, k_iters);
+          uint32_t main_started = 0;
+          for (; k < k_end; ++k) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
+            const uint32_t a_hi = st, a_lo = st + kABytes;
+            const uint32_t b_hi = st + 2 * kABytes, b_lo = b_hi + C::kBBytes;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_tf32(corr, make_kmajor_sw128_desc(a_lo + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, corr_acc);
+              corr_acc = 1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(corr, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_lo + ks * 32), idesc, 1);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_tf32(main_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, main_started);
+              main_started = 1;
+            }
+            umma_commit(&empty_bar[stage]);     // slot reusable once these MMAs have read it
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[b]);           // this chain (and every earlier MMA, incl. corrections) is complete
+        }
+      } else {
+        uint32_t accumulate = 0;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
+          const uint32_t a_hi = st, b_hi = st + kABytes;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_lo + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, accumulate);
+            umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, accumulate);
             accumulate = 1;
           }
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_lo + ks * 32), idesc, 1);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, accumulate);
-          accumulate = 1;
-        }
-        umma_commit(&empty_bar[stage]);     // slot reusable once these MMAs have read it
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        umma_commit(&tfull_bar[0]);             // accumulator complete
       }
-      umma_commit(acc_bar);                 // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -246,27 +288,71 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ow = w0 + wi, oh = h0 + hi, on = n0 + ni;
     const bool valid = ow < p.W && oh < p.H && on < p.N;
     float* yrow = p.y + (((int64_t)on * p.H + oh) * p.W + ow) * p.Cout;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
     const bool vec_ok = (p.Cout % 4) == 0;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      const int co = co0 + c;
-      if (!valid || co >= p.Cout) continue;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if constexpr (C::kSplitAcc) {
+      float acc[BN];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float b = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
-        v[j] = act_fwd(v[j] + b, p.act, p.slope);
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
+      for (int per = 0; per < periods; ++per) {
+        const int b = per & 1;
+        mbar_wait(&tfull_bar[b], (per >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN; c += 16) {
+          float v[16];
+          tmem_ld16(tmem_acc + lane_base + (uint32_t)(b * BN + c), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c + j] += v[j];
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[b]);
       }
-      if (vec_ok && co + 16 <= p.Cout) {
+      // the last tfull commit also covers the correction MMAs
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-      } else {
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
+        const int co = co0 + c;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (co + j < p.Cout) yrow[co + j] = v[j];
+        for (int j = 0; j < 16; ++j) {
+          float bsv = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
+          v[j] = act_fwd(acc[c + j] + v[j] + bsv, p.act, p.slope);
+        }
+        if (valid && co < p.Cout) {
+          if (vec_ok && co + 16 <= p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (co + j < p.Cout) yrow[co + j] = v[j];
+          }
+        }
+      }
+    } else {
+      mbar_wait(&tfull_bar[0], 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_acc + lane_base + (uint32_t)c, v);
+        const int co = co0 + c;
+        if (!valid || co >= p.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float b = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
+          v[j] = act_fwd(v[j] + b, p.act, p.slope);
+        }
+        if (vec_ok && co + 16 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (co + j < p.Cout) yrow[co + j] = v[j];
+        }
       }
     }
   }
@@ -374,7 +460,9 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
   if (co <= 32) return launch_umma<32, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
   if (co <= 64) return launch_umma<64, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
   if (co <= 80) return launch_umma<80, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
-  if (NPROD == 1 && co % 256 == 0) return launch_umma<256, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if constexpr (NPROD == 1) {
+    if (co % 256 == 0) return launch_umma<256, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  }
   return launch_umma<128, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
 }
 

@@ -690,7 +690,7 @@ int pvg_resize_bilinear(const float* x, int N, int H, int W, int C, float* y, in
 }
 
 int pvg_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream) {
-  PVG_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "max_pool2d(2) needs even H, W");
+  PVG_CHECK_ARG(H >= 2 && W >= 2, "max_pool2d(2) needs H, W >= 2");     // odd sizes floor, like nn.MaxPool2d
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
   DISPATCH_V(C, (maxpool2_fwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y)));
   PVG_LAUNCH_OK();
@@ -699,7 +699,7 @@ int pvg_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* y, void*
 
 int pvg_maxpool2_bwd(const float* dy, const float* x, const float* y, int N, int H, int W, int C, int relu_mask, float* dx,
                      void* stream) {
-  PVG_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "max_pool2d(2) needs even H, W");
+  PVG_CHECK_ARG(H >= 2 && W >= 2, "max_pool2d(2) needs H, W >= 2");     // the caller zero-fills dx when H or W is odd
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
   DISPATCH_V(C, (maxpool2_bwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, y, N, H, W, C,
                                                                                                  relu_mask, dx)));

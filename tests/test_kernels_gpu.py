@@ -142,6 +142,18 @@ def test_conv_backward(shape):
         _close(f"conv_bwd_db{shape}", bg.grad, br.grad, 1e-5, 1e-6)
 
 
+@pytest.mark.parametrize("shape", [(2, 201, 224, 512, 8, 8, 3, True, 0), (2, 128, 128, 128, 16, 16, 3, False, 0),
+                                   (2, 64, 64, 3, 16, 16, 3, True, 3)])
+def test_conv_backward_fp32_simt(shape):
+    """same as above with every conv forced onto the CUDA-core fp32 path (the cross-check implementation)."""
+    ops = _ops()
+    ops.set_precision("fp32")
+    try:
+        test_conv_backward(shape)
+    finally:
+        ops.set_precision("tf32x3")
+
+
 # -----------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cfg", [dict(c=16, pool=True, res=False, train=True, groups=1),
                                  dict(c=65, pool=False, res=True, train=True, groups=1),

@@ -25,8 +25,11 @@ case $s in
   smoke) run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
   bench_small) run bench_small 600 python bench.py --workload bair64_b2_t4 --steps 3 --warmup 3 --no-cpu-baseline ;;
   bench) run bench 600 python bench.py --steps 3 --warmup 3 ;;
+  diag_fp32) run diag_fp32 600 python tools/grad_diag.py full_bair_feedback fp32 ;;
+  diag_tf32x3) run diag_tf32x3 600 python tools/grad_diag.py full_bair_feedback tf32x3 ;;
+  allkernels) run allkernels 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider ;;
   bench_ref) run bench_ref 900 python bench.py --impl reference --steps 1 --warmup 0 ;;
-  ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline ;;
+  ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline ;;
 esac
 done
 cp $OUT/summary.txt $OUT/summary_$(date +%s).txt 2>/dev/null
