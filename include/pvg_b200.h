@@ -66,6 +66,11 @@ int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, i
  * physical channels of which the first Cin are real.  dw must be zero-initialised by the caller. */
 int pvg_conv2d_wgrad(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* dy, float* dw_oihw,
                      void* stream);
+/* Tensor-core weight gradient (tcgen05, MN-major tf32 operands, split-K over pixel patches).  x: [N,H,W,d->Cin]
+ * (d->Cin % 32 == 0), g = dY: [N,H,W,d->Cout] (d->Cout % 4 == 0), *_lo their 3xTF32 residual planes (nprod == 3, else
+ * NULL).  scratch: float[Cout*R*S*Cin], zero-initialised by the caller.  dw_oihw[co][ci<Cin_logical][r][s] += result. */
+int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* x_lo, const float* g,
+                          const float* g_lo, float* scratch, float* dw_oihw, void* stream);
 /* out[c] = sum over M rows of x[M][C]  (bias gradient); scratch: double[C] */
 int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* out, void* stream);
 /* hi != NULL: hi = rna_tf32(x), lo = x - hi.  hi == NULL: lo = x - trunc_tf32(x) (x itself then serves as the hi

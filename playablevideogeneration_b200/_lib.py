@@ -25,6 +25,7 @@ _SIGNATURES = {
     "pvg_conv2d_fwd": [POINTER(ConvDesc), P, P, P, P, P, P, P],
     "pvg_pack_conv_weight": [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P],
     "pvg_conv2d_wgrad": [POINTER(ConvDesc), c_int, P, P, P, P],
+    "pvg_conv2d_wgrad_umma": [POINTER(ConvDesc), c_int, P, P, P, P, P, P, P],
     "pvg_channel_sum": [P, c_int64, c_int, P, P, P],
     "pvg_split_tf32": [P, P, P, c_int64, P],
     "pvg_act_bwd": [P, P, c_int, c_float, P, c_int64, P],

@@ -1,0 +1,294 @@
+// Weight gradient of the 'same' convolution on the tcgen05 tensor cores (sm_100a).
+//
+//   dW[co][r][s][ci] = sum over pixels p of dY[p][co] * X[p + (r,s) - pad][ci]
+//
+//   GEMM view   D[M = 128 co][N = BN ci] += A[M][K] * B[N][K] with K = pixels.  Both operands are "MN-major": in NHWC memory
+//               the channel index is contiguous and the reduction index (pixel) strides by C.  A 4-D TMA box
+//               {32 ch, tw, th, tn} (32 pixels) lands as 32 rows (pixels) x 128 B (32 channels) with the 32-byte-atom
+//               128B swizzle (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), which is exactly the canonical MN-major
+//               SWIZZLE_128B_BASE32B UMMA layout - the only one the tensor core takes for MN-major tf32 (4-pixel atoms of
+//               512 B along K, SBO = 512; the next 32 channels are the next box, LBO = 4096 B).  The (r,s) shift and the zero padding of X are, as in the
+//               forward kernel, TMA coordinates + out-of-bounds zero fill.
+//   work split  CTA = (128-co tile) x (BN-ci tile) x (tap) x (slice of the pixel patches); partial tiles are combined
+//               with fp32 atomics into a packed [Cout][R*S][CinP] buffer (zeroed by the caller), unpacked to OIHW after.
+//   accuracy    K (pixels) reaches 5e5: the accumulation chain in TMEM is cut every kDrain stages (32 MMAs) and drained
+//               into fp32 registers exactly as in conv_umma.cu; NPROD=3 adds the A_lo*B_hi + A_hi*B_lo corrections.
+#include "umma.cuh"
+
+namespace pvg {
+
+constexpr int kWThreads = 192;
+constexpr int kPix = 32;                    // pixels (K) per pipeline stage
+constexpr int kBoxBytes = kPix * 128;       // one {32 ch x 32 px} box
+constexpr int kWSmemBudget = 200 * 1024;
+
+template <int BN, int NPROD>
+struct WCfg {
+  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
+  static constexpr int kABytes = 4 * kBoxBytes;                 // 128 co
+  static constexpr int kBBytes = (BN / 32) * kBoxBytes;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kStagesRaw = kWSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kDrain = 8;
+  static constexpr int kAccCols = (NPROD == 3 ? 3 : 2) * BN;    // [main0 | main1 | (correction)]
+  static constexpr int kTmemCols = kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 128, "BN must be 32..128 in steps of 32");
+  static_assert(kStages >= 2, "need at least a double buffer");
+};
+
+struct WgradParams {
+  int N, H, W, CinP, Cout, R, S, pad;
+  int tw, th, tn;                 // 32-pixel patch
+  int tiles_w, tiles_h, tiles_n;  // patches per dim
+  int ci_tiles;
+  int patches_per_split;
+  float* dwp;                     // [Cout][R*S][CinP]
+};
+
+template <int BN, int NPROD>
+__global__ void __launch_bounds__(kWThreads, 1)
+conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmGlo,
+                       const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+                       const WgradParams p) {
+  using C = WCfg<BN, NPROD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int co0 = blockIdx.x * 128;
+  const int tap = blockIdx.y / p.ci_tiles;
+  const int ci0 = (blockIdx.y - tap * p.ci_tiles) * BN;
+  const int r = tap / p.S, s = tap - r * p.S;
+  const int total_patches = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int p_begin = blockIdx.z * p.patches_per_split;
+  const int p_end = min(p_begin + p.patches_per_split, total_patches);
+  const int iters = p_end - p_begin;          // >= 1 by construction
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmG); prefetch_tmap(&tmX);
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 128); mbar_init(&tempty_bar[1], 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+  const int periods = (iters + C::kDrain - 1) / C::kDrain;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        int t = p_begin + it;
+        const int pw = t % p.tiles_w; t /= p.tiles_w;
+        const int ph = t % p.tiles_h; t /= p.tiles_h;
+        const int w0 = pw * p.tw, h0 = ph * p.th, n0 = t * p.tn;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * C::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tma_load_4d(st + g * kBoxBytes, &tmG, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
+        uint8_t* sb = st + C::kPlanes * C::kABytes;
+#pragma unroll
+        for (int g = 0; g < BN / 32; ++g)
+          tma_load_4d(sb + g * kBoxBytes, &tmX, &full_bar[stage], ci0 + 32 * g, w0 + s - p.pad, h0 + r - p.pad, n0);
+        if (NPROD == 3) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            tma_load_4d(st + C::kABytes + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g)
+            tma_load_4d(sb + C::kBBytes + g * kBoxBytes, &tmXlo, &full_bar[stage], ci0 + 32 * g, w0 + s - p.pad, h0 + r - p.pad, n0);
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32_ex<BN>(true, true);
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t corr = tmem_acc + 2 * BN;
+      uint32_t corr_acc = 0;
+      int it = 0;
+      for (int per = 0; per < periods; ++per) {
+        const int b = per & 1;
+        mbar_wait(&tempty_bar[b], ((per >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t main_acc = tmem_acc + b * BN;
+        const int it_end = min(it + C::kDrain, iters);
+        uint32_t main_started = 0;
+        for (; it < it_end; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t a_hi = st, a_lo = st + C::kABytes;
+          const uint32_t b_hi = st + C::kPlanes * C::kABytes, b_lo = b_hi + C::kBBytes;
+          if (NPROD == 3) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_tf32(corr, make_mnmajor_sw128_desc(a_lo + ks * 1024, kBoxBytes), make_mnmajor_sw128_desc(b_hi + ks * 1024, kBoxBytes), idesc, corr_acc);
+              corr_acc = 1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(corr, make_mnmajor_sw128_desc(a_hi + ks * 1024, kBoxBytes), make_mnmajor_sw128_desc(b_lo + ks * 1024, kBoxBytes), idesc, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_tf32(main_acc, make_mnmajor_sw128_desc(a_hi + ks * 1024, kBoxBytes), make_mnmajor_sw128_desc(b_hi + ks * 1024, kBoxBytes), idesc, main_started);
+            main_started = 1;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[b]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int per = 0; per < periods; ++per) {
+      const int b = per & 1;
+      mbar_wait(&tfull_bar[b], (per >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_acc + lane_base + (uint32_t)(b * BN + c), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c + j] += v[j];
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[b]);
+    }
+    float* out = p.dwp + ((int64_t)co * (p.R * p.S) + tap) * p.CinP + ci0;
+#pragma unroll
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      if (NPROD == 3) {
+        tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      if (co < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (ci0 + c + j < p.CinP) atomicAdd(out + c + j, acc[c + j] + v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, C::kTmemCols);
+}
+
+__global__ void __launch_bounds__(256) unpack_dw_kernel(const float* __restrict__ dwp, int Cout, int Cin, int R, int S, int CinP,
+                                                        float* __restrict__ dw) {
+  const int64_t total = (int64_t)Cout * Cin * R * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = (int)(i % S);
+    int64_t t = i / S;
+    int r = (int)(t % R); t /= R;
+    int ci = (int)(t % Cin);
+    int co = (int)(t / Cin);
+    dw[i] += dwp[((int64_t)co * R * S + r * S + s) * CinP + ci];
+  }
+}
+
+static void choose_patch32(int N, int H, int W, int* tw, int* th, int* tn) {
+  static const int cand[][3] = {{8, 4, 1}, {4, 8, 1}, {16, 2, 1}, {2, 16, 1}, {32, 1, 1}, {1, 32, 1}, {4, 4, 2}, {8, 2, 2},
+                                {2, 8, 2}, {4, 2, 4}, {2, 4, 4}, {2, 2, 8}, {1, 1, 32}, {16, 1, 2}, {8, 1, 4}, {4, 1, 8}};
+  double best = -1;
+  for (auto& c : cand) {
+    int64_t tiles = (int64_t)ceil_div(W, c[0]) * ceil_div(H, c[1]) * ceil_div(N, c[2]);
+    double util = (double)N * H * W / ((double)tiles * 32.0);
+    if (util > best + 1e-9) { best = util; *tw = c[0]; *th = c[1]; *tn = c[2]; }
+  }
+}
+
+template <int BN, int NPROD>
+static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* g, const float* g_lo,
+                        float* dwp, cudaStream_t st) {
+  using C = WCfg<BN, NPROD>;
+  WgradParams p;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp;
+  choose_patch32(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
+  p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
+  p.ci_tiles = ceil_div(d->Cin, BN);
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int gx = ceil_div(d->Cout, 128), gy = d->R * d->S * p.ci_tiles;
+  int want = ceil_div(kSMs * 2, gx * gy);
+  int max_splits = ceil_div(total, 8);                 // at least 8 stages of work per CTA
+  int splits = want < max_splits ? want : max_splits;
+  if (splits < 1) splits = 1;
+  p.patches_per_split = ceil_div(total, splits);
+  splits = ceil_div(total, p.patches_per_split);
+  CUtensorMap tmG, tmGlo, tmX, tmXlo;
+  int rc;
+  if ((rc = encode_nhwc_map(&tmG, g, d->N, d->H, d->W, d->Cout, 32, p.tw, p.th, p.tn, true))) return rc;
+  if ((rc = encode_nhwc_map(&tmX, x, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn, true))) return rc;
+  if (NPROD == 3) {
+    if ((rc = encode_nhwc_map(&tmGlo, g_lo, d->N, d->H, d->W, d->Cout, 32, p.tw, p.th, p.tn, true))) return rc;
+    if ((rc = encode_nhwc_map(&tmXlo, x_lo, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn, true))) return rc;
+  } else {
+    tmGlo = tmG; tmXlo = tmX;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PVG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(gx, gy, splits);
+  conv_wgrad_umma_kernel<BN, NPROD><<<grid, kWThreads, C::kSmemBytes, st>>>(tmG, tmGlo, tmX, tmXlo, p);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace pvg
+
+using namespace pvg;
+
+// Tensor-core weight gradient.  x: [N,H,W,CinP] (CinP % 32 == 0), g = dY: [N,H,W,Cout] (Cout % 4 == 0), *_lo their
+// 3xTF32 residual planes (nprod == 3).  scratch: float[Cout * R*S * CinP], zero-initialised by the caller.
+// dw_oihw [Cout][Cin_logical][R][S] += unpack(scratch).
+extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* x_lo, const float* g,
+                                     const float* g_lo, float* scratch, float* dw_oihw, void* stream) {
+  PVG_CHECK_ARG(d && x && g && scratch && dw_oihw, "null argument");
+  PVG_CHECK_ARG(d->Cin % 32 == 0 && d->Cout % 4 == 0, "tensor-core wgrad needs CinP % 32 == 0 and Cout % 4 == 0");
+  PVG_CHECK_ARG((((uintptr_t)x | (uintptr_t)g) & 15) == 0, "operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const int cin = d->Cin;
+  if (d->nprod == 3) {
+    PVG_CHECK_ARG(x_lo && g_lo, "nprod == 3 needs x_lo and g_lo");
+    if (cin <= 32) rc = launch_wgrad<32, 3>(d, x, x_lo, g, g_lo, scratch, st);
+    else if (cin <= 64) rc = launch_wgrad<64, 3>(d, x, x_lo, g, g_lo, scratch, st);
+    else if (cin <= 96) rc = launch_wgrad<96, 3>(d, x, x_lo, g, g_lo, scratch, st);
+    else rc = launch_wgrad<128, 3>(d, x, x_lo, g, g_lo, scratch, st);
+  } else {
+    if (cin <= 32) rc = launch_wgrad<32, 1>(d, x, nullptr, g, nullptr, scratch, st);
+    else if (cin <= 64) rc = launch_wgrad<64, 1>(d, x, nullptr, g, nullptr, scratch, st);
+    else if (cin <= 96) rc = launch_wgrad<96, 1>(d, x, nullptr, g, nullptr, scratch, st);
+    else rc = launch_wgrad<128, 1>(d, x, nullptr, g, nullptr, scratch, st);
+  }
+  if (rc) return rc;
+  int64_t total = (int64_t)d->Cout * Cin_logical * d->R * d->S;
+  unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, d->Cin, dw_oihw);
+  PVG_LAUNCH_OK();
+  return 0;
+}

@@ -168,15 +168,19 @@ def _split(x: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 def _conv_forward(x: Tensor, packs: Tensor, which: int, cout: int, ksize: int, bias, act: int, slope: float,
-                  algo: int, nprod: int, alg_flops: float = 0.0) -> Tensor:
+                  algo: int, nprod: int, alg_flops: float = 0.0, split=None) -> Tensor:
+    """``split``: optional pre-computed (hi, lo) planes of x (shared with the weight-gradient kernel)."""
     n, cin, h, w = x.shape
     y = empty_nhwc((n, cout, h, w), x.device)
     if algo == ALGO_UMMA and nprod == 3:
-        hi, lo = _split(x)
+        hi, lo = split if split is not None else _split(x)
         _run_conv(hi, lo, packs[which], packs[which + 1], bias, y, ksize, (ksize - 1) // 2, act, slope, algo, nprod, alg_flops)
     else:
         _run_conv(x, None, packs[which], None, bias, y, ksize, (ksize - 1) // 2, act, slope, algo, nprod, alg_flops)
     return y
+
+
+wgrad_profile = None    # like conv_profile, for the tensor-core weight-gradient kernel
 
 
 class Conv2dFn(torch.autograd.Function):
@@ -214,15 +218,41 @@ class Conv2dFn(torch.autograd.Function):
         else:
             g = dy
         dx = dw = db = None
+        nprod = 3 if _precision == "tf32x3" else 1
+        g_split = [None]
+
+        def split_g():
+            if g_split[0] is None:
+                g_split[0] = _split(g)
+            return g_split[0]
+
         if ctx.needs_input_grad[0]:
-            algo, nprod = _conv_algo(cout)
+            algo, np_ = _conv_algo(cout)
             packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
             # data gradient = "same" convolution of g with the tap-flipped, transposed pack [CinP][R][S][Cout]
-            dx = _conv_forward(g, packs, 2, cin_p, r, None, ACT_NONE, 0.0, algo, nprod, 2.0 * n * h * w * cout * r * s * cin_log)
+            dx = _conv_forward(g, packs, 2, cin_p, r, None, ACT_NONE, 0.0, algo, np_, 2.0 * n * h * w * cout * r * s * cin_log,
+                               split=split_g() if (algo == ALGO_UMMA and np_ == 3) else None)
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-            d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, 1)
-            call("pvg_conv2d_wgrad", d, cin_log, x.data_ptr(), g.data_ptr(), dw.data_ptr(), _stream())
+            d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod)
+            if _precision != "fp32" and cin_p % 32 == 0 and cout % 4 == 0:
+                scratch = torch.zeros((cout * r * s * cin_p,), dtype=torch.float32, device=dy.device)
+                if nprod == 3:
+                    x_hi, x_lo = _split(x)
+                    g_hi, g_lo = split_g()
+                else:
+                    x_hi, x_lo, g_hi, g_lo = x, None, g, None
+                prof = wgrad_profile is not None
+                if prof:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                call("pvg_conv2d_wgrad_umma", d, cin_log, x_hi.data_ptr(), _p(x_lo), g_hi.data_ptr(), _p(g_lo),
+                     scratch.data_ptr(), dw.data_ptr(), _stream())
+                if prof:
+                    e1.record()
+                    wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout * r * s * cin_log))
+            else:
+                call("pvg_conv2d_wgrad", d, cin_log, x.data_ptr(), g.data_ptr(), dw.data_ptr(), _stream())
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((cout,), dtype=torch.float32, device=dy.device)
             scratch = torch.empty((cout,), dtype=torch.float64, device=dy.device)

@@ -117,7 +117,9 @@ def test_conv_umma_forward_tf32(shape):
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64, 16, 16, 3, True, 0), (2, 201, 224, 512, 8, 8, 3, True, 0),
                                    (2, 3, 3, 16, 16, 16, 3, False, 0), (1, 64, 64, 65, 16, 16, 1, False, 0),
-                                   (2, 32, 32, 3, 16, 16, 7, True, 3), (2, 137, 160, 256, 16, 16, 3, False, 0)])
+                                   (2, 32, 32, 3, 16, 16, 7, True, 3), (2, 137, 160, 256, 16, 16, 3, False, 0),
+                                   (8, 64, 64, 32, 64, 64, 3, False, 0), (3, 64, 64, 128, 26, 20, 3, True, 0),
+                                   (2, 96, 96, 16, 16, 16, 1, False, 0), (2, 256, 256, 132, 8, 8, 3, False, 0)])
 def test_conv_backward(shape):
     """dx (tensor-core dgrad with flipped packed weights or SIMT), dw (split-K wgrad), db vs torch autograd on CPU."""
     ops = _ops()
