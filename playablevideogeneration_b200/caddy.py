@@ -26,8 +26,63 @@ from .ops import ACT_LRELU, ACT_NONE, ACT_TANH
 SLOPE = 0.2
 
 
+class NoiseSource:
+    """Where the model's random numbers come from.
+
+    ``cpu`` (default): drawn on the global CPU generator at the point of use and copied to the device - exactly the
+    reference's behaviour and draw order (action_network.py:45, gumbel_softmax.py:33, model.py:496).
+    ``record``: like ``cpu`` but remembers the sequence of draws of one step.
+    ``static``: every draw returns a persistent device buffer; ``refill()`` (host side, before a CUDA-graph replay)
+    redraws the whole sequence on the CPU generator in the recorded order and uploads it.  This keeps the reference's
+    RNG stream while letting the step be captured in a CUDA graph (no host work between kernels)."""
+
+    def __init__(self):
+        self.mode = "cpu"
+        self.plan = []          # (kind, shape, device or None)
+        self.bufs = []
+        self.cursor = 0
+
+    def _draw(self, kind, shape):
+        return torch.randn(shape, dtype=torch.float32) if kind == "randn" else torch.rand(shape)
+
+    def sample(self, kind, shape, device):
+        shape = tuple(shape)
+        if self.mode == "static":
+            buf = self.bufs[self.cursor]
+            self.cursor += 1
+            if device is None:
+                return None
+            assert buf is not None and tuple(buf.shape) == shape
+            return buf
+        t = self._draw(kind, shape)
+        if self.mode == "record":
+            self.plan.append((kind, shape, device))
+        return t.to(device) if device is not None else t
+
+    def begin_step(self):
+        self.cursor = 0
+        if self.mode == "record":
+            self.plan = []
+
+    def freeze(self):
+        self.bufs = [torch.empty(shape, dtype=torch.float32, device=dev) if dev is not None else None
+                     for _, shape, dev in self.plan]
+        self.mode = "static"
+        self.refill()
+
+    def refill(self):
+        for (kind, shape, dev), buf in zip(self.plan, self.bufs):
+            t = self._draw(kind, shape)
+            if buf is not None:
+                buf.copy_(t)
+        self.cursor = 0
+
+
 def _conv(cin, cout, k, bias):
     return nn.Conv2d(cin, cout, kernel_size=k, stride=1, padding=(k - 1) // 2, bias=bias)
+
+
+_DEFAULT_NOISE = NoiseSource()
 
 
 class ResidualBlock(nn.Module):
@@ -214,9 +269,11 @@ class ActionNetwork(nn.Module):
         self.variance_fc = nn.Linear(2 * sf, dim)
         self.final_fc = nn.Linear(dim, config["data"]["actions_count"])
 
-    @staticmethod
-    def sample(mean, variance):
-        noise = torch.randn(mean.size(), dtype=torch.float32).to(mean.device)     # CPU generator, as the reference (:45)
+    noise = None        # NoiseSource shared with the owning Model (set by Model.__init__)
+
+    def sample(self, mean, variance):
+        src = self.noise if self.noise is not None else _DEFAULT_NOISE
+        noise = src.sample("randn", mean.size(), mean.device)                     # CPU generator, as the reference (:45)
         return noise * torch.sqrt(variance) + mean
 
     def forward(self, states, attention):
@@ -267,6 +324,8 @@ class RenderingNetwork(nn.Module):
 class GumbelSoftmax(nn.Module):
     """model/layers/gumbel_softmax.py:7-72 (uniform noise drawn on the CPU generator, :33)."""
 
+    noise = None
+
     def __init__(self, initial_temperature, hard=True):
         super().__init__()
         self.current_temperature = initial_temperature
@@ -275,7 +334,8 @@ class GumbelSoftmax(nn.Module):
     def forward(self, logp, temperature=None):
         if temperature is not None:
             self.current_temperature = temperature
-        u = torch.rand(logp.size()).to(logp.device)
+        src = self.noise if self.noise is not None else _DEFAULT_NOISE
+        u = src.sample("rand", logp.size(), logp.device)
         g = -torch.log(-torch.log(u + 1e-20) + 1e-20)
         soft = F.softmax((logp + g) / self.current_temperature, dim=-1)
         if self.hard:
@@ -302,7 +362,9 @@ class CentroidEstimator(nn.Module):
             means = points_priors.reshape(-1, 2, self.space_dimensions)[:, 0]
             assign = centroid_assignments.reshape(-1, self.centroids_count)
             est = (means.unsqueeze(1) * assign.unsqueeze(-1)).sum(0) / assign.sum(0).unsqueeze(-1)
-            self.estimated_centroids.data = (self.estimated_centroids * (1 - self.alpha) + est * self.alpha).detach()
+            # the reference rebinds ``.data``; an in-place copy is numerically identical and keeps the buffer address
+            # stable (CUDA-graph replays read and write the same storage)
+            self.estimated_centroids.data.copy_(self.estimated_centroids * (1 - self.alpha) + est * self.alpha)
 
     def compute_variations(self, points, centroid_assignments):
         lead = list(points.size())[:-1]
@@ -337,6 +399,10 @@ class Model(nn.Module):
         self.centroid_estimator = CentroidEstimator(self.actions_count, m["action_network"]["action_space_dimension"],
                                                     m["centroid_estimator"]["alpha"])
         self.train_forward_counts = 0
+        self.noise = NoiseSource()
+        for net in self.action_network:
+            net.noise = self.noise
+        self.gumbel_softmax.noise = self.noise
 
     # ----------------------------------------------------------------------------------------------------------
     def forward(self, batch_tuple, ground_truth_observations_init=0, pretraining=False, gumbel_temperature=None,
@@ -460,7 +526,7 @@ class Model(nn.Module):
     def generate_noise(self, batch_size: int):
         """model.py:488-497.  Drawn on the CPU generator like the reference; the dynamics network ignores it
         (conv_dynamics_network.py:111-133), so it is not copied to the device."""
-        return torch.randn((batch_size, self.random_noise_size))
+        return self.noise.sample("randn", (batch_size, self.random_noise_size), None)
 
     def compute_current_observation(self, idx, ground_truth_observations_init, ground_truth_observations,
                                     all_reconstructed_observations):
@@ -506,7 +572,7 @@ class Model(nn.Module):
         actions_batch = torch.zeros((1, self.actions_count), dtype=torch.float32, device=dev)
         actions_batch[0, action] = 1.0
         if noise:
-            variation = torch.randn((1, dim), dtype=torch.float32).to(dev)
+            variation = self.noise.sample("randn", (1, dim), dev)
         else:
             variation = torch.zeros((1, dim), dtype=torch.float32, device=dev)
         frame = self._rollout_step(observation.unsqueeze(0), actions_batch, variation).squeeze(0)

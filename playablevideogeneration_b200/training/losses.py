@@ -184,7 +184,8 @@ class FixedMatrixEstimator(nn.Module):
 
     def forward(self, latest):
         out = self.estimated_matrix * (1 - self.alpha) + latest * self.alpha
-        self.estimated_matrix.data = out.detach()
+        with torch.no_grad():       # reference: ``.data = out.detach()``; in-place keeps the address stable for CUDA graphs
+            self.estimated_matrix.data.copy_(out)
         return out
 
 
