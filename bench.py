@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--workload", default="bair256_b8_t16", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-frames", type=int, default=8, help="frames (B=1 x T) of the CPU baseline sample")
     return ap.parse_args()
 
@@ -181,7 +182,7 @@ def main():
     from oracle.cases import build_config            # config dict only (plain data; no oracle compute on this path)
     from playablevideogeneration_b200 import _lib, ops
     from playablevideogeneration_b200.caddy import Model
-    from playablevideogeneration_b200.training.step import TrainStep
+    from playablevideogeneration_b200.training.step import GraphedTrainStep, TrainStep
     from playablevideogeneration_b200.vgg import Vgg19
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,23 +225,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    use_graph = not args.no_graph
+    if use_graph:
+        # eager warm-up (inside GraphedTrainStep) + capture of the whole step; W more replays warm the graph itself
+        gstep = GraphedTrainStep(step, resident, w["gt_init"], 1.0, warmup=2)
+        run_resident = lambda: gstep()
+        run_host = lambda: gstep(host)
+    else:
+        run_resident = lambda: step.step(resident, w["gt_init"], 1.0)
+        run_host = lambda: step.step(tuple(t.to(dev, non_blocking=True) for t in host), w["gt_init"], 1.0)
     for _ in range(args.warmup):
-        step.step(resident, w["gt_init"], 1.0)
+        run_resident()
     # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------------
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
-    ops.conv_profile = []
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step.step(resident, w["gt_init"], 1.0)
+        run_resident()
     e1.record()
     barrier()
-    launches = _lib.launch_count - launches0
-    prof, ops.conv_profile = ops.conv_profile, None
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     # ---- timed region 2: end to end through the public API from pinned host memory ---------------------------------
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -248,12 +255,20 @@ def main():
     e2.record()
     loss_host = 0.0
     for _ in range(args.steps):
-        batch = tuple(t.to(dev, non_blocking=True) for t in host)          # H2D of this step's inputs
-        total, _ = step.step(batch, w["gt_init"], 1.0)
+        total, _ = run_host()                                              # H2D of this step's inputs + the step
         loss_host = float(total.cpu()[0])                                  # D2H of the step's result
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3) / args.steps)
+    # ---- one more step launched kernel by kernel with CUDA events around every tensor-core conv / wgrad launch: the
+    #      per-kernel durations behind `roofline` (events cannot be timed inside a graph replay); also counts launches ----
+    ops.conv_profile, ops.wgrad_profile = [], []
+    launches0 = _lib.launch_count
+    step.step(resident, w["gt_init"], 1.0)
+    barrier()
+    launches = (_lib.launch_count - launches0) * args.steps
+    prof, ops.conv_profile = ops.conv_profile, None
+    wprof, ops.wgrad_profile = ops.wgrad_profile, None
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(t.numel() * t.element_size() for t in host)
 
@@ -264,10 +279,16 @@ def main():
         tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
         flops = sum(f for _, _, f in prof)
         ach = flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        wg = None
+        if wprof:
+            wms = sum(a.elapsed_time(b) for a, b, _ in wprof)
+            wg = dict(kernel="conv_wgrad_umma_kernel", launches_per_step=len(wprof), ms_per_step=wms,
+                      achieved=sum(f for _, _, f in wprof) / (wms * 1e-3) / 1e12 if wms > 0 else 0.0, unit="TFLOP/s")
         roof = dict(bound="tensor", kernel="conv_umma_kernel (tcgen05 kind::tf32" + (", 3 MMAs per k-step" if args.precision == "tf32x3" else "") + ")",
                     achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=None,
-                    launches_per_step=len(prof) / args.steps, avg_launch_us=tot_ms * 1e3 / len(prof),
-                    share_of_step=tot_ms / args.steps / ms_dev, peak_source=peaks["source"],
+                    launches_per_step=len(prof), avg_launch_us=tot_ms * 1e3 / len(prof), ms_per_step=tot_ms,
+                    share_of_step=tot_ms / ms_dev, peak_source=peaks["source"], weight_gradient=wg,
+                    measured="CUDA events around each launch in one extra eager (non-graph) step after the timed region",
                     note="achieved = algorithmic conv FLOPs (2*N*H*W*Cout*R*S*Cin, unpadded) / CUDA-event time of the launches; "
                          "peak is the measured bf16 cuBLAS figure - kind::tf32 tops out at half of it, 3xTF32 at a sixth")
     if rank != 0:
@@ -282,6 +303,7 @@ def main():
                 data="synthetic", impl="pvg_b200",
                 config=dict(workload=args.workload, per_gpu_batch=w["B"], seq_len=w["T"], frame=f"{w['H']}x{w['W']}x3",
                             gt_init=w["gt_init"], parallelism=f"dp{world}", precision=args.precision,
+                            launch="cuda-graph replay of the whole step" if use_graph else "eager (one launch per kernel from Python)",
                             l2="inputs (100.7 MB/step) and per-step activations (>10 GB) exceed the 126 MB L2; no explicit flush"),
                 e2e=dict(value=frames_per_step / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d * world,
                          d2h_bytes_per_step=8 * world, ms_per_step=ms_e2e, last_loss=loss_host),

@@ -139,6 +139,10 @@ int pvg_absdiff_mean_bwd(const float* a, const float* b, const float* gout, int 
 int pvg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* same update with the step-dependent scalars read from DEVICE memory, so the launch can live in a CUDA graph:
+ * hyper = [lr / (1 - beta1^t), sqrt(1 - beta2^t), beta1, beta2, eps, weight_decay, grad_scale] */
+int pvg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "pvg_absdiff_mean_fwd": [P, P, c_int, c_int64, P, P],
     "pvg_absdiff_mean_bwd": [P, P, P, c_int, c_int64, P, P],
     "pvg_adam_step": [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P],
+    "pvg_adam_step_dev": [P, P, P, P, c_int64, P, P],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["pvg_last_error", "pvg_version", "pvg_has_umma"])
 

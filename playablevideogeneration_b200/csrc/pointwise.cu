@@ -561,6 +561,20 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// hyper (device): [lr / bias_correction1, sqrt(bias_correction2), beta1, beta2, eps, weight_decay, grad_scale]
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, int64_t n, const float* __restrict__ hyper) {
+  const float step_size = hyper[0], bc2_sqrt = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4], wd = hyper[5], gs = hyper[6];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] * gs + wd * pi;
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
 }  // namespace pvg
 
 using namespace pvg;
@@ -785,6 +799,12 @@ int pvg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
                                                                 bc2_sqrt, grad_scale);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream) {
+  adam_dev_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper);
   PVG_LAUNCH_OK();
   return 0;
 }

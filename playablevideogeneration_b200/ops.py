@@ -536,3 +536,8 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, 
     """In-place torch.optim.Adam update (L2-style weight decay) over flat fp32 buffers."""
     call("pvg_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1),
          float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _stream())
+
+
+def adam_step_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, hyper: Tensor) -> None:
+    """Adam update whose step-dependent scalars live in device memory (``hyper``, 7 floats) - graph-capturable."""
+    call("pvg_adam_step_dev", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), hyper.data_ptr(), _stream())

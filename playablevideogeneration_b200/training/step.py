@@ -85,6 +85,11 @@ class TrainStep:
         self.global_step = 0
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self._capturing = False
+        self._graph_runs = []
+        self._hyper_dev_buf = torch.zeros((16, 7), dtype=torch.float32, device=dev)
+        self._hyper_dev = self._hyper_dev_buf
+        self._hyper_host = torch.zeros((16, 7), dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros((16, 7))
 
     # ----------------------------------------------------------------------------------------------------------
     def current_lr(self) -> float:
@@ -159,15 +164,11 @@ class TrainStep:
         packed = torch.stack([info[k].reshape(()).double() for k in keys]).cpu()
         return {k: float(v) for k, v in zip(keys, packed)}
 
-    def optimizer_step(self):
-        if self.pg is not None and self.world > 1:
-            torch.distributed.all_reduce(self.arena.grad, group=self.pg)       # one NCCL all-reduce over NVLink / NVSwitch
-        self.global_step += 1
+    def _adam_runs(self):
+        """Runs of consecutive arena parameters that received a gradient and share a step count: one Adam launch each
+        (steady state: one or two launches for the whole model).  torch.optim.Adam skips parameters without a gradient."""
         a = self.arena
-        lr = self.current_lr()
-        # one launch per run of consecutive parameters that (a) received a gradient and (b) share a step count
-        # (in steady state: one or two launches for the whole model)
-        i, n = 0, len(a.params)
+        runs, i, n = [], 0, len(a.params)
         while i < n:
             if i not in a.touched:
                 i += 1
@@ -175,13 +176,46 @@ class TrainStep:
             j = i
             while j + 1 < n and (j + 1) in a.touched and a.steps[j + 1] == a.steps[i]:
                 j += 1
-            lo, hi = a.offsets[i], a.offsets[j] + a.sizes[j]
+            runs.append((i, j, a.offsets[i], a.offsets[j] + a.sizes[j]))
+            i = j + 1
+        return runs
+
+    def _hyper(self, step: int):
+        b1, b2 = 0.9, 0.999
+        return [self.current_lr() / (1.0 - b1 ** step), math.sqrt(1.0 - b2 ** step), b1, b2, 1e-8, self.weight_decay,
+                1.0 / self.world]
+
+    def optimizer_step(self):
+        if self.pg is not None and self.world > 1:
+            torch.distributed.all_reduce(self.arena.grad, group=self.pg)       # one NCCL all-reduce over NVLink / NVSwitch
+        a = self.arena
+        if self._capturing:
+            # CUDA-graph capture: record the launches only; counters and hyper-parameters are advanced by prepare_replay()
+            self._graph_runs = self._adam_runs()
+            self._hyper_dev = self._hyper_dev_buf[:len(self._graph_runs)]
+            for k, (i, j, lo, hi) in enumerate(self._graph_runs):
+                ops.adam_step_dev(a.flat[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._hyper_dev[k])
+            return
+        self.global_step += 1
+        lr = self.current_lr()
+        for i, j, lo, hi in self._adam_runs():
             for k in range(i, j + 1):
                 a.steps[k] += 1
             ops.adam_step(a.flat[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], a.steps[i], lr,
                           weight_decay=self.weight_decay, grad_scale=1.0 / self.world)
-            i = j + 1
         ops.invalidate_weight_cache()
+
+    def prepare_replay(self):
+        """Host work before a graph replay: advance the step counters and upload the Adam scalars of every run."""
+        self.global_step += 1
+        a = self.arena
+        rows = []
+        for i, j, lo, hi in self._graph_runs:
+            for k in range(i, j + 1):
+                a.steps[k] += 1
+            rows.append(self._hyper(a.steps[i]))
+        self._hyper_host[:len(rows)].copy_(torch.tensor(rows, dtype=torch.float32))
+        self._hyper_dev.copy_(self._hyper_host[:len(rows)], non_blocking=True)
 
     def step(self, batch_tuple, ground_truth_observations_count: int, gumbel_temperature: float, pretraining: bool = False):
         self.module.train()
@@ -190,3 +224,47 @@ class TrainStep:
         total.backward()
         self.optimizer_step()
         return total.detach(), info
+
+
+class GraphedTrainStep:
+    """The whole optimiser step (forward, losses, backward, all-reduce, Adam) captured once in a CUDA graph and replayed:
+    ~5 000 kernel launches per step are submitted by ONE cudaGraphLaunch instead of by the Python interpreter.
+
+    Per replay the host only (1) copies the batch into the static input buffers, (2) redraws the step's random numbers
+    on the CPU generator in the reference's order and uploads them (NoiseSource.refill), (3) uploads Adam's bias
+    corrections / learning rate.  Shapes, ``ground_truth_observations_count`` and the Gumbel temperature are fixed per
+    graph (re-capture when the trainer's schedule changes them)."""
+
+    def __init__(self, step: TrainStep, example_batch, ground_truth_observations_count: int, gumbel_temperature: float,
+                 pretraining: bool = False, warmup: int = 2):
+        self.step = step
+        self.args = (ground_truth_observations_count, gumbel_temperature, pretraining)
+        self.static_batch = tuple(t.clone() for t in example_batch)
+        noise = step.module.noise
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(max(1, warmup)):            # eager warm-up: lazy inits, kernel attributes, allocator pools
+                noise.mode = "record"
+                noise.begin_step()
+                step.step(self.static_batch, *self.args)
+            noise.freeze()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        step._capturing = True
+        try:
+            with torch.cuda.graph(self.graph):
+                noise.begin_step()
+                self.static_total, self.static_info = step.step(self.static_batch, *self.args)
+        finally:
+            step._capturing = False
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            for dst, src in zip(self.static_batch, batch):
+                dst.copy_(src, non_blocking=True)
+        self.step.module.noise.refill()
+        self.step.prepare_replay()
+        self.graph.replay()
+        return self.static_total, self.static_info

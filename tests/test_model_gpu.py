@@ -188,3 +188,29 @@ def test_batched_rollout_step_equals_single():
         fb, nb = model.generate_next_batch(obs.unsqueeze(0).repeat(4, 1, 1, 1), torch.tensor([3, 1, 3, 0], device=DEV))
     assert float((fb[0] - f1).abs().max()) <= 1e-5 and float((fb[2] - f1).abs().max()) <= 1e-5
     assert float((fb[1] - f1).abs().max()) > 1e-4
+
+
+def test_graphed_step_matches_eager_steps():
+    """The CUDA-graph replay of the whole optimiser step must reproduce the kernel-by-kernel (eager) step: same seeds ->
+    same losses over three steps (1e-6 rel: the only difference is the order of fp32 atomics)."""
+    from playablevideogeneration_b200.training.step import GraphedTrainStep
+    case, _ = load_case("full_bair")
+    cfg, sd, vgg_sd, obs = case_inputs(case)
+    bt = _to_dev(batch_tuple(obs))
+    _, eager = _build(case, cfg, sd, vgg_sd)
+    ref_losses = []
+    for s in range(3):
+        torch.manual_seed(500 + s); random.seed(500 + s)
+        total, _ = eager.step(bt, case["gt_init"], 0.9)
+        ref_losses.append(float(total.cpu()[0]))
+    _, gs = _build(case, cfg, sd, vgg_sd)
+    torch.manual_seed(500); random.seed(500)
+    graphed = GraphedTrainStep(gs, bt, case["gt_init"], 0.9, warmup=1)       # warm-up = eager step 0
+    got = []
+    for s in (1, 2):
+        torch.manual_seed(500 + s); random.seed(500 + s)
+        total, info = graphed(bt)
+        got.append(float(total.cpu()[0]))
+    _log("graph_vs_eager", eager=ref_losses, graphed=got)
+    for a, b in zip(got, ref_losses[1:]):
+        assert abs(a - b) <= 2e-6 * abs(b), (got, ref_losses)
