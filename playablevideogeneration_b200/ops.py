@@ -235,22 +235,34 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
             d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod)
-            if _precision != "fp32" and cin_p % 32 == 0 and cout % 4 == 0:
-                scratch = torch.zeros((cout * r * s * cin_p,), dtype=torch.float32, device=dy.device)
-                if nprod == 3:
-                    x_hi, x_lo = _split(x)
-                    g_hi, g_lo = split_g()
+            if _precision != "fp32" and cin_p % 32 == 0:
+                # tensor-core weight gradient; dY needs a channel count that is a multiple of 4 (16-byte TMA strides):
+                # the 3-channel image heads and the 65-channel encoder tail are zero-padded (a few MB)
+                cout4 = (cout + 3) // 4 * 4
+                if cout4 != cout:
+                    g4 = empty_nhwc((n, cout4, h, w), dy.device)
+                    g4[:, :cout].copy_(g)
+                    g4[:, cout:].zero_()
+                    dw4 = torch.zeros((cout4, cin_log, r, s), dtype=torch.float32, device=dy.device)
+                    d = ConvDesc(n, h, w, cin_p, cout4, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod)
+                    g_pair = _split(g4) if nprod == 3 else (g4, None)
                 else:
-                    x_hi, x_lo, g_hi, g_lo = x, None, g, None
+                    g4, dw4 = g, dw
+                    g_pair = split_g() if nprod == 3 else (g, None)
+                scratch = torch.zeros((cout4 * r * s * cin_p,), dtype=torch.float32, device=dy.device)
+                x_hi, x_lo = _split(x) if nprod == 3 else (x, None)
+                g_hi, g_lo = g_pair
                 prof = wgrad_profile is not None
                 if prof:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                 call("pvg_conv2d_wgrad_umma", d, cin_log, x_hi.data_ptr(), _p(x_lo), g_hi.data_ptr(), _p(g_lo),
-                     scratch.data_ptr(), dw.data_ptr(), _stream())
+                     scratch.data_ptr(), dw4.data_ptr(), _stream())
                 if prof:
                     e1.record()
                     wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout * r * s * cin_log))
+                if cout4 != cout:
+                    dw = dw4[:cout].contiguous()
             else:
                 call("pvg_conv2d_wgrad", d, cin_log, x.data_ptr(), g.data_ptr(), dw.data_ptr(), _stream())
         if has_bias and ctx.needs_input_grad[2]:

@@ -31,7 +31,7 @@ case $s in
   bench2) run bench2 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline ;;
   bench_nograph) run bench_nograph 600 python bench.py --steps 3 --warmup 2 --no-graph --no-cpu-baseline ;;
   bench_ref) run bench_ref 900 python bench.py --impl reference --steps 1 --warmup 0 ;;
-  ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline ;;
+  ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph ;;
 esac
 done
 cp $OUT/summary.txt $OUT/summary_$(date +%s).txt 2>/dev/null
