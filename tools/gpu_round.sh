@@ -30,6 +30,9 @@ case $s in
   allkernels) run allkernels 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider ;;
   bench2) run bench2 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline ;;
   bench_nograph) run bench_nograph 600 python bench.py --steps 3 --warmup 2 --no-graph --no-cpu-baseline ;;
+  convbench) run convbench 600 python tools/conv_bench.py tf32x3 5 ;;
+  convbench1) run convbench1 600 python tools/conv_bench.py tf32 5 ;;
+  ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_umma_kernel -c 10 -f -o $OUT/prof_conv python tools/conv_bench.py tf32x3 1 ;;
   bench_ref) run bench_ref 900 python bench.py --impl reference --steps 1 --warmup 0 ;;
   ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph ;;
 esac
