@@ -2,14 +2,17 @@
 //
 //   dW[co][r][s][ci] = sum over pixels p of dY[p][co] * X[p + (r,s) - pad][ci]
 //
-//   GEMM view   D[M = 128 co][N = BN ci] += A[M][K] * B[N][K] with K = pixels.  Both operands are "MN-major": in NHWC memory
+//   GEMM view   D[M = 128 rows of (tap, ci)][N = BN co] += A[M][K] * B[N][K] with K = pixels.  An M tile is FOUR groups of 32
+//               input channels, each group with its own tap (r,s) - so M is always full whatever Cout is (the roles are
+//               swapped w.r.t. the textbook dW = dY^T X: layers with 3..64 output channels would waste the 128-row MMA).
+//               Both operands are "MN-major": in NHWC memory
 //               the channel index is contiguous and the reduction index (pixel) strides by C.  A 4-D TMA box
 //               {32 ch, tw, th, tn} (32 pixels) lands as 32 rows (pixels) x 128 B (32 channels) with the 32-byte-atom
 //               128B swizzle (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), which is exactly the canonical MN-major
 //               SWIZZLE_128B_BASE32B UMMA layout - the only one the tensor core takes for MN-major tf32 (4-pixel atoms of
 //               512 B along K, SBO = 512; the next 32 channels are the next box, LBO = 4096 B).  The (r,s) shift and the zero padding of X are, as in the
 //               forward kernel, TMA coordinates + out-of-bounds zero fill.
-//   work split  CTA = (128-co tile) x (BN-ci tile) x (tap) x (slice of the pixel patches); partial tiles are combined
+//   work split  CTA = (4 (tap, 32-ci) groups) x (BN-co tile) x (slice of the pixel patches); partial tiles are combined
 //               with fp32 atomics into a packed [Cout][R*S][CinP] buffer (zeroed by the caller), unpacked to OIHW after.
 //   accuracy    K (pixels) reaches 5e5: the accumulation chain in TMEM is cut every kDrain stages (32 MMAs) and drained
 //               into fp32 registers exactly as in conv_umma.cu; NPROD=3 adds the A_lo*B_hi + A_hi*B_lo corrections.
@@ -25,7 +28,7 @@ constexpr int kWSmemBudget = 200 * 1024;
 template <int BN, int NPROD>
 struct WCfg {
   static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
-  static constexpr int kABytes = 4 * kBoxBytes;                 // 128 co
+  static constexpr int kABytes = 4 * kBoxBytes;                 // 4 groups of 32 input channels
   static constexpr int kBBytes = (BN / 32) * kBoxBytes;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kWSmemBudget / kStageBytes;
@@ -42,7 +45,7 @@ struct WgradParams {
   int N, H, W, CinP, Cout, R, S, pad;
   int tw, th, tn;                 // 32-pixel patch
   int tiles_w, tiles_h, tiles_n;  // patches per dim
-  int ci_tiles;
+  int chunks, groups;             // 32-channel chunks of CinP; (tap, chunk) groups = R*S*chunks
   int patches_per_split;
   float* dwp;                     // [Cout][R*S][CinP]
 };
@@ -62,10 +65,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int co0 = blockIdx.x * 128;
-  const int tap = blockIdx.y / p.ci_tiles;
-  const int ci0 = (blockIdx.y - tap * p.ci_tiles) * BN;
-  const int r = tap / p.S, s = tap - r * p.S;
+  const int g0 = blockIdx.x * 4;            // first (tap, chunk) group of this M tile
+  const int co0 = blockIdx.y * BN;
   const int total_patches = p.tiles_w * p.tiles_h * p.tiles_n;
   const int p_begin = blockIdx.z * p.patches_per_split;
   const int p_end = min(p_begin + p.patches_per_split, total_patches);
@@ -97,18 +98,21 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
         uint8_t* st = smem + stage * C::kStageBytes;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tma_load_4d(st + g * kBoxBytes, &tmG, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
+        for (int g = 0; g < 4; ++g) {
+          const int gi = g0 + g;
+          const bool ok = gi < p.groups;
+          const int tap = ok ? gi / p.chunks : 0, cc = ok ? gi - tap * p.chunks : 0;
+          const int r = tap / p.S, s = tap - r * p.S;
+          const int c0 = ok ? cc * 32 : p.CinP;                  // a group past the end loads an all-out-of-bounds (zero) box
+          tma_load_4d(st + g * kBoxBytes, &tmX, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
+          if (NPROD == 3)
+            tma_load_4d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
+        }
         uint8_t* sb = st + C::kPlanes * C::kABytes;
 #pragma unroll
-        for (int g = 0; g < BN / 32; ++g)
-          tma_load_4d(sb + g * kBoxBytes, &tmX, &full_bar[stage], ci0 + 32 * g, w0 + s - p.pad, h0 + r - p.pad, n0);
-        if (NPROD == 3) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            tma_load_4d(st + C::kABytes + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
-#pragma unroll
-          for (int g = 0; g < BN / 32; ++g)
-            tma_load_4d(sb + C::kBBytes + g * kBoxBytes, &tmXlo, &full_bar[stage], ci0 + 32 * g, w0 + s - p.pad, h0 + r - p.pad, n0);
+        for (int g = 0; g < BN / 32; ++g) {
+          tma_load_4d(sb + g * kBoxBytes, &tmG, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
+          if (NPROD == 3) tma_load_4d(sb + C::kBBytes + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
         }
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
@@ -155,8 +159,11 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
       }
     }
   } else {
-    const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
+    const int q = warp & 3;                 // TMEM lane quarter == group index inside the M tile
+    const int gi = g0 + q;
+    const bool ok = gi < p.groups;
+    const int tap = ok ? gi / p.chunks : 0, cc = ok ? gi - tap * p.chunks : 0;
+    const int ci = cc * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float acc[BN];
 #pragma unroll
@@ -175,7 +182,9 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
       tc_fence_before();
       mbar_arrive(&tempty_bar[b]);
     }
-    float* out = p.dwp + ((int64_t)co * (p.R * p.S) + tap) * p.CinP + ci0;
+    // dwp[co][tap][ci]: for a fixed co the 32 lanes of a warp hit 32 consecutive ci -> one coalesced 128-byte reduction
+    float* out = p.dwp + (int64_t)tap * p.CinP + ci;
+    const int64_t co_stride = (int64_t)p.R * p.S * p.CinP;
 #pragma unroll
     for (int c = 0; c < BN; c += 16) {
       float v[16];
@@ -185,10 +194,10 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
-      if (co < p.Cout) {
+      if (ok) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (ci0 + c + j < p.CinP) atomicAdd(out + c + j, acc[c + j] + v[j]);
+          if (co0 + c + j < p.Cout) atomicAdd(out + (co0 + c + j) * co_stride, acc[c + j] + v[j]);
       }
     }
   }
@@ -229,9 +238,10 @@ static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_l
   p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp;
   choose_patch32(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
-  p.ci_tiles = ceil_div(d->Cin, BN);
+  p.chunks = d->Cin / 32;
+  p.groups = d->R * d->S * p.chunks;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int gx = ceil_div(d->Cout, 128), gy = d->R * d->S * p.ci_tiles;
+  const int gx = ceil_div(p.groups, 4), gy = ceil_div(d->Cout, BN);
   int want = ceil_div(kSMs * 2, gx * gy);
   int max_splits = ceil_div(total, 8);                 // at least 8 stages of work per CTA
   int splits = want < max_splits ? want : max_splits;
@@ -273,7 +283,7 @@ extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, co
   PVG_CHECK_ARG((((uintptr_t)x | (uintptr_t)g) & 15) == 0, "operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  const int cin = d->Cin;
+  const int cin = d->Cout;      // BN tiles the OUTPUT channels (roles swapped, see the header comment)
   if (d->nprod == 3) {
     PVG_CHECK_ARG(x_lo && g_lo, "nprod == 3 needs x_lo and g_lo");
     if (cin <= 32) rc = launch_wgrad<32, 3>(d, x, x_lo, g, g_lo, scratch, st);
