@@ -78,6 +78,9 @@ int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* ou
 int pvg_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 /* g = dy * act'(y) for an activation fused in a conv epilogue (y is the activation OUTPUT) */
 int pvg_act_bwd(const float* dy, const float* y, int act, float slope, float* g, int64_t n, void* stream);
+/* the same, also emitting the 3xTF32 planes of g in the same pass (hi may be NULL: truncation mode, see pvg_split_tf32) */
+int pvg_act_bwd_split(const float* dy, const float* y, int act, float slope, float* g, float* hi, float* lo, int64_t n,
+                      void* stream);
 
 /* ---- BatchNorm2d (training: per-call batch statistics; eval: running statistics), optionally preceded by
  *      avg_pool2d(2) and followed by (+residual) and an activation.  Replaces F.avg_pool2d + nn.BatchNorm2d +

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "pvg_channel_sum": [P, c_int64, c_int, P, P, P],
     "pvg_split_tf32": [P, P, P, c_int64, P],
     "pvg_act_bwd": [P, P, c_int, c_float, P, c_int64, P],
+    "pvg_act_bwd_split": [P, P, c_int, c_float, P, P, P, c_int64, P],
     "pvg_bn_stats": [P, c_int, c_int, c_int, c_int, P, P],
     "pvg_pool2_stats": [P, c_int, c_int, c_int, c_int, P, c_int, P, P],
     "pvg_bn_finalize": [P, c_int64, c_int, c_int, c_float, c_float, P, P, P, P, P],

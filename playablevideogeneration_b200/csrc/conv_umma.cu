@@ -21,6 +21,8 @@
 //                  epilogue warps into fp32 REGISTER accumulators (round-to-nearest adds) while the MMA warp continues
 //                  into a second TMEM buffer (ping-pong, tfull/tempty mbarriers).  The two correction terms, 2^-11
 //                  smaller, accumulate in a third TMEM buffer for the whole K loop and are added once at the end.
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace pvg {
@@ -29,25 +31,29 @@ int conv2d_fwd_simt(const pvg_conv_desc* d, const float* x, const float* w, cons
 
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
-constexpr int kChunk = 32;                 // channels per K chunk (128 B of fp32)
-constexpr int kABytes = kTileM * 128;      // 16 KB per A plane per stage
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int BN, int NPROD>
+// KC = channels per pipeline stage: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B: half the bytes per
+// stage -> twice the stages in the same shared memory, i.e. a deeper TMA prefetch for the latency-bound 3xTF32 tiles)
+template <int BN, int NPROD, int KC>
 struct Cfg {
   static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kRowBytes = KC * 4;
+  static constexpr int kABytes = kTileM * kRowBytes;
+  static constexpr int kBBytes = BN * kRowBytes;
+  static constexpr int kKSteps = KC / 8;                      // MMAs (K = 8) per operand pair and stage
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr bool kSplitAcc = NPROD == 3;               // see "split accum" in the header comment
-  static constexpr int kDrain = 8;                            // k-iterations (x4 MMAs) per TMEM accumulation chain
+  static constexpr int kDrain = 32 / kKSteps;                 // stages per TMEM accumulation chain (32 MMAs of the main term)
   static constexpr int kAccCols = kSplitAcc ? 3 * BN : BN;    // [main0 | main1 | correction] or [acc]
   static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+  static_assert(KC == 32 || KC == 16, "KC must be 16 or 32");
 };
 
 struct ConvParams {
@@ -59,11 +65,11 @@ struct ConvParams {
   float* y;
 };
 
-template <int BN, int NPROD>
+template <int BN, int NPROD, int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const ConvParams p) {
-  using C = Cfg<BN, NPROD>;
+  using C = Cfg<BN, NPROD, KC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -82,7 +88,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tile_n = t;
   const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
   const int co0 = blockIdx.y * BN;
-  const int chunks = p.Cin / kChunk;
+  const int chunks = p.Cin / KC;
   const int k_iters = p.R * p.S * chunks;
 
   if (warp == 0 && lane == 0) {
@@ -109,11 +115,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = stage_base + stage * C::kStageBytes;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-        tma_load_4d(st, &tmA, &full_bar[stage], cc * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
-        tma_load_2d(st + C::kPlanes * kABytes, &tmB, &full_bar[stage], k * kChunk, co0);
+        tma_load_4d(st, &tmA, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
+        tma_load_2d(st + C::kPlanes * C::kABytes, &tmB, &full_bar[stage], k * KC, co0);
         if (NPROD == 3) {
-          tma_load_4d(st + kABytes, &tmAlo, &full_bar[stage], cc * kChunk, w0 + s - p.pad, h0 + r - p.pad, n0);
-          tma_load_2d(st + 2 * kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * kChunk, co0);
+          tma_load_4d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * KC, co0);
         }
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
@@ -139,19 +145,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
-            const uint32_t a_hi = st, a_lo = st + kABytes;
-            const uint32_t b_hi = st + 2 * kABytes, b_lo = b_hi + C::kBBytes;
+            const uint32_t a_hi = st, a_lo = st + C::kABytes;
+            const uint32_t b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_tf32(corr, make_kmajor_sw128_desc(a_lo + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, corr_acc);
+            for (int ks = 0; ks < C::kKSteps; ++ks) {
+              umma_tf32(corr, make_kmajor_desc<KC>(a_lo + ks * 32), make_kmajor_desc<KC>(b_hi + ks * 32), idesc, corr_acc);
               corr_acc = 1;
             }
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_tf32(corr, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_lo + ks * 32), idesc, 1);
+            for (int ks = 0; ks < C::kKSteps; ++ks)
+              umma_tf32(corr, make_kmajor_desc<KC>(a_hi + ks * 32), make_kmajor_desc<KC>(b_lo + ks * 32), idesc, 1);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_tf32(main_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, main_started);
+            for (int ks = 0; ks < C::kKSteps; ++ks) {
+              umma_tf32(main_acc, make_kmajor_desc<KC>(a_hi + ks * 32), make_kmajor_desc<KC>(b_hi + ks * 32), idesc, main_started);
               main_started = 1;
             }
             umma_commit(&empty_bar[stage]);     // slot reusable once these MMAs have read it
@@ -165,10 +171,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
-          const uint32_t a_hi = st, b_hi = st + kABytes;
+          const uint32_t a_hi = st, b_hi = st + C::kABytes;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_tf32(tmem_acc, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, accumulate);
+          for (int ks = 0; ks < C::kKSteps; ++ks) {
+            umma_tf32(tmem_acc, make_kmajor_desc<KC>(a_hi + ks * 32), make_kmajor_desc<KC>(b_hi + ks * 32), idesc, accumulate);
             accumulate = 1;
           }
           umma_commit(&empty_bar[stage]);
@@ -277,7 +283,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_nhwc_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, int box_c, int tw, int th, int tn, bool atom32) {
+int encode_nhwc_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, int box_c, int tw, int th, int tn, bool atom32,
+                    bool sw64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return -3; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -285,24 +292,24 @@ int encode_nhwc_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, 
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r)); return -3; }
   return 0;
 }
 
-static int encode_act_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, int tw, int th, int tn) {
-  return encode_nhwc_map(m, x, N, H, W, C, kChunk, tw, th, tn);
+static int encode_act_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, int kc, int tw, int th, int tn) {
+  return encode_nhwc_map(m, x, N, H, W, C, kc, tw, th, tn, false, kc == 16);
 }
 
-static int encode_w_map(CUtensorMap* m, const float* w, int Cout, int K, int bn) {
+static int encode_w_map(CUtensorMap* m, const float* w, int Cout, int K, int bn, int kc) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return -3; }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)bn};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); return -3; }
   return 0;
 }
@@ -320,10 +327,10 @@ static void choose_patch(int N, int H, int W, int* tw, int* th, int* tn) {
   }
 }
 
-template <int BN, int NPROD>
+template <int BN, int NPROD, int KC>
 static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
                        const float* bias, float* y, cudaStream_t st) {
-  using C = Cfg<BN, NPROD>;
+  using C = Cfg<BN, NPROD, KC>;
   ConvParams p;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y;
@@ -332,37 +339,51 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
   const int K = d->R * d->S * d->Cin;
   int rc;
-  if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
-  if ((rc = encode_w_map(&tmB, w, d->Cout, K, BN))) return rc;
+  if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, KC, p.tw, p.th, p.tn))) return rc;
+  if ((rc = encode_w_map(&tmB, w, d->Cout, K, BN, KC))) return rc;
   if (NPROD == 3) {
-    if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
-    if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, BN))) return rc;
+    if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, KC, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, BN, KC))) return rc;
   } else {
     tmAlo = tmA; tmBlo = tmB;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    PVG_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    PVG_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)ceil_div(d->Cout, BN));
-  conv_umma_kernel<BN, NPROD><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmAlo, tmB, tmBlo, p);
+  conv_umma_kernel<BN, NPROD, KC><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmAlo, tmB, tmBlo, p);
   PVG_LAUNCH_OK();
   return 0;
+}
+
+// PVG_KC=16 selects the 16-channel (SWIZZLE_64B) stage for the 3xTF32 128-wide tiles (A/B experiment knob)
+static int stage_channels() {
+  static int kc = 0;
+  if (!kc) {
+    const char* e = getenv("PVG_KC");
+    kc = (e && atoi(e) == 16) ? 16 : 32;
+  }
+  return kc;
 }
 
 template <int NPROD>
 static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
                        const float* bias, float* y, cudaStream_t st) {
   const int co = d->Cout;
-  if (co <= 16) return launch_umma<16, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
-  if (co <= 32) return launch_umma<32, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
-  if (co <= 64) return launch_umma<64, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
-  if (co <= 80) return launch_umma<80, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
-  if constexpr (NPROD == 1) {
-    if (co % 256 == 0) return launch_umma<256, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (co <= 16) return launch_umma<16, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (co <= 32) return launch_umma<32, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (co <= 64) {
+    if (NPROD == 3 && stage_channels() == 16) return launch_umma<64, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
+    return launch_umma<64, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   }
-  return launch_umma<128, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (co <= 80) return launch_umma<80, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+  if constexpr (NPROD == 1) {
+    if (co % 256 == 0) return launch_umma<256, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+  }
+  if (NPROD == 3 && stage_channels() == 16) return launch_umma<128, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
+  return launch_umma<128, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
 }
 
 }  // namespace pvg
@@ -376,7 +397,7 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const floa
   PVG_CHECK_ARG(d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "only odd 'same' kernels are supported");
   cudaStream_t st = (cudaStream_t)stream;
   int algo = d->algo;
-  const bool umma_ok = (d->Cin % kChunk) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
+  const bool umma_ok = (d->Cin % 32) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
   if (algo == PVG_ALGO_AUTO) algo = (umma_ok && pvg_has_umma()) ? PVG_ALGO_UMMA : PVG_ALGO_SIMT;
   if (algo == PVG_ALGO_SIMT) return conv2d_fwd_simt(d, x, w, bias, y, st);
   PVG_CHECK_ARG(umma_ok, "tensor-core path needs Cin % 32 == 0 and 16-byte aligned operands");

@@ -511,6 +511,30 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     g[i] = __ldg(dy + i) * act_bwd_from_out(__ldg(y + i), act, slope);
 }
 
+// g = dy * act'(y) and, in the same pass, the 3xTF32 residual plane of g (lo = g - tf32(g); hi optional, see split)
+__global__ void __launch_bounds__(256) act_bwd_split_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act,
+                                                            float slope, float* __restrict__ g, float* __restrict__ hi,
+                                                            float* __restrict__ lo, int64_t n) {
+  const bool rna = hi != nullptr;
+  const int64_t q = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 d = ldg4(dy + 4 * i), o = ldg4(y + 4 * i);
+    float4 v = make_float4(d.x * act_bwd_from_out(o.x, act, slope), d.y * act_bwd_from_out(o.y, act, slope),
+                           d.z * act_bwd_from_out(o.z, act, slope), d.w * act_bwd_from_out(o.w, act, slope));
+    float4 h = make_float4(tf32_part(v.x, rna), tf32_part(v.y, rna), tf32_part(v.z, rna), tf32_part(v.w, rna));
+    stg4(g + 4 * i, v);
+    if (hi) stg4(hi + 4 * i, h);
+    stg4(lo + 4 * i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+  }
+  for (int64_t i = q * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = dy[i] * act_bwd_from_out(y[i], act, slope);
+    float h = tf32_part(v, rna);
+    g[i] = v;
+    if (hi) hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(kRedThreads) channel_sum_kernel(const float* __restrict__ x, int64_t M, int C,
                                                                   double* __restrict__ out) {
@@ -767,6 +791,14 @@ int pvg_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream
 
 int pvg_act_bwd(const float* dy, const float* y, int act, float slope, float* g, int64_t n, void* stream) {
   act_bwd_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, n);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_act_bwd_split(const float* dy, const float* y, int act, float slope, float* g, float* hi, float* lo, int64_t n,
+                      void* stream) {
+  PVG_CHECK_ARG((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)g | (uintptr_t)lo | (uintptr_t)hi) & 15) == 0, "pointers must be 16-byte aligned");
+  act_bwd_split_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, hi, lo, n);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -85,14 +85,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row (1024 B) swizzle atoms stacked along M/N.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+// K-major swizzled operand tile of fp32/tf32: rows of KC*4 bytes (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row
+// swizzle atoms stacked along M/N.
+template <int KC>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, 16-byte units
   d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 1024 B between 8-row groups
+  d |= (uint64_t)((8 * KC * 4) >> 4) << 32;       // stride byte offset between 8-row groups (1024 B or 512 B)
   d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  d |= (uint64_t)(KC == 32 ? 2 : 4) << 61;        // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -134,6 +136,6 @@ EncodeTiledFn get_encode_fn();
 // 4-D map over an NHWC fp32 tensor with box {box_c, tw, th, tn}, zero OOB fill; 128B swizzle with 16-byte atoms
 // (K-major operands) or 32-byte atoms (atom32 = true, MN-major tf32 operands)
 int encode_nhwc_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, int box_c, int tw, int th, int tn,
-                    bool atom32 = false);
+                    bool atom32 = false, bool sw64 = false);
 
 }  // namespace pvg

@@ -212,14 +212,23 @@ class Conv2dFn(torch.autograd.Function):
         cout, _, r, s = weight.shape
         n, cin_p, h, w = x.shape
         dy = nhwc(dy)
+        nprod = 3 if _precision == "tf32x3" else 1
+        g_split = [None]
         if act != ACT_NONE:
             g = torch.empty_like(dy)
-            call("pvg_act_bwd", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), dy.numel(), _stream())
+            wants_split = nprod == 3 and ((ctx.needs_input_grad[0] and cout % 32 == 0) or
+                                          (ctx.needs_input_grad[1] and cin_p % 32 == 0 and cout % 4 == 0))
+            if wants_split:          # activation backward and the hi/lo split of g in one pass
+                lo = torch.empty_like(dy)
+                hi = None if tf32_truncates() else torch.empty_like(dy)
+                call("pvg_act_bwd_split", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), _p(hi), lo.data_ptr(),
+                     dy.numel(), _stream())
+                g_split[0] = (g if hi is None else hi, lo)
+            else:
+                call("pvg_act_bwd", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), dy.numel(), _stream())
         else:
             g = dy
         dx = dw = db = None
-        nprod = 3 if _precision == "tf32x3" else 1
-        g_split = [None]
 
         def split_g():
             if g_split[0] is None:
