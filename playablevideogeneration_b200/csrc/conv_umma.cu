@@ -81,13 +81,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // tile coordinates
-  int t = blockIdx.x;
+  // tile coordinates: the N tile index varies fastest, so the CTAs that re-read one activation patch run back to back
+  // and hit L2 (with N-major order the second pass over a > 126 MB tensor came from DRAM again: 4x traffic on conv4)
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int n_tile = blockIdx.x % n_tiles;
+  int t = blockIdx.x / n_tiles;
   const int tile_w = t % p.tiles_w; t /= p.tiles_w;
   const int tile_h = t % p.tiles_h; t /= p.tiles_h;
   const int tile_n = t;
   const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
-  const int co0 = blockIdx.y * BN;
+  const int co0 = n_tile * BN;
   const int chunks = p.Cin / KC;
   const int k_iters = p.R * p.S * chunks;
 
@@ -352,7 +355,7 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
     PVG_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, NPROD, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)ceil_div(d->Cout, BN));
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n * ceil_div(d->Cout, BN)));
   conv_umma_kernel<BN, NPROD, KC><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmAlo, tmB, tmBlo, p);
   PVG_LAUNCH_OK();
   return 0;

@@ -34,7 +34,13 @@ def _err(got, ref):
 
 def _close(name, got, ref, rel, abs_=0.0):
     e, scale = _err(got, ref)
-    _log(name, max_abs_err=e, ref_absmax=scale, tol=rel * scale + abs_)
+    extra = {}
+    if e > rel * scale + abs_:          # where and how many: tells a systematic error from a localised one
+        d = (got.detach().float().cpu() - ref.detach().float()).abs()
+        idx = int(d.reshape(-1).argmax())
+        extra = dict(bad=int((d > rel * scale + abs_).sum()), numel=d.numel(), argmax=idx,
+                     got=float(got.detach().float().cpu().reshape(-1)[idx]), ref=float(ref.detach().float().reshape(-1)[idx]))
+    _log(name, max_abs_err=e, ref_absmax=scale, tol=rel * scale + abs_, **extra)
     assert e <= rel * scale + abs_, f"{name}: max abs err {e:.3e} > {rel:g} * {scale:.3e} + {abs_:g}"
 
 

@@ -33,6 +33,8 @@ case $s in
   convbench) run convbench 600 python tools/conv_bench.py tf32x3 5 ;;
   convbench1) run convbench1 600 python tools/conv_bench.py tf32 5 ;;
   ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_umma_kernel -c 10 -f -o $OUT/prof_conv python tools/conv_bench.py tf32x3 1 ;;
+  allkernels2) run allkernels2 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider ;;
+  ncu_traffic) run ncu_traffic 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_umma_kernel -s 800 -c 790 --csv --log-file $OUT/conv_traffic.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph ;;
   flaky) run flaky 300 python tools/flaky_probe.py ;;
   convbench16) PVG_KC=16 run convbench16 600 python tools/conv_bench.py tf32x3 5 ;;
   kernels16) PVG_KC=16 run kernels16 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
