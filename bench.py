@@ -285,8 +285,13 @@ def main():
             wms = sum(a.elapsed_time(b) for a, b, _ in wprof)
             wg = dict(kernel="conv_wgrad_umma_kernel", launches_per_step=len(wprof), ms_per_step=wms,
                       achieved=sum(f for _, _, f in wprof) / (wms * 1e-3) / 1e12 if wms > 0 else 0.0, unit="TFLOP/s")
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        if args.precision == "tf32x3" and args.workload == "bair256_b8_t16" and os.path.isfile(tpath):
+            traffic = json.load(open(tpath))["traffic_bytes_per_launch"]      # from the committed ncu capture of this command
         roof = dict(bound="tensor", kernel="conv_umma_kernel (tcgen05 kind::tf32" + (", 3 MMAs per k-step" if args.precision == "tf32x3" else "") + ")",
-                    achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=None,
+                    achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=traffic,
+                    traffic_source="profiles/r01_conv_traffic.json (ncu dram__bytes_read+write per launch, averaged over the step's launches)" if traffic else None,
                     launches_per_step=len(prof), avg_launch_us=tot_ms * 1e3 / len(prof), ms_per_step=tot_ms,
                     share_of_step=tot_ms / ms_dev, peak_source=peaks["source"], weight_gradient=wg,
                     measured="CUDA events around each launch in one extra eager (non-graph) step after the timed region",
