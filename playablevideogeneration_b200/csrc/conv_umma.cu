@@ -270,6 +270,218 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster compute a 256-pixel x 128-channel tile with ONE MMA stream.
+// Each CTA stages its own 128-pixel A patch and HALF of the weight tile (64 rows), so every MMA reads 4 KB (A) + 2 KB (B)
+// of shared memory per SM instead of 4 + 4 KB and TMA fills 48 KB instead of 64 KB per k-iteration: the shared-memory
+// bandwidth bound (profiles/r01_conv_umma_ncu_full.md) moves from 60 % to ~80 % tensor-pipe utilisation, and the smaller
+// stage buys a 4th pipeline stage.  Protocol: both CTAs' TMA loads credit the LEADER's `full` barrier; the leader's MMA
+// thread issues tcgen05.mma.cta_group::2 (M = 256: rows 0-127 land in the leader's TMEM, 128-255 in the peer's) and its
+// commits are multicast to the `empty` / `tfull` barriers of BOTH CTAs; each CTA's epilogue drains its own TMEM and
+// arrives on the leader's `tempty` barrier (256 arrivals).
+// ---------------------------------------------------------------------------------------------------------------
+template <int NPROD>
+struct Cfg2 {
+  static constexpr int BN = 128;                              // channels per pair tile
+  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
+  static constexpr int kABytes = kTileM * 128;                // own 128-pixel patch, 32 channels
+  static constexpr int kBBytes = (BN / 2) * 128;              // own half of the weight tile
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr bool kSplitAcc = NPROD == 3;
+  static constexpr int kDrain = 8;
+  static constexpr int kAccCols = kSplitAcc ? 3 * BN : BN;
+  static constexpr int kTmemCols = kAccCols <= 128 ? 128 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int NPROD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const ConvParams p) {
+  using C = Cfg2<NPROD>;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int cid = blockIdx.x >> 1;
+  const int n_tile = cid % n_tiles;
+  int t = (cid / n_tiles) * 2 + (int)rank;                 // this CTA's 128-pixel tile (may lie past the end: all OOB)
+  const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+  const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+  const int tile_n = t;
+  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = tile_n * p.tn;
+  const int co0 = n_tile * BN;
+  const int chunks = p.Cin / 32;
+  const int k_iters = p.R * p.S * chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    if (NPROD == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 256); mbar_init(&tempty_bar[1], 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem2_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int k = 0; k < k_iters; ++k) {
+        const int tap = k / chunks, cc = k - tap * chunks;
+        const int r = tap / p.S, s = tap - r * p.S;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = stage_base + stage * C::kStageBytes;
+        if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);      // bytes of BOTH CTAs land on this barrier
+        tma2_load_4d(st, &tmA, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0);
+        tma2_load_2d(st + C::kPlanes * C::kABytes, &tmB, &full_bar[stage], k * 32, co0 + (int)rank * (BN / 2));
+        if (NPROD == 3) {
+          tma2_load_4d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma2_load_2d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * 32, co0 + (int)rank * (BN / 2));
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32_m256<BN>();
+      int stage = 0; uint32_t phase = 0;
+      if constexpr (C::kSplitAcc) {
+        const uint32_t corr = tmem_acc + 2 * BN;
+        uint32_t corr_acc = 0;
+        const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
+        int k = 0;
+        for (int per = 0; per < periods; ++per) {
+          const int b = per & 1;
+          mbar_wait(&tempty_bar[b], ((per >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t main_acc = tmem_acc + b * BN;
+          const int k_end = min(k + C::kDrain, k_iters);
+          uint32_t main_started = 0;
+          for (; k < k_end; ++k) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
+            const uint32_t a_hi = st, a_lo = st + C::kABytes;
+            const uint32_t b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma2_tf32(corr, make_kmajor_desc<32>(a_lo + ks * 32), make_kmajor_desc<32>(b_hi + ks * 32), idesc, corr_acc);
+              corr_acc = 1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma2_tf32(corr, make_kmajor_desc<32>(a_hi + ks * 32), make_kmajor_desc<32>(b_lo + ks * 32), idesc, 1);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma2_tf32(main_acc, make_kmajor_desc<32>(a_hi + ks * 32), make_kmajor_desc<32>(b_hi + ks * 32), idesc, main_started);
+              main_started = 1;
+            }
+            umma2_commit_both(&empty_bar[stage]);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          umma2_commit_both(&tfull_bar[b]);
+        }
+      } else {
+        uint32_t accumulate = 0;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
+          const uint32_t a_hi = st, b_hi = st + C::kABytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma2_tf32(tmem_acc, make_kmajor_desc<32>(a_hi + ks * 32), make_kmajor_desc<32>(b_hi + ks * 32), idesc, accumulate);
+            accumulate = 1;
+          }
+          umma2_commit_both(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_both(&tfull_bar[0]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs; each CTA owns its 128 TMEM lanes) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int wi = row % p.tw;
+    const int hi = (row / p.tw) % p.th;
+    const int ni = row / (p.tw * p.th);
+    const int ow = w0 + wi, oh = h0 + hi, on = n0 + ni;
+    const bool valid = ow < p.W && oh < p.H && on < p.N;
+    float* yrow = p.y + (((int64_t)on * p.H + oh) * p.W + ow) * p.Cout;
+    const bool vec_ok = (p.Cout % 4) == 0;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    if constexpr (C::kSplitAcc) {
+      const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
+      for (int per = 0; per < periods; ++per) {
+        const int b = per & 1;
+        mbar_wait(&tfull_bar[b], (per >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN; c += 16) {
+          float v[16];
+          tmem_ld16(tmem_acc + lane_base + (uint32_t)(b * BN + c), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c + j] += v[j];
+        }
+        tc_fence_before();
+        mbar_arrive_leader(&tempty_bar[b]);
+      }
+    } else {
+      mbar_wait(&tfull_bar[0], 0);
+      tc_fence_after();
+    }
+    constexpr int corr_col = C::kSplitAcc ? 2 * BN : 0;
+#pragma unroll
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_acc + lane_base + (uint32_t)(corr_col + c), v);
+      const int co = co0 + c;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float bsv = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
+        v[j] = act_fwd(acc[c + j] + v[j] + bsv, p.act, p.slope);
+      }
+      if (valid && co < p.Cout) {
+        if (vec_ok && co + 16 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (co + j < p.Cout) yrow[co + j] = v[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // the peer's shared memory / TMEM must stay alive until every MMA that reads it has retired
+  if (warp == 1) tmem2_dealloc(tmem_acc, C::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 EncodeTiledFn get_encode_fn() {
@@ -361,6 +573,49 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
   return 0;
 }
 
+template <int NPROD>
+static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+                        const float* bias, float* y, cudaStream_t st) {
+  using C = Cfg2<NPROD>;
+  ConvParams p;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y;
+  choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
+  p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  const int K = d->R * d->S * d->Cin;
+  int rc;
+  if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
+  if ((rc = encode_w_map(&tmB, w, d->Cout, K, C::BN / 2, 32))) return rc;
+  if (NPROD == 3) {
+    if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, C::BN / 2, 32))) return rc;
+  } else {
+    tmAlo = tmA; tmBlo = tmB;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PVG_CUDA_OK(cudaFuncSetAttribute(conv_umma2_kernel<NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pairs = ceil_div(m_tiles, 2);
+  dim3 grid((unsigned)(pairs * ceil_div(d->Cout, C::BN) * 2));
+  conv_umma2_kernel<NPROD><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmAlo, tmB, tmBlo, p);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+// PVG_2CTA=1 routes the >= 128-channel-wide tiles through the CTA-pair kernel
+static int use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PVG_2CTA");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return v;
+}
+
 // PVG_KC=16 selects the 16-channel (SWIZZLE_64B) stage for the 3xTF32 128-wide tiles (A/B experiment knob)
 static int stage_channels() {
   static int kc = 0;
@@ -383,8 +638,9 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
   }
   if (co <= 80) return launch_umma<80, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   if constexpr (NPROD == 1) {
-    if (co % 256 == 0) return launch_umma<256, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+    if (co % 256 == 0 && !use_pairs()) return launch_umma<256, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   }
+  if (use_pairs()) return launch_umma2<NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
   if (NPROD == 3 && stage_channels() == 16) return launch_umma<128, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
   return launch_umma<128, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
 }

@@ -35,6 +35,9 @@ case $s in
   ncu_conv) run ncu_conv 900 ncu --set full --clock-control none --import-source on -k regex:conv_umma_kernel -c 10 -f -o $OUT/prof_conv python tools/conv_bench.py tf32x3 1 ;;
   allkernels2) run allkernels2 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider ;;
   ncu_traffic) run ncu_traffic 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_umma_kernel -s 800 -c 790 --csv --log-file $OUT/conv_traffic.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph ;;
+  pairs_k) PVG_2CTA=1 run pairs_k 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "umma_forward or conv_backward" -p no:cacheprovider ;;
+  pairs_b) PVG_2CTA=1 run pairs_b 300 python tools/conv_bench.py tf32x3 5 ;;
+  pairs_b1) PVG_2CTA=1 run pairs_b1 300 python tools/conv_bench.py tf32 5 ;;
   flaky) run flaky 300 python tools/flaky_probe.py ;;
   convbench16) PVG_KC=16 run convbench16 600 python tools/conv_bench.py tf32x3 5 ;;
   kernels16) PVG_KC=16 run kernels16 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
