@@ -169,6 +169,15 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
+def _hard_exit(world):
+    """Multi-rank runs leave through os._exit: tearing down NCCL communicators that are referenced by a captured CUDA graph
+    at interpreter shutdown was observed to hang (rank 0 printed its line, then the job sat until the driver's timeout)."""
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     args = parse()
     w = WORKLOADS[args.workload]
@@ -298,6 +307,7 @@ def main():
                     note="achieved = algorithmic conv FLOPs (2*N*H*W*Cout*R*S*Cin, unpadded) / CUDA-event time of the launches; "
                          "peak is the measured bf16 cuBLAS figure - kind::tf32 tops out at half of it, 3xTF32 at a sixth")
     if rank != 0:
+        _hard_exit(world)
         return
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
@@ -315,8 +325,7 @@ def main():
                          d2h_bytes_per_step=8 * world, ms_per_step=ms_e2e, last_loss=loss_host),
                 gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu_base)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _hard_exit(world)
 
 
 if __name__ == "__main__":

@@ -347,6 +347,8 @@ class GumbelSoftmax(nn.Module):
 class CentroidEstimator(nn.Module):
     """model/layers/centroid_estimator.py:5-94."""
 
+    process_group = None        # data-parallel job: sum numerator / denominator over ranks = the gathered-batch update
+
     def __init__(self, centroids_count, space_dimensions, alpha):
         super().__init__()
         self.centroids_count, self.space_dimensions, self.alpha = centroids_count, space_dimensions, alpha
@@ -361,7 +363,12 @@ class CentroidEstimator(nn.Module):
         with torch.no_grad():
             means = points_priors.reshape(-1, 2, self.space_dimensions)[:, 0]
             assign = centroid_assignments.reshape(-1, self.centroids_count)
-            est = (means.unsqueeze(1) * assign.unsqueeze(-1)).sum(0) / assign.sum(0).unsqueeze(-1)
+            num, den = (means.unsqueeze(1) * assign.unsqueeze(-1)).sum(0), assign.sum(0).unsqueeze(-1)
+            if self.process_group is not None:
+                packed = torch.cat([num, den], dim=1)
+                torch.distributed.all_reduce(packed, group=self.process_group)
+                num, den = packed[:, :-1], packed[:, -1:]
+            est = num / den
             # the reference rebinds ``.data``; an in-place copy is numerically identical and keeps the buffer address
             # stable (CUDA-graph replays read and write the same storage)
             self.estimated_centroids.data.copy_(self.estimated_centroids * (1 - self.alpha) + est * self.alpha)

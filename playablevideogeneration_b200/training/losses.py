@@ -189,8 +189,27 @@ class FixedMatrixEstimator(nn.Module):
         return out
 
 
+class _AllReduceSum(torch.autograd.Function):
+    """Sum over the ranks of a data-parallel job.  Every rank then evaluates the SAME loss on the reduced value, so the
+    gradient w.r.t. the local addend is the incoming gradient unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        y = x.clone()
+        torch.distributed.all_reduce(y, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 class MutualInformationLoss(nn.Module):
-    """losses.py:238-302."""
+    """losses.py:238-302.  ``process_group``: under data parallelism the reference evaluates this loss on the GATHERED
+    batch (trainer.py:471-473 runs on GPU0 after DataParallel's gather); the joint matrix is a plain sum over samples,
+    so summing the A x A partial matrices over the ranks (49 floats) reproduces it exactly."""
+
+    process_group = None
 
     def compute_joint_probability_matrix(self, distribution_1, distribution_2):
         dim = distribution_1.size(-1)
@@ -198,6 +217,8 @@ class MutualInformationLoss(nn.Module):
         d1, d2 = distribution_1.reshape(-1, dim), distribution_2.reshape(-1, dim)
         assert d1.size(0) == d2.size(0)
         p = (d1.unsqueeze(2) * d2.unsqueeze(1)).sum(dim=0)
+        if self.process_group is not None:
+            p = _AllReduceSum.apply(p, self.process_group)
         p = (p + p.t()) / 2.0
         return p / p.sum()
 

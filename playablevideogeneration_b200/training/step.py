@@ -85,6 +85,10 @@ class TrainStep:
         self.global_step = 0
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        if self.world > 1:
+            # the two batch-coupled statistics: MI joint matrix and centroid EMA see the global batch
+            self.mutual_information_loss.process_group = process_group
+            self.module.centroid_estimator.process_group = process_group
         self._capturing = False
         self._graph_runs = []
         self._hyper_dev_buf = torch.zeros((16, 7), dtype=torch.float32, device=dev)
@@ -145,6 +149,11 @@ class TrainStep:
                  + lw["action_directions_kl_lambda" + sfx] * kl_dir
                  + lw["action_mutual_information_lambda" + sfx] * mi
                  + lw["action_state_distribution_kl_lambda" + sfx] * kl_state)
+        if self.world > 1:
+            # every rank holds the GLOBAL MI value but differentiates it through its local samples only, and gradients are
+            # averaged over ranks: scale this term's gradient (not its value) by the world size
+            lam = lw["action_mutual_information_lambda" + sfx]
+            total = total + (self.world - 1) * lam * (mi - mi.detach())
         if pretraining:
             hid_rec = self.hidden_states_loss(hidden, rec_hidden.detach())
             total = total + lw["hidden_states_rec_lambda_pretraining"] * hid_rec

@@ -68,3 +68,38 @@ def test_two_rank_gloo_step_keeps_replicas_in_sync(tmp_path):
     assert r["ranks_differ"], "shards should produce different local gradients"
     assert r["reduced_is_sum"], "arena.grad after the all-reduce must be the sum of the per-rank gradients (Adam scales by 1/world)"
     assert r["sync"], "parameters diverged across ranks"
+
+
+def _mi_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from playablevideogeneration_b200.training.losses import MutualInformationLoss
+    g = torch.Generator().manual_seed(3)
+    p1 = torch.softmax(torch.randn(4, 5, 7, generator=g), -1)
+    p2 = torch.softmax(torch.randn(4, 5, 7, generator=g), -1)
+    full = MutualInformationLoss()
+    a = p1.clone().requires_grad_(True)
+    ref = full(a, p2)                                      # "gathered batch" on one device (the reference's semantics)
+    ref.backward()
+    sharded = MutualInformationLoss()
+    sharded.process_group = dist.group.WORLD
+    sl = slice(rank * 2, rank * 2 + 2)
+    b = p1[sl].clone().requires_grad_(True)
+    got = sharded(b, p2[sl])
+    got.backward()
+    # the MI value is a cancellation-dominated O(1e-2) number: compare on the scale of its terms (|P log P| ~ 0.1)
+    ok = bool(abs(float(got) - float(ref)) <= 2e-7) and bool(torch.allclose(b.grad, a.grad[sl], rtol=1e-4, atol=2e-7))
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if rank == 0:
+        torch.save(dict(ok=all(flags)), out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_mutual_information_equals_gathered_batch(tmp_path):
+    """The 7x7 joint-matrix all-reduce makes the per-rank MI loss (value and local gradients) identical to the loss on
+    the gathered batch that the reference's DataParallel trainer computes."""
+    out = str(tmp_path / "mi.pt")
+    mp.spawn(_mi_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]
