@@ -606,14 +606,20 @@ static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_l
   return 0;
 }
 
-// PVG_2CTA=1 routes the >= 128-channel-wide tiles through the CTA-pair kernel
-static int use_pairs() {
-  static int v = -1;
-  if (v < 0) {
+// The CTA-pair kernel pays two cluster barriers and a pair-wide TMEM allocation per tile; measured on B200
+// (profiles/r01_conv_bench_pairs.json) it wins by ~20 % on the K-deep layers (VGG conv4/conv5: 144 k-iterations) and is
+// neutral below ~70 k-iterations, so it is used for deep-K tiles with enough M tiles to fill the machine twice.
+// PVG_2CTA=1 / 0 forces it on / off.
+static bool use_pairs(const pvg_conv_desc* d) {
+  static int forced = -2;
+  if (forced == -2) {
     const char* e = getenv("PVG_2CTA");
-    v = (e && atoi(e) == 1) ? 1 : 0;
+    forced = e ? atoi(e) : -1;
   }
-  return v;
+  if (forced >= 0) return forced == 1;
+  const int k_iters = d->R * d->S * (d->Cin / 32);
+  const int64_t m_tiles = ((int64_t)d->N * d->H * d->W + 127) / 128;
+  return k_iters >= 96 && m_tiles >= 2 * kSMs;
 }
 
 // PVG_KC=16 selects the 16-channel (SWIZZLE_64B) stage for the 3xTF32 128-wide tiles (A/B experiment knob)
@@ -638,9 +644,9 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
   }
   if (co <= 80) return launch_umma<80, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   if constexpr (NPROD == 1) {
-    if (co % 256 == 0 && !use_pairs()) return launch_umma<256, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+    if (co % 256 == 0 && !use_pairs(d)) return launch_umma<256, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   }
-  if (use_pairs()) return launch_umma2<NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  if (use_pairs(d)) return launch_umma2<NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
   if (NPROD == 3 && stage_channels() == 16) return launch_umma<128, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
   return launch_umma<128, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
 }
