@@ -28,7 +28,7 @@ case $s in
   diag_fp32) run diag_fp32 600 python tools/grad_diag.py full_bair_feedback fp32 ;;
   diag_tf32x3) run diag_tf32x3 600 python tools/grad_diag.py full_bair_feedback tf32x3 ;;
   allkernels) run allkernels 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -p no:cacheprovider ;;
-  bench2) run bench2 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline ;;
+  bench2) run bench2 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-cpu-baseline ;;
   bench_nograph) run bench_nograph 600 python bench.py --steps 3 --warmup 2 --no-graph --no-cpu-baseline ;;
   convbench) run convbench 600 python tools/conv_bench.py tf32x3 5 ;;
   convbench1) run convbench1 600 python tools/conv_bench.py tf32 5 ;;
