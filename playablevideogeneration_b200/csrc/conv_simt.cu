@@ -167,7 +167,12 @@ __global__ void __launch_bounds__(THREADS) conv_wgrad_simt_kernel(const float* _
   }
 }
 
+int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+
 int conv2d_fwd_simt(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+  // image-facing layers (3/12 channels on one side) have dedicated direct kernels (conv_direct.cu)
+  const int taken = conv2d_fwd_direct(d, x, w, bias, y, st);
+  if (taken != 0) return taken < 0 ? taken : 0;
   int64_t M = (int64_t)d->N * d->H * d->W;
   if (d->Cout <= 16) {
     dim3 grid((unsigned)ceil_div64(M, BM), ceil_div(d->Cout, 16));
