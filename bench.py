@@ -23,6 +23,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "frames/sec (train step, 256x256x3, seq=16)"
+
 WORKLOADS = {
     # name: (config kind, reduced, H, W, S, B per GPU, T, gt_init)
     "bair256_b8_t16": dict(config="bair", reduced=False, H=256, W=256, S=1, B=8, T=16, gt_init=6),
@@ -161,10 +163,13 @@ def run_reference(args, w):
     if rank != 0:
         return
     cb, mean = cpu_reference_step_time(w, args.cpu_sample_frames, max(1, args.steps), max(0, args.warmup))
-    line = dict(impl="reference", metric="frames/sec (train step)", value=cb["value"], unit="frames/s", n_gpus=args.gpus,
+    line = dict(impl="reference", metric=METRIC, value=cb["value"], unit="frames/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=mean * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=args.workload, note="reference algorithm on host CPU cores; bounded sample: " + cb["sample"]),
+                config=dict(workload=args.workload, per_gpu_batch=w["B"], seq_len=w["T"], frame=f"{w['H']}x{w['W']}x3",
+                            gt_init=w["gt_init"],
+                            note="reference algorithm (CPU oracle port) on the host cores; each step is a bounded sample of "
+                                 "the workload: " + cb["sample"]),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -312,7 +317,7 @@ def main():
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_step_time(w, args.cpu_sample_frames, 1, 0)
-    line = dict(metric="frames/sec (train step, 256x256x3, seq=16)", value=frames_per_step / (ms_dev * 1e-3), unit="frames/s",
+    line = dict(metric=METRIC, value=frames_per_step / (ms_dev * 1e-3), unit="frames/s",
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype={"tf32x3": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "tf32": "tf32",
                                          "fp32": "f32"}[args.precision],
