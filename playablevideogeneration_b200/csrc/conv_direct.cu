@@ -6,6 +6,8 @@
 //   conv_small_cout : Cout <= 4, Cin % 4 == 0             (tanh heads 128/64/32 -> 3 incl. the 7x7, data gradients of the
 //                     stems: 16 -> 3S, 64 -> 3)
 // Weights arrive in the common pack [Cout][R][S][Cin] (pvg_pack_conv_weight, unrounded fp32).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pvg {
@@ -132,6 +134,9 @@ int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, co
   const unsigned grid = (unsigned)ceil_div64(M, kDThreads);
   const int K = d->R * d->S * d->Cin;
   if (d->R != d->S) return 0;
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("PVG_NO_DIRECT"); disabled = (e && atoi(e) == 1) ? 1 : 0; }
+  if (disabled) return 0;
   if ((d->Cin == 3 || d->Cin == 12) && d->Cout % 4 == 0 && (size_t)K * d->Cout * 4 <= 96 * 1024) {
     const size_t smem = (size_t)K * d->Cout * 4;
 #define PVG_LAUNCH_CIN(CIN, KS)                                                                                          \

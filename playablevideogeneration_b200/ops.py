@@ -115,7 +115,7 @@ def _conv_algo(cin_phys: int, cout: int = 1 << 30) -> Tuple[int, int]:
     """(algo, nprod) for a conv whose A operand has cin_phys physical channels and which produces cout channels.
     The CUDA-core path (fp32, incl. the direct kernels of conv_direct.cu) takes the image-facing layers: A operands that
     are not a multiple of 32 channels wide, and outputs of <= 4 channels (tanh heads, gradients w.r.t. images)."""
-    if _precision == "fp32" or cin_phys % 32 != 0 or cout <= 4:
+    if _precision == "fp32" or cin_phys % 32 != 0 or (cout <= 4 and os.environ.get("PVG_NO_DIRECT") != "1"):
         return ALGO_SIMT, 1
     return ALGO_UMMA, (3 if _precision == "tf32x3" else 1)
 
