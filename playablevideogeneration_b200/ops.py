@@ -111,11 +111,11 @@ def _get_packs(weight: Tensor, cin_p: int, round_hi: bool) -> Tensor:
     return bufs
 
 
-def _conv_algo(cin_phys: int, cout: int = 1 << 30) -> Tuple[int, int]:
+def _conv_algo(cin_phys: int, cout: int = 1 << 30, ksize: int = 3) -> Tuple[int, int]:
     """(algo, nprod) for a conv whose A operand has cin_phys physical channels and which produces cout channels.
     The CUDA-core path (fp32, incl. the direct kernels of conv_direct.cu) takes the image-facing layers: A operands that
     are not a multiple of 32 channels wide, and outputs of <= 4 channels (tanh heads, gradients w.r.t. images)."""
-    if _precision == "fp32" or cin_phys % 32 != 0 or (cout <= 4 and os.environ.get("PVG_NO_DIRECT") != "1"):
+    if _precision == "fp32" or cin_phys % 32 != 0 or (cout <= 4 and ksize <= 3 and os.environ.get("PVG_NO_DIRECT") != "1"):
         return ALGO_SIMT, 1
     return ALGO_UMMA, (3 if _precision == "tf32x3" else 1)
 
@@ -198,7 +198,7 @@ class Conv2dFn(torch.autograd.Function):
         cin_p = x.shape[1]
         if cin_log > cin_p or r != s:
             raise _lib.PvgError(f"conv weight {tuple(weight.shape)} does not fit input with {cin_p} channels")
-        algo, nprod = _conv_algo(cin_p, cout)
+        algo, nprod = _conv_algo(cin_p, cout, r)
         packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
         b = bias.detach().contiguous() if bias is not None else None
         flops = 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * cout * r * s * cin_log
@@ -238,7 +238,7 @@ class Conv2dFn(torch.autograd.Function):
             return g_split[0]
 
         if ctx.needs_input_grad[0]:
-            algo, np_ = _conv_algo(cout, cin_p)
+            algo, np_ = _conv_algo(cout, cin_p, r)
             packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
             # data gradient = "same" convolution of g with the tap-flipped, transposed pack [CinP][R][S][Cout]
             dx = _conv_forward(g, packs, 2, cin_p, r, None, ACT_NONE, 0.0, algo, np_, 2.0 * n * h * w * cout * r * s * cin_log,
