@@ -40,6 +40,7 @@ case $s in
   pairs_b1) PVG_2CTA=1 run pairs_b1 300 python tools/conv_bench.py tf32 5 ;;
   directb) run directb 300 python tools/direct_bench.py ;;
   directb0) PVG_NO_DIRECT=1 run directb0 300 python tools/direct_bench.py ;;
+  wgradb) run wgradb 300 python tools/wgrad_bench.py tf32x3 ;;
   flaky) run flaky 300 python tools/flaky_probe.py ;;
   convbench16) PVG_KC=16 run convbench16 600 python tools/conv_bench.py tf32x3 5 ;;
   kernels16) PVG_KC=16 run kernels16 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
