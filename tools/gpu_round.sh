@@ -41,6 +41,8 @@ case $s in
   directb) run directb 300 python tools/direct_bench.py ;;
   directb0) PVG_NO_DIRECT=1 run directb0 300 python tools/direct_bench.py ;;
   wgradb) run wgradb 300 python tools/wgrad_bench.py tf32x3 ;;
+  rollout) run rollout 300 python tools/rollout_bench.py 64 100 tf32x3 ;;
+  stepprof) run stepprof 400 python tools/step_profile.py tf32x3 gpurun_out/step_profile.json ;;
   flaky) run flaky 300 python tools/flaky_probe.py ;;
   convbench16) PVG_KC=16 run convbench16 600 python tools/conv_bench.py tf32x3 5 ;;
   kernels16) PVG_KC=16 run kernels16 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
