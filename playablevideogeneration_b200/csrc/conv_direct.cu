@@ -128,6 +128,296 @@ __global__ void __launch_bounds__(kDThreads) conv_small_cout_kernel(const float*
   for (int j = 0; j < Cout; ++j) yp[j] = act_fwd(acc[j] + (bias ? __ldg(bias + j) : 0.f), act, slope);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shared-memory tiled variants for the layers where the one-pixel-per-thread kernels above are latency/L1 bound:
+// the tanh heads (Cin -> 3, 3x3 and the 7x7 of the 256^2 head), the data gradient of the 7x7 head (3 -> Cin) and the VGG
+// conv1_1 data gradient (64 -> 3 over 120 frames).  The input patch (with its halo) is staged once per CTA in a
+// channel-planar layout so that a warp's reads are contiguous along x; every thread keeps a strip of outputs in registers.
+// ---------------------------------------------------------------------------------------------------------------
+template <int KS>
+struct Cout4Cfg {
+  static constexpr int TH = 16, TW = 64, CC = 8;               // output tile, input channels per shared-memory chunk
+  static constexpr int PH = TH + KS - 1, PW = TW + KS - 1;      // staged patch
+  static constexpr int NV = (4 + KS - 1 + 3) / 4;               // float4 loads per 4-pixel strip (4 + KS - 1 values)
+  static constexpr int PWS = 60 + 4 * NV;                       // row stride: last strip starts at 60 and reads 4*NV values
+  static constexpr int kXFloats = CC * PH * PWS;
+  static constexpr int kSmemBytes = kXFloats * 4 + CC * KS * KS * 16;
+  static_assert(PWS >= PW && PWS % 4 == 0, "row stride");
+};
+
+// Cout <= 3, Cin % 8 == 0.  128 threads = 16 rows x 8 strips; a thread owns pixels [4*tx, 4*tx+4) and [32+4*tx, 32+4*tx+4)
+// of its row (two strips 32 apart keep the float4 shared-memory reads of a quarter-warp contiguous: no bank conflicts).
+template <int KS>
+__global__ void __launch_bounds__(kDThreads) conv_cout4_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, float* __restrict__ y,
+                                                                     int N, int H, int W, int Cin, int Cout, int act,
+                                                                     float slope) {
+  using C = Cout4Cfg<KS>;
+  constexpr int PAD = KS / 2;
+  extern __shared__ float4 smem4[];
+  float* xs = reinterpret_cast<float*>(smem4);                       // [CC][PH][PWS]
+  float4* ws = smem4 + C::kXFloats / 4;                              // [CC][KS*KS] -> (co0, co1, co2, co3)
+  const int tiles_w = ceil_div(W, C::TW), tiles_h = ceil_div(H, C::TH);
+  int t = blockIdx.x;
+  const int tile_w = t % tiles_w; t /= tiles_w;
+  const int tile_h = t % tiles_h;
+  const int n = t / tiles_h;
+  const int ow0 = tile_w * C::TW, oh0 = tile_h * C::TH;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int K = KS * KS * Cin;
+  float acc[2][4][3];
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[g][j][0] = acc[g][j][1] = acc[g][j][2] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += C::CC) {
+    __syncthreads();                                                 // the previous chunk has been consumed
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      for (int i = threadIdx.x; i < C::PH * C::PW; i += kDThreads) {
+        const int py = i / C::PW, px = i - py * C::PW;
+        const int ih = oh0 + py - PAD, iw = ow0 + px - PAD;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = ldg4(x + (((int64_t)n * H + ih) * W + iw) * Cin + c0 + half * 4);
+        float* d = xs + ((half * 4) * C::PH + py) * C::PWS + px;
+        d[0] = v.x; d[C::PH * C::PWS] = v.y; d[2 * C::PH * C::PWS] = v.z; d[3 * C::PH * C::PWS] = v.w;
+      }
+    }
+    for (int i = threadIdx.x; i < C::CC * KS * KS; i += kDThreads) {
+      const int c = i / (KS * KS), tap = i - c * (KS * KS);
+      const float* wp = w + tap * Cin + c0 + c;
+      ws[i] = make_float4(__ldg(wp), Cout > 1 ? __ldg(wp + K) : 0.f, Cout > 2 ? __ldg(wp + 2 * K) : 0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < C::CC; ++c) {
+#pragma unroll
+      for (int r = 0; r < KS; ++r) {
+        const float* row = xs + (c * C::PH + ty + r) * C::PWS + tx * 4;
+        float xv[2][4 * C::NV];
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int i = 0; i < C::NV; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(row + g * 32 + 4 * i);
+            xv[g][4 * i] = v.x; xv[g][4 * i + 1] = v.y; xv[g][4 * i + 2] = v.z; xv[g][4 * i + 3] = v.w;
+          }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          const float4 wv = ws[c * (KS * KS) + r * KS + s];
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[g][j][0] = fmaf(xv[g][s + j], wv.x, acc[g][j][0]);
+              acc[g][j][1] = fmaf(xv[g][s + j], wv.y, acc[g][j][1]);
+              acc[g][j][2] = fmaf(xv[g][s + j], wv.z, acc[g][j][2]);
+            }
+        }
+      }
+    }
+  }
+  const int oy = oh0 + ty;
+  if (oy >= H) return;
+  float b[3];
+#pragma unroll
+  for (int co = 0; co < 3; ++co) b[co] = (bias != nullptr && co < Cout) ? __ldg(bias + co) : 0.f;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int ox = ow0 + g * 32 + tx * 4;
+    if (ox >= W) continue;
+    float* yp = y + (((int64_t)n * H + oy) * W + ox) * Cout;
+    float v[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int co = 0; co < 3; ++co) v[j * 3 + co] = act_fwd(acc[g][j][co] + b[co], act, slope);
+    if (Cout == 3 && ox + 4 <= W && (((uintptr_t)yp) & 15) == 0) {
+      stg4(yp, make_float4(v[0], v[1], v[2], v[3]));
+      stg4(yp + 4, make_float4(v[4], v[5], v[6], v[7]));
+      stg4(yp + 8, make_float4(v[8], v[9], v[10], v[11]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (ox + j < W)
+#pragma unroll
+          for (int co = 0; co < 3; ++co)
+            if (co < Cout) yp[j * Cout + co] = v[j * 3 + co];
+    }
+  }
+}
+
+// Cin == 3 (data gradient of a tanh head), KS x KS, CO output channels per CTA (blockIdx.y walks the chunks of Cout).
+// 128 threads = 4 rows x 32 lanes; a thread owns pixels (row, lane) and (row, lane + 32) and all CO channels of both.
+template <int KS, int CO>
+__global__ void __launch_bounds__(kDThreads) conv_cin3_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                    const float* __restrict__ bias, float* __restrict__ y,
+                                                                    int N, int H, int W, int Cout, int act, float slope) {
+  constexpr int PAD = KS / 2, TH = 4, TW = 64, PH = TH + KS - 1, PW = TW + KS - 1, PWS = PW + 2, K = KS * KS * 3;
+  extern __shared__ float4 smem4[];
+  float4* ws4 = smem4;                                               // [K][CO]
+  float* ws = reinterpret_cast<float*>(smem4);
+  float* xs = ws + K * CO;                                           // [3][PH][PWS]
+  const int tiles_w = ceil_div(W, TW), tiles_h = ceil_div(H, TH);
+  int t = blockIdx.x;
+  const int tile_w = t % tiles_w; t /= tiles_w;
+  const int tile_h = t % tiles_h;
+  const int n = t / tiles_h;
+  const int ow0 = tile_w * TW, oh0 = tile_h * TH;
+  const int co0 = blockIdx.y * CO;
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < PH * PW; i += kDThreads) {
+    const int py = i / PW, px = i - py * PW;
+    const int ih = oh0 + py - PAD, iw = ow0 + px - PAD;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const float* px_ = x + (((int64_t)n * H + ih) * W + iw) * 3;
+      v0 = __ldg(px_); v1 = __ldg(px_ + 1); v2 = __ldg(px_ + 2);
+    }
+    float* d = xs + py * PWS + px;
+    d[0] = v0; d[PH * PWS] = v1; d[2 * PH * PWS] = v2;
+  }
+  for (int i = threadIdx.x; i < K * CO; i += kDThreads) {            // lanes walk co: conflict-free stores, L1-served loads
+    const int k = i / CO, co = i - k * CO;
+    ws[i] = (co0 + co < Cout) ? __ldg(w + (int64_t)(co0 + co) * K + k) : 0.f;
+  }
+  __syncthreads();
+  float acc[2][CO];
+#pragma unroll
+  for (int j = 0; j < CO; ++j) acc[0][j] = acc[1][j] = 0.f;
+#pragma unroll 1
+  for (int r = 0; r < KS; ++r) {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* xp = xs + (ci * PH + row + r) * PWS + lane + s;
+        const float x0 = xp[0], x1 = xp[32];
+        const float4* wk = ws4 + ((r * KS + s) * 3 + ci) * (CO / 4);
+#pragma unroll
+        for (int q = 0; q < CO / 4; ++q) {
+          const float4 wv = wk[q];
+          acc[0][4 * q] = fmaf(x0, wv.x, acc[0][4 * q]); acc[0][4 * q + 1] = fmaf(x0, wv.y, acc[0][4 * q + 1]);
+          acc[0][4 * q + 2] = fmaf(x0, wv.z, acc[0][4 * q + 2]); acc[0][4 * q + 3] = fmaf(x0, wv.w, acc[0][4 * q + 3]);
+          acc[1][4 * q] = fmaf(x1, wv.x, acc[1][4 * q]); acc[1][4 * q + 1] = fmaf(x1, wv.y, acc[1][4 * q + 1]);
+          acc[1][4 * q + 2] = fmaf(x1, wv.z, acc[1][4 * q + 2]); acc[1][4 * q + 3] = fmaf(x1, wv.w, acc[1][4 * q + 3]);
+        }
+      }
+    }
+  }
+  const int oy = oh0 + row;
+  if (oy >= H) return;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int ox = ow0 + lane + 32 * g;
+    if (ox >= W) continue;
+    float* yp = y + (((int64_t)n * H + oy) * W + ox) * Cout + co0;
+#pragma unroll
+    for (int q = 0; q < CO / 4; ++q) {
+      if (co0 + 4 * q >= Cout) break;                               // Cout % 4 == 0
+      float4 b = bias != nullptr ? ldg4(bias + co0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      stg4(yp + 4 * q, make_float4(act_fwd(acc[g][4 * q] + b.x, act, slope), act_fwd(acc[g][4 * q + 1] + b.y, act, slope),
+                                   act_fwd(acc[g][4 * q + 2] + b.z, act, slope), act_fwd(acc[g][4 * q + 3] + b.w, act, slope)));
+    }
+  }
+}
+
+// Weight gradient of a KS x KS head with Cout <= 3 and <= 32 input channels:
+//   dW[co][ci][r][s] += sum_p dY[p][co] * X[p + (r,s) - pad][ci].
+// Persistent CTAs of KS warps: warp = tap row r, lane = ci, 3*KS accumulators per thread; per 4 x 32-pixel tile the X patch
+// ([y][x][ci]: a warp reads 32 consecutive ci) and the dY tile are staged in shared memory, a row of X is held in
+// registers while the 32 pixels of the output row slide over it.  One atomic flush per CTA.
+template <int KS>
+__global__ void __launch_bounds__(KS * 32) wgrad_cout4_tiled_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                    float* __restrict__ dw, int N, int H, int W, int CinP,
+                                                                    int Cin, int Cout) {
+  constexpr int PAD = KS / 2, TH = 4, TW = 32, PH = TH + KS - 1, PW = TW + KS - 1, THREADS = KS * 32;
+  extern __shared__ float4 smem4[];
+  float4* xs4 = smem4;                                               // [PH][PW][32 ci]
+  const float* xs = reinterpret_cast<const float*>(smem4);
+  float4* gs = smem4 + PH * PW * 8;                                  // [TH][TW] -> (dy0, dy1, dy2, dy3)
+  const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_w = ceil_div(W, TW), tiles_h = ceil_div(H, TH);
+  const int tiles_total = tiles_w * tiles_h * N;
+  float acc[KS][3];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) acc[s][0] = acc[s][1] = acc[s][2] = 0.f;
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    int t = tile;
+    const int tile_w = t % tiles_w; t /= tiles_w;
+    const int tile_h = t % tiles_h;
+    const int n = t / tiles_h;
+    const int ow0 = tile_w * TW, oh0 = tile_h * TH;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PH * PW * 8; i += THREADS) {
+      const int pix = i >> 3, q = i & 7;
+      const int py = pix / PW, px = pix - py * PW;
+      const int ih = oh0 + py - PAD, iw = ow0 + px - PAD;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q * 4 < CinP && ih >= 0 && ih < H && iw >= 0 && iw < W) v = ldg4(x + (((int64_t)n * H + ih) * W + iw) * CinP + q * 4);
+      xs4[i] = v;
+    }
+    for (int i = threadIdx.x; i < TH * TW; i += THREADS) {
+      const int py = i / TW, px = i - py * TW;
+      const int oh = oh0 + py, ow = ow0 + px;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oh < H && ow < W) {
+        const float* g = dy + (((int64_t)n * H + oh) * W + ow) * Cout;
+        v.x = __ldg(g);
+        if (Cout > 1) v.y = __ldg(g + 1);
+        if (Cout > 2) v.z = __ldg(g + 2);
+      }
+      gs[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int oy = 0; oy < TH; ++oy) {
+      const float* xr = xs + (oy + r) * PW * 32 + lane;
+      float xrow[PW];
+#pragma unroll
+      for (int k = 0; k < PW; ++k) xrow[k] = xr[k * 32];
+#pragma unroll
+      for (int ox = 0; ox < TW; ++ox) {
+        const float4 g = gs[oy * TW + ox];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          acc[s][0] = fmaf(xrow[ox + s], g.x, acc[s][0]);
+          acc[s][1] = fmaf(xrow[ox + s], g.y, acc[s][1]);
+          acc[s][2] = fmaf(xrow[ox + s], g.z, acc[s][2]);
+        }
+      }
+    }
+  }
+  if (lane < Cin) {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+#pragma unroll
+      for (int co = 0; co < 3; ++co)
+        if (co < Cout) atomicAdd(dw + (((int64_t)co * Cin + lane) * KS + r) * KS + s, acc[s][co]);
+    }
+  }
+}
+
+// returns 1 when the tiled weight-gradient kernel took the problem, 0 otherwise, < 0 on error
+int conv2d_wgrad_direct(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* dy, float* dw, cudaStream_t st) {
+  if (!(d->R == 7 && d->S == 7 && d->Cout <= 3 && d->Cin <= 32 && d->Cin % 4 == 0 && (((uintptr_t)x) & 15) == 0)) return 0;
+  constexpr int KS = 7, PH = 4 + KS - 1, PW = 32 + KS - 1;
+  const int smem = PH * PW * 32 * 4 + 4 * 32 * 16;
+  static bool set = false;
+  if (!set) {
+    PVG_CUDA_OK(cudaFuncSetAttribute(wgrad_cout4_tiled_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    set = true;
+  }
+  const int64_t tiles = (int64_t)ceil_div(d->W, 32) * ceil_div(d->H, 4) * d->N;
+  const int64_t cap = (int64_t)kSMs * 4;
+  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+  wgrad_cout4_tiled_kernel<KS><<<grid, KS * 32, smem, st>>>(x, dy, dw, d->N, d->H, d->W, d->Cin, Cin_logical, d->Cout);
+  PVG_LAUNCH_OK();
+  return 1;
+}
+
 // returns 1 when a direct kernel took the problem, 0 when the caller should fall back, < 0 on error
 int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
   const int64_t M = (int64_t)d->N * d->H * d->W;
@@ -137,6 +427,47 @@ int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, co
   static int disabled = -1;
   if (disabled < 0) { const char* e = getenv("PVG_NO_DIRECT"); disabled = (e && atoi(e) == 1) ? 1 : 0; }
   if (disabled) return 0;
+  if (d->Cin == 3 && d->R == 7 && d->Cout % 16 == 0 && (((uintptr_t)y) & 15) == 0 &&
+      (bias == nullptr || (((uintptr_t)bias) & 15) == 0)) {
+    // data gradient of the 7x7 tanh head
+    constexpr int TH = 4, TW = 64, PH = TH + 6, PWS = TW + 6 + 2, K7 = 49 * 3;
+    const unsigned tiles = (unsigned)(ceil_div(d->W, TW) * ceil_div(d->H, TH) * d->N);
+#define PVG_LAUNCH_CIN3(CO)                                                                                              \
+  do {                                                                                                                   \
+    const int smem = (K7 * CO + 3 * PH * PWS) * 4;                                                                       \
+    static bool set = false;                                                                                             \
+    if (!set) {                                                                                                          \
+      PVG_CUDA_OK(cudaFuncSetAttribute(conv_cin3_tiled_kernel<7, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      set = true;                                                                                                        \
+    }                                                                                                                    \
+    conv_cin3_tiled_kernel<7, CO><<<dim3(tiles, ceil_div(d->Cout, CO)), kDThreads, smem, st>>>(                          \
+        x, w, bias, y, d->N, d->H, d->W, d->Cout, d->act, d->slope);                                                     \
+    PVG_LAUNCH_OK();                                                                                                     \
+    return 1;                                                                                                            \
+  } while (0)
+    if (d->Cout % 32 == 0) PVG_LAUNCH_CIN3(32);
+    PVG_LAUNCH_CIN3(16);
+#undef PVG_LAUNCH_CIN3
+  }
+  if (d->Cout <= 3 && d->Cin % 8 == 0 && (d->R == 3 || d->R == 7) && (((uintptr_t)x) & 15) == 0) {
+    const unsigned tiles = (unsigned)(ceil_div(d->W, 64) * ceil_div(d->H, 16) * d->N);
+#define PVG_LAUNCH_COUT4(KS)                                                                                             \
+  do {                                                                                                                   \
+    static bool set = false;                                                                                             \
+    if (!set) {                                                                                                          \
+      PVG_CUDA_OK(cudaFuncSetAttribute(conv_cout4_tiled_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                       Cout4Cfg<KS>::kSmemBytes));                                                       \
+      set = true;                                                                                                        \
+    }                                                                                                                    \
+    conv_cout4_tiled_kernel<KS><<<tiles, kDThreads, Cout4Cfg<KS>::kSmemBytes, st>>>(x, w, bias, y, d->N, d->H, d->W, d->Cin, \
+                                                                                    d->Cout, d->act, d->slope);          \
+    PVG_LAUNCH_OK();                                                                                                     \
+    return 1;                                                                                                            \
+  } while (0)
+    if (d->R == 3) PVG_LAUNCH_COUT4(3);
+    PVG_LAUNCH_COUT4(7);
+#undef PVG_LAUNCH_COUT4
+  }
   if ((d->Cin == 3 || d->Cin == 12) && d->Cout % 4 == 0 && (size_t)K * d->Cout * 4 <= 96 * 1024) {
     const size_t smem = (size_t)K * d->Cout * 4;
 #define PVG_LAUNCH_CIN(CIN, KS)                                                                                          \

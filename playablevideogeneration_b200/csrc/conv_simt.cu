@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(THREADS) conv_wgrad_simt_kernel(const float* _
 }
 
 int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int conv2d_wgrad_direct(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* dy, float* dw, cudaStream_t st);
 
 int conv2d_fwd_simt(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
   // image-facing layers (3/12 channels on one side) have dedicated direct kernels (conv_direct.cu)
@@ -195,6 +196,10 @@ extern "C" int pvg_conv2d_wgrad(const pvg_conv_desc* d, int Cin_logical, const f
                                 void* stream) {
   PVG_CHECK_ARG(d && x && dy && dw_oihw, "null argument");
   PVG_CHECK_ARG(Cin_logical >= 1 && Cin_logical <= d->Cin, "Cin_logical out of range");
+  {  // 7x7 tanh head (Cout = 3): tiled direct kernel (conv_direct.cu)
+    const int taken = conv2d_wgrad_direct(d, Cin_logical, x, dy, dw_oihw, (cudaStream_t)stream);
+    if (taken != 0) return taken < 0 ? taken : 0;
+  }
   int64_t M = (int64_t)d->N * d->H * d->W;
   int gx = ceil_div(d->Cout, 64), gy = ceil_div(d->R * d->S * Cin_logical, 64);
   int64_t want_splits = ceil_div64((int64_t)kSMs * 4, (int64_t)gx * gy);

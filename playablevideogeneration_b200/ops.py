@@ -115,7 +115,8 @@ def _conv_algo(cin_phys: int, cout: int = 1 << 30, ksize: int = 3) -> Tuple[int,
     """(algo, nprod) for a conv whose A operand has cin_phys physical channels and which produces cout channels.
     The CUDA-core path (fp32, incl. the direct kernels of conv_direct.cu) takes the image-facing layers: A operands that
     are not a multiple of 32 channels wide, and outputs of <= 4 channels (tanh heads, gradients w.r.t. images)."""
-    if _precision == "fp32" or cin_phys % 32 != 0 or (cout <= 4 and ksize <= 3 and os.environ.get("PVG_NO_DIRECT") != "1"):
+    if _precision == "fp32" or cin_phys % 32 != 0 or (cout <= 4 and ksize <= (7 if cout <= 3 else 3)
+                                                       and os.environ.get("PVG_NO_DIRECT") != "1"):
         return ALGO_SIMT, 1
     return ALGO_UMMA, (3 if _precision == "tf32x3" else 1)
 
@@ -246,7 +247,8 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
             d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod)
-            if _precision != "fp32" and cin_p % 32 == 0:
+            head7 = r == 7 and cout <= 3 and cin_p <= 32 and os.environ.get("PVG_NO_DIRECT") != "1"
+            if _precision != "fp32" and cin_p % 32 == 0 and not head7:
                 # tensor-core weight gradient; dY needs a channel count that is a multiple of 4 (16-byte TMA strides):
                 # the 3-channel image heads and the 65-channel encoder tail are zero-padded (a few MB)
                 cout4 = (cout + 3) // 4 * 4

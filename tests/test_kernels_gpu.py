@@ -52,7 +52,10 @@ def _rand(*shape, seed=0, scale=1.0):
 # -----------------------------------------------------------------------------------------------------------------
 CONV_SIMT_SHAPES = [  # N, Cin, Cout, H, W, k, bias
     (2, 3, 16, 20, 20, 3, False), (1, 12, 16, 12, 36, 3, False), (2, 16, 32, 16, 16, 1, False),
-    (2, 16, 16, 10, 14, 3, True), (1, 3, 64, 32, 32, 3, True), (2, 20, 3, 16, 16, 7, True)]
+    (2, 16, 16, 10, 14, 3, True), (1, 3, 64, 32, 32, 3, True), (2, 20, 3, 16, 16, 7, True),
+    # shared-memory tiled head kernels (conv_direct.cu): ragged tiles, several channel chunks
+    (2, 32, 3, 40, 70, 7, True), (1, 16, 3, 21, 36, 7, True), (2, 64, 3, 20, 68, 3, True), (1, 128, 2, 17, 64, 3, False),
+    (2, 3, 32, 9, 70, 7, False), (1, 3, 16, 12, 33, 7, True), (1, 3, 64, 6, 64, 7, False)]
 
 
 @pytest.mark.parametrize("shape", CONV_SIMT_SHAPES)
@@ -124,6 +127,7 @@ def test_conv_umma_forward_tf32(shape):
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64, 16, 16, 3, True, 0), (2, 201, 224, 512, 8, 8, 3, True, 0),
                                    (2, 3, 3, 16, 16, 16, 3, False, 0), (1, 64, 64, 65, 16, 16, 1, False, 0),
                                    (2, 32, 32, 3, 16, 16, 7, True, 3), (2, 137, 160, 256, 16, 16, 3, False, 0),
+                                   (2, 32, 32, 3, 40, 70, 7, True, 3), (1, 16, 16, 3, 21, 36, 7, True, 0),
                                    (8, 64, 64, 32, 64, 64, 3, False, 0), (3, 64, 64, 128, 26, 20, 3, True, 0),
                                    (2, 96, 96, 16, 16, 16, 1, False, 0), (2, 256, 256, 132, 8, 8, 3, False, 0)])
 def test_conv_backward(shape):

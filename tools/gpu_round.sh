@@ -48,6 +48,13 @@ case $s in
   kernels16) PVG_KC=16 run kernels16 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
   bench_ref) run bench_ref 900 python bench.py --impl reference --steps 1 --warmup 0 ;;
   ncu_list) run ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph ;;
+  lb_heads) run lb_heads 300 python tools/layer_bench.py tf32x3 heads ;;
+  lb_enc) run lb_enc 300 python tools/layer_bench.py tf32x3 enc ;;
+  lb_vgg) run lb_vgg 300 python tools/layer_bench.py tf32x3 vgg ;;
+  lb_model) run lb_model 300 python tools/layer_bench.py tf32x3 model ;;
+  lb_all) run lb_all 600 python tools/layer_bench.py tf32x3 all ;;
+  t_direct) run t_direct 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv_simt or conv_backward" -p no:cacheprovider ;;
+  t_conv) run t_conv 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv" -p no:cacheprovider ;;
 esac
 done
 cp $OUT/summary.txt $OUT/summary_$(date +%s).txt 2>/dev/null
