@@ -303,14 +303,15 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
         if args.precision == "tf32x3" and args.workload == "bair256_b8_t16" and os.path.isfile(tpath):
             traffic = json.load(open(tpath))["traffic_bytes_per_launch"]      # from the committed ncu capture of this command
-        roof = dict(bound="tensor", kernel="conv_umma_kernel (tcgen05 kind::tf32" + (", 3 MMAs per k-step" if args.precision == "tf32x3" else "") + ")",
+        roof = dict(bound="tensor", kernel="conv_umma_kernel (tcgen05 kind::tf32" + (" main product + 2 correction products: " + json.dumps(ops._corr) if args.precision == "tf32x3" else "") + ")",
                     achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=traffic,
                     traffic_source="profiles/r01_conv_traffic.json (ncu dram__bytes_read+write per launch, averaged over the step's launches)" if traffic else None,
                     launches_per_step=len(prof), avg_launch_us=tot_ms * 1e3 / len(prof), ms_per_step=tot_ms,
                     share_of_step=tot_ms / ms_dev, peak_source=peaks["source"], weight_gradient=wg,
                     measured="CUDA events around each launch in one extra eager (non-graph) step after the timed region",
                     note="achieved = algorithmic conv FLOPs (2*N*H*W*Cout*R*S*Cin, unpadded) / CUDA-event time of the launches; "
-                         "peak is the measured bf16 cuBLAS figure - kind::tf32 tops out at half of it, 3xTF32 at a sixth")
+                         "peak is the measured bf16 cuBLAS figure - kind::tf32 tops out at half of it; the fp32-equivalent split costs "
+                         "1 TF32 + 2 16-bit MMAs (= 2 TF32 MMA times) per product, i.e. a ceiling of a quarter of the peak")
     if rank != 0:
         _hard_exit(world)
         return
@@ -319,11 +320,12 @@ def main():
         cpu_base, _ = cpu_reference_step_time(w, args.cpu_sample_frames, 1, 0)
     line = dict(metric=METRIC, value=frames_per_step / (ms_dev * 1e-3), unit="frames/s",
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype={"tf32x3": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "tf32": "tf32",
+                vs_baseline=None, dtype={"tf32x3": "f32 (fp32-equivalent split product on the tensor cores: TF32 main term + two correction terms, fp32 accumulate)", "tf32": "tf32",
                                          "fp32": "f32"}[args.precision],
                 data="synthetic", impl="pvg_b200",
                 config=dict(workload=args.workload, per_gpu_batch=w["B"], seq_len=w["T"], frame=f"{w['H']}x{w['W']}x3",
                             gt_init=w["gt_init"], parallelism=f"dp{world}", precision=args.precision,
+                            corrections=dict(ops._corr) if args.precision == "tf32x3" else None,
                             launch="cuda-graph replay of the whole step" if use_graph else "eager (one launch per kernel from Python)",
                             l2="inputs (100.7 MB/step) and per-step activations (>10 GB) exceed the 126 MB L2; no explicit flush"),
                 e2e=dict(value=frames_per_step / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d * world,

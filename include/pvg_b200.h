@@ -13,6 +13,12 @@
  *     on the calling thread;
  *   - "lo" companions: in the fp32-equivalent 3xTF32 mode (nprod == 3) a tensor-core operand X is consumed as
  *     X_hi + X_lo with X_lo = X - tf32(X); pvg_split_tf32 produces X_lo.
+ *   - nprod == 2 is the same split with the two correction products (2^-11 of the result) evaluated as 16-bit MMAs
+ *     (kind::f16, K = 16): the "lo" argument is then a PAIR of 16-bit planes [2][numel] =
+ *     { f16((X - trunc_tf32(X)) * 2^12), f16(X) } for activations (pvg_split_16 / pvg_act_bwd_split_16) and
+ *     { f16(W_lo * 2^12), f16(W_hi) } for packed weights (pvg_pack_16x2), f16 = bf16 or fp16 (pvg_conv_desc.corr_fmt; both
+ *     operands of one conv use the same format).  fp16 holds the tf32 mantissa of a weight exactly (no error that is
+ *     coherent over the batch) and suits O(1) activations; bf16 has fp32's exponent range (gradients).
  */
 #ifndef PVG_B200_H_
 #define PVG_B200_H_
@@ -30,6 +36,9 @@ extern "C" {
 #define PVG_ACT_TANH    3   /* model/layers/final_block.py:27 */
 #define PVG_ACT_SIGMOID 4   /* model/main_model/representation_network.py:55 */
 
+#define PVG_CORR_BF16 0
+#define PVG_CORR_FP16 1
+
 #define PVG_ALGO_AUTO 0
 #define PVG_ALGO_SIMT 1     /* fp32 CUDA-core implicit GEMM (any shape) */
 #define PVG_ALGO_UMMA 2     /* tcgen05 / TMEM / TMA implicit GEMM (Cin % 32 == 0) */
@@ -42,7 +51,9 @@ typedef struct pvg_conv_desc {
   int32_t act;              /* PVG_ACT_* fused into the epilogue (after bias) */
   float   slope;            /* leaky slope for PVG_ACT_LRELU */
   int32_t algo;             /* PVG_ALGO_* */
-  int32_t nprod;            /* 1 = single TF32 product, 3 = 3xTF32 (fp32-equivalent); SIMT ignores it */
+  int32_t nprod;            /* 1 = single TF32 product, 3 = 3xTF32 (fp32-equivalent), 2 = TF32 + 2 bf16 corrections
+                               (fp32-equivalent, see above); SIMT ignores it */
+  int32_t corr_fmt;         /* PVG_CORR_BF16 / PVG_CORR_FP16: format of the 16-bit correction planes (nprod == 2) */
 } pvg_conv_desc;
 
 const char* pvg_last_error(void);
@@ -55,7 +66,7 @@ int pvg_has_umma(void);
  *      model.py:413, vgg.py:48-52 ------------------------------------------------------------------------------ */
 /* w: [Cout][R][S][Cin] (K-major pack from pvg_pack_conv_weight); w_lo may be NULL when nprod == 1 / SIMT.
  * y[n,h,w,co] = act(bias[co] + sum_{r,s,ci} x[n,h+r-pad,w+s-pad,ci] * w[co,r,s,ci]).   bias may be NULL. */
-int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo, const float* w, const void* w_lo,
                    const float* bias, float* y, void* stream);
 /* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinP] (zero padded to CinP >= Cin) and data-gradient pack
  * [CinP][R][S][Cout] with flipped taps (dgrad = pvg_conv2d_fwd(dy, bwd pack)).  *_lo = w - tf32(w); *_hi = tf32(w)
@@ -69,18 +80,26 @@ int pvg_conv2d_wgrad(const pvg_conv_desc* d, int Cin_logical, const float* x, co
 /* Tensor-core weight gradient (tcgen05, MN-major tf32 operands, split-K over pixel patches).  x: [N,H,W,d->Cin]
  * (d->Cin % 32 == 0), g = dY: [N,H,W,d->Cout] (d->Cout % 4 == 0), *_lo their 3xTF32 residual planes (nprod == 3, else
  * NULL).  scratch: float[Cout*R*S*Cin], zero-initialised by the caller.  dw_oihw[co][ci<Cin_logical][r][s] += result. */
-int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* x_lo, const float* g,
-                          const float* g_lo, float* scratch, float* dw_oihw, void* stream);
+int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const void* x_lo, const float* g,
+                          const void* g_lo, float* scratch, float* dw_oihw, void* stream);
 /* out[c] = sum over M rows of x[M][C]  (bias gradient); scratch: double[C] */
 int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* out, void* stream);
 /* hi != NULL: hi = rna_tf32(x), lo = x - hi.  hi == NULL: lo = x - trunc_tf32(x) (x itself then serves as the hi
  * operand; valid when the tensor core truncates raw fp32 inputs - probed at start-up by the host side). */
 int pvg_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* planes: 16-bit [2][n] = { f16((x - trunc_tf32(x)) * 2^12), f16(x) }, fmt = PVG_CORR_BF16 | PVG_CORR_FP16 (saturating):
+ * the correction operands of nprod == 2 */
+int pvg_split_16(const float* x, void* planes, int64_t n, int fmt, void* stream);
+/* the same for a packed weight given its tf32 hi / residual lo planes: planes = { f16(lo * 2^12), f16(hi) } */
+int pvg_pack_16x2(const float* hi, const float* lo, void* planes, int64_t n, int fmt, void* stream);
 /* g = dy * act'(y) for an activation fused in a conv epilogue (y is the activation OUTPUT) */
 int pvg_act_bwd(const float* dy, const float* y, int act, float slope, float* g, int64_t n, void* stream);
 /* the same, also emitting the 3xTF32 planes of g in the same pass (hi may be NULL: truncation mode, see pvg_split_tf32) */
 int pvg_act_bwd_split(const float* dy, const float* y, int act, float slope, float* g, float* hi, float* lo, int64_t n,
                       void* stream);
+/* g = dy * act'(y) and the 16-bit plane pair of g (pvg_split_16) in one pass */
+int pvg_act_bwd_split_16(const float* dy, const float* y, int act, float slope, float* g, void* planes, int64_t n, int fmt,
+                         void* stream);
 
 /* ---- BatchNorm2d (training: per-call batch statistics; eval: running statistics), optionally preceded by
  *      avg_pool2d(2) and followed by (+residual) and an activation.  Replaces F.avg_pool2d + nn.BatchNorm2d +

@@ -10,13 +10,14 @@ LIB_PATH = os.path.join(_HERE, "libpvg_b200.so")
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 ALGO_AUTO, ALGO_SIMT, ALGO_UMMA = 0, 1, 2
+CORR_BF16, CORR_FP16 = 0, 1
 
 
 class ConvDesc(Structure):
     """struct pvg_conv_desc (include/pvg_b200.h)."""
     _fields_ = [("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
                 ("R", c_int32), ("S", c_int32), ("pad", c_int32), ("act", c_int32), ("slope", c_float),
-                ("algo", c_int32), ("nprod", c_int32)]
+                ("algo", c_int32), ("nprod", c_int32), ("corr_fmt", c_int32)]
 
 
 P = c_void_p
@@ -28,6 +29,9 @@ _SIGNATURES = {
     "pvg_conv2d_wgrad_umma": [POINTER(ConvDesc), c_int, P, P, P, P, P, P, P],
     "pvg_channel_sum": [P, c_int64, c_int, P, P, P],
     "pvg_split_tf32": [P, P, P, c_int64, P],
+    "pvg_split_16": [P, P, c_int64, c_int, P],
+    "pvg_pack_16x2": [P, P, P, c_int64, c_int, P],
+    "pvg_act_bwd_split_16": [P, P, c_int, c_float, P, P, c_int64, c_int, P],
     "pvg_act_bwd": [P, P, c_int, c_float, P, c_int64, P],
     "pvg_act_bwd_split": [P, P, c_int, c_float, P, P, P, c_int64, P],
     "pvg_bn_stats": [P, c_int, c_int, c_int, c_int, P, P],

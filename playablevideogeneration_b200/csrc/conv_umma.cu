@@ -15,7 +15,12 @@
 //                  accumulator.
 //   epilogue       tcgen05.ld 32 lanes x 16 columns per warp-instruction -> +bias -> activation -> NHWC global stores
 //                  (each thread owns one output pixel and writes its channels contiguously).
-//   split accum    (NPROD=3) The tensor core adds into its fp32 accumulator with truncation, so an accumulation chain of L
+//   NPROD=2        same split, but the two correction terms (2^-11 of the result, so 8 mantissa bits are plenty) run as
+//                  16-bit MMAs: kind::f16, K = 16, on 16-bit copies {lo * 2^12, x} of both operands (pvg_split_16 /
+//                  pvg_pack_16x2), bf16 or fp16 (pvg_conv_desc.corr_fmt; fp16 keeps the tf32 mantissa of a weight exactly, so
+//                  the weight side adds no error that is coherent over the batch; bf16 has the range gradients need).  Per 32-channel chunk: 4 tf32 + 4 bf16 MMAs instead of 12 tf32, and
+//                  the correction operands are half as wide in shared memory - the kernel's measured limiter.
+//   split accum    (NPROD>=2) The tensor core adds into its fp32 accumulator with truncation, so an accumulation chain of L
 //                  MMAs drifts by ~L * 2^-24 (measured on B200: 2.3e-5 at K = 4.7k).  To stay fp32-equivalent the main
 //                  term A_hi*B_hi is accumulated in TMEM for only kDrain k-iterations (32 MMAs), then drained by the
 //                  epilogue warps into fp32 REGISTER accumulators (round-to-nearest adds) while the MMA warp continues
@@ -37,7 +42,7 @@ constexpr int kSmemBudget = 200 * 1024;
 // stage -> twice the stages in the same shared memory, i.e. a deeper TMA prefetch for the latency-bound 3xTF32 tiles)
 template <int BN, int NPROD, int KC>
 struct Cfg {
-  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
+  static constexpr int kPlanes = NPROD >= 2 ? 2 : 1;         // NPROD == 2: the second 'plane' holds the two bf16 half-width tiles
   static constexpr int kRowBytes = KC * 4;
   static constexpr int kABytes = kTileM * kRowBytes;
   static constexpr int kBBytes = BN * kRowBytes;
@@ -45,7 +50,7 @@ struct Cfg {
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr bool kSplitAcc = NPROD == 3;               // see "split accum" in the header comment
+  static constexpr bool kSplitAcc = NPROD >= 2;               // see "split accum" in the header comment
   static constexpr int kDrain = 32 / kKSteps;                 // stages per TMEM accumulation chain (32 MMAs of the main term)
   static constexpr int kAccCols = kSplitAcc ? 3 * BN : BN;    // [main0 | main1 | correction] or [acc]
   static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
@@ -54,6 +59,7 @@ struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
   static_assert(KC == 32 || KC == 16, "KC must be 16 or 32");
+  static_assert(NPROD != 2 || KC == 32, "bf16 corrections use 32-channel stages");
 };
 
 struct ConvParams {
@@ -63,7 +69,58 @@ struct ConvParams {
   int tiles_w, tiles_h, tiles_n;
   const float* bias;
   float* y;
+  int corr_fp16;                // NPROD == 2: the 16-bit correction planes are fp16 (else bf16)
 };
+
+// bias + activation of 16 consecutive output channels and their NHWC store.  Everything that is uniform over the tile (bias
+// pointer, activation kind, Cout bounds) is tested once per 16 channels, not per element: the straightforward per-element
+// form compiled to ~66 instructions per output value and made the final epilogue 30 % of a 72-k-iteration tile (ncu).
+__device__ __forceinline__ void finish16(float (&v)[16], const float* __restrict__ bias, int co, int Cout, int act, float slope,
+                                         float* __restrict__ yrow, bool valid, bool vec_ok) {
+  if (co >= Cout) return;
+  const bool full = co + 16 <= Cout;
+  if (bias != nullptr) {
+    if (full && vec_ok) {                         // Cout % 4 == 0 and 16-byte aligned rows => bias + co is 16-byte aligned too
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = ldg4(bias + co + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (co + j < Cout) v[j] += __ldg(bias + co + j);
+    }
+  }
+  switch (act) {
+    case PVG_ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+      break;
+    case PVG_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case PVG_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+      break;
+    case PVG_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+      break;
+    default: break;
+  }
+  if (!valid) return;
+  if (full && vec_ok) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (co + j < Cout) yrow[co + j] = v[j];
+  }
+}
 
 template <int BN, int NPROD, int KC>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -96,7 +153,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-    if (NPROD == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
+    if (NPROD >= 2) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], 128); mbar_init(&tempty_bar[1], 128);
@@ -110,12 +167,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int k = 0; k < k_iters; ++k) {
-        const int tap = k / chunks, cc = k - tap * chunks;
-        const int r = tap / p.S, s = tap - r * p.S;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    const uint32_t leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int k = 0; k < k_iters; ++k) {
+      const int tap = k / chunks, cc = k - tap * chunks;
+      const int r = tap / p.S, s = tap - r * p.S;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (leader) {
         uint8_t* st = stage_base + stage * C::kStageBytes;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
         tma_load_4d(st, &tmA, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
@@ -123,68 +181,93 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (NPROD == 3) {
           tma_load_4d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
           tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * KC, co0);
+        } else if (NPROD == 2) {      // both 16-bit planes of each operand in one box: [f16(lo * 2^12) tile | f16(x) tile]
+          tma_load_5d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+          tma_load_3d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * KC, co0, 0);
         }
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == C::kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32<BN>();
-      int stage = 0; uint32_t phase = 0;
-      if constexpr (C::kSplitAcc) {
-        const uint32_t corr = tmem_acc + 2 * BN;
-        uint32_t corr_acc = 0;
-        const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
-        int k = 0;
-        for (int per = 0; per < periods; ++per) {
-          const int b = per & 1;
-          mbar_wait(&tempty_bar[b], ((per >> 1) & 1) ^ 1);       // epilogue finished draining this buffer
+    // Descriptors are base + offset in 16-byte units (the start-address field is the low 14 bits; no carry can leave it).
+    const uint32_t leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_tf32<BN>();
+    const uint64_t d32 = make_kmajor_desc<KC>(smem_u32(stage_base));       // fp32 tiles (KC*4-byte rows)
+    const uint64_t d16 = make_kmajor_desc<16>(smem_u32(stage_base));       // 16-bit tiles (64-byte rows, SWIZZLE_64B)
+    constexpr uint32_t kStageU = C::kStageBytes >> 4, kAU = C::kABytes >> 4, kBU = C::kBBytes >> 4;
+    int stage = 0; uint32_t phase = 0;
+    if constexpr (C::kSplitAcc) {
+      const uint32_t corr = tmem_acc + 2 * BN;
+      const uint32_t idesc16 = make_idesc_f16<BN>(p.corr_fp16 != 0);
+      uint32_t corr_acc = 0;
+      const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
+      int k = 0;
+      for (int per = 0; per < periods; ++per) {
+        const int b = per & 1;
+        mbar_wait(&tempty_bar[b], ((per >> 1) & 1) ^ 1);       // epilogue finished draining this buffer
+        tc_fence_after();
+        const uint32_t main_acc = tmem_acc + b * BN;
+        const int k_end = min(k + C::kDrain, k_iters);
+        uint32_t main_started = 0;
+        for (; k < k_end; ++k) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t main_acc = tmem_acc + b * BN;
-          const int k_end = min(k + C::kDrain, k_iters);
-          uint32_t main_started = 0;
-          for (; k < k_end; ++k) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
-            const uint32_t a_hi = st, a_lo = st + C::kABytes;
-            const uint32_t b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
+          if (leader) {
+            const uint32_t a_hi = stage * kStageU, a_lo = a_hi + kAU, b_hi = a_hi + 2 * kAU, b_lo = b_hi + kBU;
+            if constexpr (NPROD == 2) {
+              // a_lo region: [f16(x_lo * 2^12) | f16(x)] tiles, b_lo region: [f16(w_lo * 2^12) | f16(w_hi)] tiles, 64-byte rows,
+              // K = 16 per MMA; the accumulator holds 2^12 x the correction
+              const uint32_t a_xb = a_lo + kAU / 2, b_xb = b_lo + kBU / 2;
 #pragma unroll
-            for (int ks = 0; ks < C::kKSteps; ++ks) {
-              umma_tf32(corr, make_kmajor_desc<KC>(a_lo + ks * 32), make_kmajor_desc<KC>(b_hi + ks * 32), idesc, corr_acc);
-              corr_acc = 1;
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_bf16(corr, d16 + (a_lo + 2 * ks), d16 + (b_xb + 2 * ks), idesc16, corr_acc);
+                corr_acc = 1;
+              }
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) umma_bf16(corr, d16 + (a_xb + 2 * ks), d16 + (b_lo + 2 * ks), idesc16, 1);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < C::kKSteps; ++ks) {
+                umma_tf32(corr, d32 + (a_lo + 2 * ks), d32 + (b_hi + 2 * ks), idesc, corr_acc);
+                corr_acc = 1;
+              }
+#pragma unroll
+              for (int ks = 0; ks < C::kKSteps; ++ks) umma_tf32(corr, d32 + (a_hi + 2 * ks), d32 + (b_lo + 2 * ks), idesc, 1);
             }
 #pragma unroll
-            for (int ks = 0; ks < C::kKSteps; ++ks)
-              umma_tf32(corr, make_kmajor_desc<KC>(a_hi + ks * 32), make_kmajor_desc<KC>(b_lo + ks * 32), idesc, 1);
-#pragma unroll
             for (int ks = 0; ks < C::kKSteps; ++ks) {
-              umma_tf32(main_acc, make_kmajor_desc<KC>(a_hi + ks * 32), make_kmajor_desc<KC>(b_hi + ks * 32), idesc, main_started);
+              umma_tf32(main_acc, d32 + (a_hi + 2 * ks), d32 + (b_hi + 2 * ks), idesc, main_started);
               main_started = 1;
             }
             umma_commit(&empty_bar[stage]);     // slot reusable once these MMAs have read it
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[b]);           // this chain (and every earlier MMA, incl. corrections) is complete
+          __syncwarp();
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-      } else {
-        uint32_t accumulate = 0;
-        for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
-          const uint32_t a_hi = st, b_hi = st + C::kABytes;
+        if (leader) umma_commit(&tfull_bar[b]);   // this chain (and every earlier MMA, incl. corrections) is complete
+        __syncwarp();
+      }
+    } else {
+      uint32_t accumulate = 0;
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a_hi = stage * kStageU, b_hi = a_hi + kAU;
 #pragma unroll
           for (int ks = 0; ks < C::kKSteps; ++ks) {
-            umma_tf32(tmem_acc, make_kmajor_desc<KC>(a_hi + ks * 32), make_kmajor_desc<KC>(b_hi + ks * 32), idesc, accumulate);
+            umma_tf32(tmem_acc, d32 + (a_hi + 2 * ks), d32 + (b_hi + 2 * ks), idesc, accumulate);
             accumulate = 1;
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[0]);             // accumulator complete
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tfull_bar[0]);     // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -196,7 +279,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ow = w0 + wi, oh = h0 + hi, on = n0 + ni;
     const bool valid = ow < p.W && oh < p.H && on < p.N;
     float* yrow = p.y + (((int64_t)on * p.H + oh) * p.W + ow) * p.Cout;
-    const bool vec_ok = (p.Cout % 4) == 0;
+    const bool vec_ok = (p.Cout % 4) == 0 && (((uintptr_t)p.y | (uintptr_t)p.bias) & 15) == 0;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     if constexpr (C::kSplitAcc) {
       float acc[BN];
@@ -217,50 +300,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_before();
         mbar_arrive(&tempty_bar[b]);
       }
-      // the last tfull commit also covers the correction MMAs
+      // the last tfull commit also covers the correction MMAs (NPROD == 2: accumulated at 2^12 x their value)
+      constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
 #pragma unroll
       for (int c = 0; c < BN; c += 16) {
         float v[16];
         tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
-        const int co = co0 + c;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float bsv = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
-          v[j] = act_fwd(acc[c + j] + v[j] + bsv, p.act, p.slope);
-        }
-        if (valid && co < p.Cout) {
-          if (vec_ok && co + 16 <= p.Cout) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (co + j < p.Cout) yrow[co + j] = v[j];
-          }
-        }
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], kCorrScale, acc[c + j]);
+        finish16(v, p.bias, co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);
       }
     } else {
       mbar_wait(&tfull_bar[0], 0);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll 2
       for (int c = 0; c < BN; c += 16) {
         float v[16];
         tmem_ld16(tmem_acc + lane_base + (uint32_t)c, v);
-        const int co = co0 + c;
-        if (!valid || co >= p.Cout) continue;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float b = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
-          v[j] = act_fwd(v[j] + b, p.act, p.slope);
-        }
-        if (vec_ok && co + 16 <= p.Cout) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (co + j < p.Cout) yrow[co + j] = v[j];
-        }
+        finish16(v, p.bias, co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);
       }
     }
   }
@@ -282,13 +339,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int NPROD>
 struct Cfg2 {
   static constexpr int BN = 128;                              // channels per pair tile
-  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
+  static constexpr int kPlanes = NPROD >= 2 ? 2 : 1;
   static constexpr int kABytes = kTileM * 128;                // own 128-pixel patch, 32 channels
   static constexpr int kBBytes = (BN / 2) * 128;              // own half of the weight tile
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr bool kSplitAcc = NPROD == 3;
+  static constexpr bool kSplitAcc = NPROD >= 2;
   static constexpr int kDrain = 8;
   static constexpr int kAccCols = kSplitAcc ? 3 * BN : BN;
   static constexpr int kTmemCols = kAccCols <= 128 ? 128 : 512;
@@ -328,7 +385,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-    if (NPROD == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
+    if (NPROD >= 2) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], 256); mbar_init(&tempty_bar[1], 256);
@@ -342,12 +399,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int k = 0; k < k_iters; ++k) {
-        const int tap = k / chunks, cc = k - tap * chunks;
-        const int r = tap / p.S, s = tap - r * p.S;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    const uint32_t elected = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int k = 0; k < k_iters; ++k) {
+      const int tap = k / chunks, cc = k - tap * chunks;
+      const int r = tap / p.S, s = tap - r * p.S;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elected) {
         uint8_t* st = stage_base + stage * C::kStageBytes;
         if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);      // bytes of BOTH CTAs land on this barrier
         tma2_load_4d(st, &tmA, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0);
@@ -355,17 +413,26 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (NPROD == 3) {
           tma2_load_4d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0);
           tma2_load_2d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * 32, co0 + (int)rank * (BN / 2));
+        } else if (NPROD == 2) {
+          tma2_load_5d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+          tma2_load_3d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * 32, co0 + (int)rank * (BN / 2), 0);
         }
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == C::kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
+      const uint32_t elected = elect_one();
       constexpr uint32_t idesc = make_idesc_tf32_m256<BN>();
+      const uint64_t d32 = make_kmajor_desc<32>(smem_u32(stage_base));
+      const uint64_t d16 = make_kmajor_desc<16>(smem_u32(stage_base));
+      constexpr uint32_t kStageU = C::kStageBytes >> 4, kAU = C::kABytes >> 4, kBU = C::kBBytes >> 4;
       int stage = 0; uint32_t phase = 0;
       if constexpr (C::kSplitAcc) {
         const uint32_t corr = tmem_acc + 2 * BN;
+        const uint32_t idesc16 = make_idesc_f16<BN>(p.corr_fp16 != 0, false, false, 256);
         uint32_t corr_acc = 0;
         const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
         int k = 0;
@@ -379,43 +446,58 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (; k < k_end; ++k) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
-            const uint32_t a_hi = st, a_lo = st + C::kABytes;
-            const uint32_t b_hi = st + 2 * C::kABytes, b_lo = b_hi + C::kBBytes;
+            if (elected) {
+              const uint32_t a_hi = stage * kStageU, a_lo = a_hi + kAU, b_hi = a_hi + 2 * kAU, b_lo = b_hi + kBU;
+              if constexpr (NPROD == 2) {
+                const uint32_t a_xb = a_lo + kAU / 2, b_xb = b_lo + kBU / 2;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma2_tf32(corr, make_kmajor_desc<32>(a_lo + ks * 32), make_kmajor_desc<32>(b_hi + ks * 32), idesc, corr_acc);
-              corr_acc = 1;
+                for (int ks = 0; ks < 2; ++ks) {
+                  umma2_bf16(corr, d16 + (a_lo + 2 * ks), d16 + (b_xb + 2 * ks), idesc16, corr_acc);
+                  corr_acc = 1;
+                }
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) umma2_bf16(corr, d16 + (a_xb + 2 * ks), d16 + (b_lo + 2 * ks), idesc16, 1);
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  umma2_tf32(corr, d32 + (a_lo + 2 * ks), d32 + (b_hi + 2 * ks), idesc, corr_acc);
+                  corr_acc = 1;
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma2_tf32(corr, d32 + (a_hi + 2 * ks), d32 + (b_lo + 2 * ks), idesc, 1);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma2_tf32(main_acc, d32 + (a_hi + 2 * ks), d32 + (b_hi + 2 * ks), idesc, main_started);
+                main_started = 1;
+              }
+              umma2_commit_both(&empty_bar[stage]);
             }
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma2_tf32(corr, make_kmajor_desc<32>(a_hi + ks * 32), make_kmajor_desc<32>(b_lo + ks * 32), idesc, 1);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma2_tf32(main_acc, make_kmajor_desc<32>(a_hi + ks * 32), make_kmajor_desc<32>(b_hi + ks * 32), idesc, main_started);
-              main_started = 1;
-            }
-            umma2_commit_both(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
-          umma2_commit_both(&tfull_bar[b]);
+          if (elected) umma2_commit_both(&tfull_bar[b]);
+          __syncwarp();
         }
       } else {
         uint32_t accumulate = 0;
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(stage_base + stage * C::kStageBytes);
-          const uint32_t a_hi = st, b_hi = st + C::kABytes;
+          if (elected) {
+            const uint32_t a_hi = stage * kStageU, b_hi = a_hi + kAU;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma2_tf32(tmem_acc, make_kmajor_desc<32>(a_hi + ks * 32), make_kmajor_desc<32>(b_hi + ks * 32), idesc, accumulate);
-            accumulate = 1;
+            for (int ks = 0; ks < 4; ++ks) {
+              umma2_tf32(tmem_acc, d32 + (a_hi + 2 * ks), d32 + (b_hi + 2 * ks), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma2_commit_both(&empty_bar[stage]);
           }
-          umma2_commit_both(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma2_commit_both(&tfull_bar[0]);
+        if (elected) umma2_commit_both(&tfull_bar[0]);
+        __syncwarp();
       }
     }
   } else {
@@ -428,7 +510,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ow = w0 + wi, oh = h0 + hi, on = n0 + ni;
     const bool valid = ow < p.W && oh < p.H && on < p.N;
     float* yrow = p.y + (((int64_t)on * p.H + oh) * p.W + ow) * p.Cout;
-    const bool vec_ok = (p.Cout % 4) == 0;
+    const bool vec_ok = (p.Cout % 4) == 0 && (((uintptr_t)p.y | (uintptr_t)p.bias) & 15) == 0;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float acc[BN];
 #pragma unroll
@@ -454,26 +536,14 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
     }
     constexpr int corr_col = C::kSplitAcc ? 2 * BN : 0;
+    constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
 #pragma unroll
     for (int c = 0; c < BN; c += 16) {
       float v[16];
       tmem_ld16(tmem_acc + lane_base + (uint32_t)(corr_col + c), v);
-      const int co = co0 + c;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float bsv = (p.bias != nullptr && co + j < p.Cout) ? __ldg(p.bias + co + j) : 0.f;
-        v[j] = act_fwd(acc[c + j] + v[j] + bsv, p.act, p.slope);
-      }
-      if (valid && co < p.Cout) {
-        if (vec_ok && co + 16 <= p.Cout) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (co + j < p.Cout) yrow[co + j] = v[j];
-        }
-      }
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], kCorrScale, acc[c + j]);
+      finish16(v, p.bias, co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);
     }
   }
   tc_fence_before();
@@ -509,6 +579,32 @@ int encode_nhwc_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, 
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r)); return -3; }
+  return 0;
+}
+
+int encode_nhwc_16x2_map(CUtensorMap* m, const void* planes, int N, int H, int W, int C, int tw, int th, int tn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return -3; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)N * H * W * C * 2};
+  cuuint32_t box[5] = {32, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, 2};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(bf16 activation planes) failed: " + std::to_string((int)r)); return -3; }
+  return 0;
+}
+
+int encode_w_16x2_map(CUtensorMap* m, const void* planes, int rows, int K, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return -3; }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows * K * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)planes,      /* 16-bit payload: bf16 or fp16 */ dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(16-bit weight planes) failed: " + std::to_string((int)r)); return -3; }
   return 0;
 }
 
@@ -548,7 +644,7 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
   using C = Cfg<BN, NPROD, KC>;
   ConvParams p;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
-  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
@@ -559,6 +655,9 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
   if (NPROD == 3) {
     if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, KC, p.tw, p.th, p.tn))) return rc;
     if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, BN, KC))) return rc;
+  } else if (NPROD == 2) {
+    if ((rc = encode_nhwc_16x2_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_16x2_map(&tmBlo, w_lo, d->Cout, K, BN))) return rc;
   } else {
     tmAlo = tmA; tmBlo = tmB;
   }
@@ -579,7 +678,7 @@ static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_l
   using C = Cfg2<NPROD>;
   ConvParams p;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
-  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
@@ -590,6 +689,9 @@ static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_l
   if (NPROD == 3) {
     if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
     if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, C::BN / 2, 32))) return rc;
+  } else if (NPROD == 2) {
+    if ((rc = encode_nhwc_16x2_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_16x2_map(&tmBlo, w_lo, d->Cout, K, C::BN / 2))) return rc;
   } else {
     tmAlo = tmA; tmBlo = tmB;
   }
@@ -639,7 +741,9 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
   if (co <= 16) return launch_umma<16, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   if (co <= 32) return launch_umma<32, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   if (co <= 64) {
-    if (NPROD == 3 && stage_channels() == 16) return launch_umma<64, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
+    if constexpr (NPROD == 3) {
+      if (stage_channels() == 16) return launch_umma<64, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
+    }
     return launch_umma<64, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   }
   if (co <= 80) return launch_umma<80, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
@@ -647,7 +751,9 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
     if (co % 256 == 0 && !use_pairs(d)) return launch_umma<256, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   }
   if (use_pairs(d)) return launch_umma2<NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
-  if (NPROD == 3 && stage_channels() == 16) return launch_umma<128, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
+  if constexpr (NPROD == 3) {
+    if (stage_channels() == 16) return launch_umma<128, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
+  }
   return launch_umma<128, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
 }
 
@@ -655,8 +761,10 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
 
 using namespace pvg;
 
-extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo_, const float* w, const void* w_lo_,
                               const float* bias, float* y, void* stream) {
+  const float* x_lo = (const float*)x_lo_;      // fp32 residual plane (nprod == 3) or bf16 plane pair (nprod == 2)
+  const float* w_lo = (const float*)w_lo_;
   PVG_CHECK_ARG(d && x && w && y, "null argument");
   PVG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "empty problem");
   PVG_CHECK_ARG(d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "only odd 'same' kernels are supported");
@@ -669,6 +777,11 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const floa
   if (d->nprod == 3) {
     PVG_CHECK_ARG(x_lo && w_lo, "nprod == 3 needs x_lo and w_lo");
     return dispatch_bn<3>(d, x, x_lo, w, w_lo, bias, y, st);
+  }
+  if (d->nprod == 2) {      // x_lo / w_lo: bf16 plane pairs [2][numel] (pvg_split_16 / pvg_pack_16x2)
+    PVG_CHECK_ARG(x_lo && w_lo, "nprod == 2 needs the bf16 plane pairs of x and w");
+    PVG_CHECK_ARG((((uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0, "bf16 planes must be 16-byte aligned");
+    return dispatch_bn<2>(d, x, x_lo, w, w_lo, bias, y, st);
   }
   return dispatch_bn<1>(d, x, nullptr, w, nullptr, bias, y, st);
 }

@@ -15,7 +15,10 @@
 //   work split  CTA = (4 (tap, 32-ci) groups) x (BN-co tile) x (slice of the pixel patches); partial tiles are combined
 //               with fp32 atomics into a packed [Cout][R*S][CinP] buffer (zeroed by the caller), unpacked to OIHW after.
 //   accuracy    K (pixels) reaches 5e5: the accumulation chain in TMEM is cut every kDrain stages (32 MMAs) and drained
-//               into fp32 registers exactly as in conv_umma.cu; NPROD=3 adds the A_lo*B_hi + A_hi*B_lo corrections.
+//               into fp32 registers exactly as in conv_umma.cu; NPROD=3 adds the A_lo*B_hi + A_hi*B_lo corrections,
+//               NPROD=2 evaluates those two corrections as bf16 MMAs (kind::f16, K = 16) on the bf16 plane pairs
+//               {f16(lo * 2^12), f16(x)} of both operands: MN-major 64-byte-swizzled {32 ch x 32 px} tiles, both planes of a
+//               channel group in one 5-D TMA box.
 #include "umma.cuh"
 
 namespace pvg {
@@ -27,14 +30,14 @@ constexpr int kWSmemBudget = 200 * 1024;
 
 template <int BN, int NPROD>
 struct WCfg {
-  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
+  static constexpr int kPlanes = NPROD >= 2 ? 2 : 1;
   static constexpr int kABytes = 4 * kBoxBytes;                 // 4 groups of 32 input channels
   static constexpr int kBBytes = (BN / 32) * kBoxBytes;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kStagesRaw = kWSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kDrain = 8;
-  static constexpr int kAccCols = (NPROD == 3 ? 3 : 2) * BN;    // [main0 | main1 | (correction)]
+  static constexpr int kAccCols = (NPROD >= 2 ? 3 : 2) * BN;    // [main0 | main1 | (correction)]
   static constexpr int kTmemCols = kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 128, "BN must be 32..128 in steps of 32");
@@ -48,6 +51,7 @@ struct WgradParams {
   int chunks, groups;             // 32-channel chunks of CinP; (tap, chunk) groups = R*S*chunks
   int patches_per_split;
   float* dwp;                     // [Cout][R*S][CinP]
+  int corr_fp16;                  // NPROD == 2: 16-bit correction planes are fp16 (else bf16)
 };
 
 template <int BN, int NPROD>
@@ -74,6 +78,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmG); prefetch_tmap(&tmX);
+    if (NPROD >= 2) { prefetch_tmap(&tmGlo); prefetch_tmap(&tmXlo); }
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], 128); mbar_init(&tempty_bar[1], 128);
@@ -87,14 +92,15 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
   const int periods = (iters + C::kDrain - 1) / C::kDrain;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        int t = p_begin + it;
-        const int pw = t % p.tiles_w; t /= p.tiles_w;
-        const int ph = t % p.tiles_h; t /= p.tiles_h;
-        const int w0 = pw * p.tw, h0 = ph * p.th, n0 = t * p.tn;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    const uint32_t leader = elect_one();      // see umma.cuh: single-lane issue without per-instruction election loops
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      int t = p_begin + it;
+      const int pw = t % p.tiles_w; t /= p.tiles_w;
+      const int ph = t % p.tiles_h; t /= p.tiles_h;
+      const int w0 = pw * p.tw, h0 = ph * p.th, n0 = t * p.tn;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (leader) {
         uint8_t* st = smem + stage * C::kStageBytes;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
 #pragma unroll
@@ -107,56 +113,76 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
           tma_load_4d(st + g * kBoxBytes, &tmX, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
           if (NPROD == 3)
             tma_load_4d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
+          if (NPROD == 2)     // [f16(lo * 2^12) 32 px x 64 B | f16(x) 32 px x 64 B] of this channel group
+            tma_load_5d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
         }
         uint8_t* sb = st + C::kPlanes * C::kABytes;
 #pragma unroll
         for (int g = 0; g < BN / 32; ++g) {
           tma_load_4d(sb + g * kBoxBytes, &tmG, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
           if (NPROD == 3) tma_load_4d(sb + C::kBBytes + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
+          if (NPROD == 2) tma_load_5d(sb + C::kBBytes + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0, 0);
         }
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == C::kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32_ex<BN>(true, true);
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t corr = tmem_acc + 2 * BN;
-      uint32_t corr_acc = 0;
-      int it = 0;
-      for (int per = 0; per < periods; ++per) {
-        const int b = per & 1;
-        mbar_wait(&tempty_bar[b], ((per >> 1) & 1) ^ 1);
+    const uint32_t leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_tf32_ex<BN>(true, true);
+    const uint32_t idesc16 = make_idesc_f16<BN>(p.corr_fp16 != 0, true, true);
+    // descriptors = base + offset in 16-byte units (start-address field: low 14 bits, cannot carry out)
+    const uint64_t d32 = make_mnmajor_sw128_desc(smem_u32(smem), kBoxBytes);
+    const uint64_t d16 = make_mnmajor_sw64_desc(smem_u32(smem), kBoxBytes);
+    constexpr uint32_t kStageU = C::kStageBytes >> 4, kAU = C::kABytes >> 4, kBU = C::kBBytes >> 4;
+    constexpr uint32_t kHalfU = (kBoxBytes / 2) >> 4;          // the f16(x) tile follows the f16(lo) tile of each group
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t corr = tmem_acc + 2 * BN;
+    uint32_t corr_acc = 0;
+    int it = 0;
+    for (int per = 0; per < periods; ++per) {
+      const int b = per & 1;
+      mbar_wait(&tempty_bar[b], ((per >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t main_acc = tmem_acc + b * BN;
+      const int it_end = min(it + C::kDrain, iters);
+      uint32_t main_started = 0;
+      for (; it < it_end; ++it) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t main_acc = tmem_acc + b * BN;
-        const int it_end = min(it + C::kDrain, iters);
-        uint32_t main_started = 0;
-        for (; it < it_end; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t a_hi = st, a_lo = st + C::kABytes;
-          const uint32_t b_hi = st + C::kPlanes * C::kABytes, b_lo = b_hi + C::kBBytes;
-          if (NPROD == 3) {
+        if (leader) {
+          const uint32_t a_hi = stage * kStageU, a_lo = a_hi + kAU;
+          const uint32_t b_hi = a_hi + C::kPlanes * kAU, b_lo = b_hi + kBU;
+          if (NPROD == 2) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_tf32(corr, make_mnmajor_sw128_desc(a_lo + ks * 1024, kBoxBytes), make_mnmajor_sw128_desc(b_hi + ks * 1024, kBoxBytes), idesc, corr_acc);
+            for (int ks = 0; ks < 2; ++ks) {           // K = 16 pixels = two 8-row (512 B) atoms: 1024 B = 64 units per step
+              umma_bf16(corr, d16 + (a_lo + 64 * ks), d16 + (b_lo + kHalfU + 64 * ks), idesc16, corr_acc);
               corr_acc = 1;
             }
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_tf32(corr, make_mnmajor_sw128_desc(a_hi + ks * 1024, kBoxBytes), make_mnmajor_sw128_desc(b_lo + ks * 1024, kBoxBytes), idesc, 1);
+            for (int ks = 0; ks < 2; ++ks) umma_bf16(corr, d16 + (a_lo + kHalfU + 64 * ks), d16 + (b_lo + 64 * ks), idesc16, 1);
+          }
+          if (NPROD == 3) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_tf32(corr, d32 + (a_lo + 64 * ks), d32 + (b_hi + 64 * ks), idesc, corr_acc);
+              corr_acc = 1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_tf32(corr, d32 + (a_hi + 64 * ks), d32 + (b_lo + 64 * ks), idesc, 1);
           }
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_tf32(main_acc, make_mnmajor_sw128_desc(a_hi + ks * 1024, kBoxBytes), make_mnmajor_sw128_desc(b_hi + ks * 1024, kBoxBytes), idesc, main_started);
+          for (int ks = 0; ks < 4; ++ks) {             // K = 8 pixels = two 4-row (512 B) atoms: 1024 B per step
+            umma_tf32(main_acc, d32 + (a_hi + 64 * ks), d32 + (b_hi + 64 * ks), idesc, main_started);
             main_started = 1;
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[b]);
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tfull_bar[b]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;                 // TMEM lane quarter == group index inside the M tile
@@ -188,16 +214,18 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
 #pragma unroll
     for (int c = 0; c < BN; c += 16) {
       float v[16];
-      if (NPROD == 3) {
+      if (NPROD >= 2) {
         tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
       if (ok) {
+        // NPROD == 2: the residual planes carry a 2^12 factor (pvg_split_16), so does the correction accumulator
+        constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (co0 + c + j < p.Cout) atomicAdd(out + (co0 + c + j) * co_stride, acc[c + j] + v[j]);
+          if (co0 + c + j < p.Cout) atomicAdd(out + (co0 + c + j) * co_stride, acc[c + j] + v[j] * kCorrScale);
       }
     }
   }
@@ -235,7 +263,7 @@ static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_l
                         float* dwp, cudaStream_t st) {
   using C = WCfg<BN, NPROD>;
   WgradParams p;
-  p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
   choose_patch32(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   p.chunks = d->Cin / 32;
@@ -255,6 +283,9 @@ static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_l
   if (NPROD == 3) {
     if ((rc = encode_nhwc_map(&tmGlo, g_lo, d->N, d->H, d->W, d->Cout, 32, p.tw, p.th, p.tn, true))) return rc;
     if ((rc = encode_nhwc_map(&tmXlo, x_lo, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn, true))) return rc;
+  } else if (NPROD == 2) {
+    if ((rc = encode_nhwc_16x2_map(&tmGlo, g_lo, d->N, d->H, d->W, d->Cout, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_nhwc_16x2_map(&tmXlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
   } else {
     tmGlo = tmG; tmXlo = tmX;
   }
@@ -276,8 +307,10 @@ using namespace pvg;
 // Tensor-core weight gradient.  x: [N,H,W,CinP] (CinP % 32 == 0), g = dY: [N,H,W,Cout] (Cout % 4 == 0), *_lo their
 // 3xTF32 residual planes (nprod == 3).  scratch: float[Cout * R*S * CinP], zero-initialised by the caller.
 // dw_oihw [Cout][Cin_logical][R][S] += unpack(scratch).
-extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* x_lo, const float* g,
-                                     const float* g_lo, float* scratch, float* dw_oihw, void* stream) {
+extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const void* x_lo_, const float* g,
+                                     const void* g_lo_, float* scratch, float* dw_oihw, void* stream) {
+  const float* x_lo = (const float*)x_lo_;      // fp32 residual planes (nprod == 3) or bf16 plane pairs (nprod == 2)
+  const float* g_lo = (const float*)g_lo_;
   PVG_CHECK_ARG(d && x && g && scratch && dw_oihw, "null argument");
   PVG_CHECK_ARG(d->Cin % 32 == 0 && d->Cout % 4 == 0, "tensor-core wgrad needs CinP % 32 == 0 and Cout % 4 == 0");
   PVG_CHECK_ARG((((uintptr_t)x | (uintptr_t)g) & 15) == 0, "operands must be 16-byte aligned");
@@ -290,6 +323,13 @@ extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, co
     else if (cin <= 64) rc = launch_wgrad<64, 3>(d, x, x_lo, g, g_lo, scratch, st);
     else if (cin <= 96) rc = launch_wgrad<96, 3>(d, x, x_lo, g, g_lo, scratch, st);
     else rc = launch_wgrad<128, 3>(d, x, x_lo, g, g_lo, scratch, st);
+  } else if (d->nprod == 2) {
+    PVG_CHECK_ARG(x_lo && g_lo, "nprod == 2 needs the bf16 plane pairs of x and g");
+    PVG_CHECK_ARG(d->Cout % 8 == 0 && (((uintptr_t)x_lo | (uintptr_t)g_lo) & 15) == 0, "bf16 planes need Cout % 8 == 0 and 16-byte alignment");
+    if (cin <= 32) rc = launch_wgrad<32, 2>(d, x, x_lo, g, g_lo, scratch, st);
+    else if (cin <= 64) rc = launch_wgrad<64, 2>(d, x, x_lo, g, g_lo, scratch, st);
+    else if (cin <= 96) rc = launch_wgrad<96, 2>(d, x, x_lo, g, g_lo, scratch, st);
+    else rc = launch_wgrad<128, 2>(d, x, x_lo, g, g_lo, scratch, st);
   } else {
     if (cin <= 32) rc = launch_wgrad<32, 1>(d, x, nullptr, g, nullptr, scratch, st);
     else if (cin <= 64) rc = launch_wgrad<64, 1>(d, x, nullptr, g, nullptr, scratch, st);

@@ -3,6 +3,9 @@
 // weight packing.  All tensors NHWC fp32.  Every kernel is a coalesced, float4-vectorised (when C % 4 == 0)
 // grid-stride loop sized in multiples of the SM count; reductions accumulate in fp64 and finish with one atomic per
 // CTA and channel.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pvg {
@@ -505,6 +508,61 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+// 16-bit correction operands of the nprod == 2 product: planes[0][i] = f16((x - trunc_tf32(x)) * 2^12), planes[1][i] = f16(x)
+// with f16 = bf16 (round to nearest) or fp16 (round to nearest, saturating at +-65504).  The 2^12 keeps the residual in
+// fp16's normal range; the tensor-core kernels fold it back (2^-12) when they add the correction accumulator.
+// fp16 carries 11 significant bits: it holds the tf32 "hi" plane of a WEIGHT exactly, so the weight side adds no error
+// that is coherent over the batch (with bf16 weights that error measured 30x the fp32 CPU oracle's on cancellation-heavy
+// gradients); bf16 keeps fp32's exponent range and is what gradients (1e-6..1e-12) need.  kind::f16 cannot mix the two
+// formats in one MMA (illegal instruction on sm_100a), so a conv uses one format for both operands.
+template <bool FP16>
+__device__ __forceinline__ uint32_t f16x2_bits(float a, float b) {
+  if (FP16) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <bool FP16>
+__device__ __forceinline__ void store_16_planes(uint16_t* planes, int64_t n, int64_t i4, float4 v) {
+  const float4 h = make_float4(tf32_part(v.x, false), tf32_part(v.y, false), tf32_part(v.z, false), tf32_part(v.w, false));
+  constexpr float kS = 4096.f;
+  uint2 lo = make_uint2(f16x2_bits<FP16>((v.x - h.x) * kS, (v.y - h.y) * kS), f16x2_bits<FP16>((v.z - h.z) * kS, (v.w - h.w) * kS));
+  uint2 xb = make_uint2(f16x2_bits<FP16>(v.x, v.y), f16x2_bits<FP16>(v.z, v.w));
+  *reinterpret_cast<uint2*>(planes + 4 * i4) = lo;
+  *reinterpret_cast<uint2*>(planes + n + 4 * i4) = xb;
+}
+template <bool FP16>
+__global__ void __launch_bounds__(256) split_16_kernel(const float* __restrict__ x, uint16_t* __restrict__ planes, int64_t n) {
+  const int64_t q = n / 4;                      // n % 8 == 0 (checked by the host wrapper)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x)
+    store_16_planes<FP16>(planes, n, i, ldg4(x + 4 * i));
+}
+// the same for a packed weight given its tf32 hi / residual lo planes: planes = { f16(lo * 2^12), f16(hi) }
+template <bool FP16>
+__global__ void __launch_bounds__(256) pack_16x2_kernel(const float* __restrict__ hi, const float* __restrict__ lo,
+                                                        uint16_t* __restrict__ planes, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = f16x2_bits<FP16>(lo[i] * 4096.f, hi[i]);
+    planes[i] = (uint16_t)(v & 0xffffu);
+    planes[n + i] = (uint16_t)(v >> 16);
+  }
+}
+template <bool FP16>
+__global__ void __launch_bounds__(256) act_bwd_split_16_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                               int act, float slope, float* __restrict__ g,
+                                                               uint16_t* __restrict__ planes, int64_t n) {
+  const int64_t q = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 d = ldg4(dy + 4 * i), o = ldg4(y + 4 * i);
+    float4 v = make_float4(d.x * act_bwd_from_out(o.x, act, slope), d.y * act_bwd_from_out(o.y, act, slope),
+                           d.z * act_bwd_from_out(o.z, act, slope), d.w * act_bwd_from_out(o.w, act, slope));
+    stg4(g + 4 * i, v);
+    store_16_planes<FP16>(planes, n, i, v);
+  }
+}
+
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act,
                                                       float slope, float* __restrict__ g, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -785,6 +843,34 @@ int pvg_absdiff_mean_bwd(const float* a, const float* b, const float* gout, int 
 int pvg_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
   PVG_CHECK_ARG((((uintptr_t)x | (uintptr_t)lo | (uintptr_t)hi) & 15) == 0, "pointers must be 16-byte aligned");
   split_tf32_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_split_16(const float* x, void* planes, int64_t n, int fmt, void* stream) {
+  PVG_CHECK_ARG(n % 8 == 0 && (((uintptr_t)x | (uintptr_t)planes) & 15) == 0, "n % 8 == 0 and 16-byte aligned pointers required");
+  if (fmt == PVG_CORR_FP16) split_16_kernel<true><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n);
+  else split_16_kernel<false><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_pack_16x2(const float* hi, const float* lo, void* planes, int64_t n, int fmt, void* stream) {
+  PVG_CHECK_ARG(hi && lo && planes, "null argument");
+  if (fmt == PVG_CORR_FP16) pack_16x2_kernel<true><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(hi, lo, (uint16_t*)planes, n);
+  else pack_16x2_kernel<false><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(hi, lo, (uint16_t*)planes, n);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_act_bwd_split_16(const float* dy, const float* y, int act, float slope, float* g, void* planes, int64_t n, int fmt,
+                         void* stream) {
+  PVG_CHECK_ARG(n % 8 == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)g | (uintptr_t)planes) & 15) == 0,
+                "n % 8 == 0 and 16-byte aligned pointers required");
+  if (fmt == PVG_CORR_FP16)
+    act_bwd_split_16_kernel<true><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
+  else
+    act_bwd_split_16_kernel<false><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
   PVG_LAUNCH_OK();
   return 0;
 }

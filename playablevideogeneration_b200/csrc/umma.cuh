@@ -32,6 +32,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a CONVERGED warp (all 32 lanes must call it).  Single-thread work (TMA issue, tcgen05.mma issue) is written as
+//   leader = elect_one();  loop { all lanes wait on the mbarrier; if (leader) { issue }; __syncwarp(); }
+// so that ptxas knows exactly one lane is active and emits straight-line UTMALDG / UTCHMMA: behind an `if (lane == 0)` it
+// wraps EVERY such instruction in an ELECT + BRA.U.ANY loop (~20 instructions per MMA), which made the MMA-issuing thread,
+// not the tensor pipe, the limiter of the 128-wide tiles (ncu: 37 % pipe-active with the issuer never waiting for data).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -45,6 +55,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -66,6 +88,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 with bf16 operands (K = 16 per instruction), fp32 accumulate: the correction terms of the split product
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -108,6 +139,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32() {
 }
 
 
+// kind::f16 instruction descriptor: (bf16 x bf16 | fp16 x fp16) -> fp32, M = 128; K-major operands unless a_mn / b_mn.
+// The two operand formats must be equal (a bf16 x fp16 MMA traps as an illegal instruction on sm_100a).
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc_f16(bool fp16, bool a_mn = false, bool b_mn = false, int m = 128) {
+  return (1u << 4)                      // D format: F32
+         | ((fp16 ? 0u : 1u) << 7)      // A format: F16 = 0, BF16 = 1
+         | ((fp16 ? 0u : 1u) << 10)     // B format
+         | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+         | ((uint32_t)(BN >> 3) << 17)
+         | ((uint32_t)(m >> 4) << 24);
+}
+
 // ---- cta_group::2 (CTA pair) variants -------------------------------------------------------------------------
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-parity bit of a shared::cluster address -> the even (leader) CTA
 
@@ -133,6 +176,18 @@ __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, 
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tmem2_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -146,6 +201,14 @@ __device__ __forceinline__ void umma2_tf32(uint32_t tmem_c, uint64_t adesc, uint
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -174,6 +237,19 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
   return d;
 }
 
+// MN-major bf16 operand tile with the 64-byte swizzle: element (mn, k) lives at row k (64 B = 32 consecutive mn values),
+// 8-row (512 B) swizzle atoms stacked along K (SBO = 512 B, one K = 16 MMA spans two atoms); the next 32 mn values start
+// `mn_group_stride` bytes further (LBO).  TMA produces it with CU_TENSOR_MAP_SWIZZLE_64B from a {32 ch, 32 px} bf16 box.
+__device__ __forceinline__ uint64_t make_mnmajor_sw64_desc(uint32_t smem_addr, uint32_t mn_group_stride) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((mn_group_stride >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                                    // SWIZZLE_64B
+  return d;
+}
+
 // instruction descriptor of the pair MMA: M = 256 (128 rows per CTA)
 template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc_tf32_m256() {
@@ -194,5 +270,10 @@ EncodeTiledFn get_encode_fn();
 // (K-major operands) or 32-byte atoms (atom32 = true, MN-major tf32 operands)
 int encode_nhwc_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, int box_c, int tw, int th, int tn,
                     bool atom32 = false, bool sw64 = false);
+// 5-D map over the two 16-bit correction planes [2][N][H][W][C] of an activation tensor (pvg_split_16): box
+// {32 ch, tw, th, tn, 2} lands as two consecutive 64-byte-row tiles (plane 0 = f16(lo * 2^12), plane 1 = f16(x)), SWIZZLE_64B
+int encode_nhwc_16x2_map(CUtensorMap* m, const void* planes, int N, int H, int W, int C, int tw, int th, int tn);
+// 3-D map over the two 16-bit planes [2][rows][K] of a packed weight: box {32, box_rows, 2}, SWIZZLE_64B
+int encode_w_16x2_map(CUtensorMap* m, const void* planes, int rows, int K, int box_rows);
 
 }  // namespace pvg

@@ -24,6 +24,18 @@ Tensor = torch.Tensor
 #   "fp32"  : force the CUDA-core fp32 path everywhere (debug / cross-check)
 # ---------------------------------------------------------------------------------------------------------------
 _precision = os.environ.get("PVG_PRECISION", "tf32x3")
+# how the two correction products of "tf32x3" are evaluated, per kernel role (forward conv / data gradient / weight gradient):
+#   "tf32": all three products in TF32 (C-ABI nprod = 3; the original scheme)
+#   "bf16" / "fp16": kind::f16 MMAs on 16-bit copies of the operands (nprod = 2): the corrections are 2^-11 of the result,
+#           so few mantissa bits suffice.  fp16 (11 bits) holds the tf32 mantissa of a weight exactly - with bf16 weights
+#           the rounding error of a weight, identical for every pixel, showed up 30x above the fp32 CPU oracle in
+#           cancellation-heavy gradients of the ill-conditioned training graph - and suits the O(1) forward activations;
+#           bf16 has fp32's exponent range, which the gradients (1e-6 .. 1e-12) need.  The weight gradient multiplies two
+#           activation tensors (no weight operand): bf16.
+CORR_MODES = ("tf32", "bf16", "fp16")
+DEFAULT_CORR = {"fwd": os.environ.get("PVG_CORR", "fp16"), "dgrad": os.environ.get("PVG_DGRAD_CORR", "bf16"),
+                "wgrad": os.environ.get("PVG_WGRAD_CORR", "bf16")}
+_corr = dict(DEFAULT_CORR)
 _tf32_truncates: Optional[bool] = None     # does tcgen05 kind::tf32 truncate raw fp32 operands? (probed lazily)
 
 
@@ -36,6 +48,25 @@ def set_precision(mode: str) -> None:
 
 def get_precision() -> str:
     return _precision
+
+
+def set_correction(fwd: Optional[str] = None, dgrad: Optional[str] = None, wgrad: Optional[str] = None) -> None:
+    """Selects how the correction products are evaluated per kernel role; None restores that role's default."""
+    for role, mode in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad)):
+        mode = DEFAULT_CORR[role] if mode is None else mode
+        if mode not in CORR_MODES:
+            raise ValueError(f"correction mode must be one of {CORR_MODES}, got {mode!r}")
+        _corr[role] = mode
+
+
+def _mode(role: str) -> Tuple[int, int]:
+    """(nprod, corr_fmt) of the C ABI for the tensor-core kernel playing ``role`` under the current precision mode."""
+    if _precision != "tf32x3":
+        return 1, 0
+    c = _corr[role]
+    if c == "tf32" or not tf32_truncates():
+        return 3, 0
+    return 2, (_lib.CORR_FP16 if c == "fp16" else _lib.CORR_BF16)
 
 
 def _stream() -> int:
@@ -86,10 +117,35 @@ def invalidate_weight_cache() -> None:
     weights_epoch += 1
 
 
-def _get_packs(weight: Tensor, cin_p: int, round_hi: bool) -> Tensor:
-    """Packed (+tf32-split) copies of a conv weight: rows 0/1 = forward hi/lo [Cout][R][S][CinP], rows 2/3 = data-gradient
-    hi/lo [CinP][R][S][Cout] (flipped taps).  Cached ON the tensor object (so a recycled allocation can never alias a
-    stale pack) and rebuilt when the tensor's autograd version or the global weights epoch moves."""
+class _Packs:
+    """Packed copies of one conv weight.  ``f32``: rows 0/1 = forward hi/lo [Cout][R][S][CinP], rows 2/3 = data-gradient
+    hi/lo [CinP][R][S][Cout] (flipped taps).  ``lo(which, 2, fmt)``: the 16-bit plane pair {f16(lo * 2^12), f16(hi)} of the
+    forward (which = 0) or data-gradient (which = 2) pack, built on first use (nprod == 2)."""
+
+    def __init__(self, f32: Tensor):
+        self.f32 = f32
+        self._bf = {}
+
+    def hi(self, which: int) -> Tensor:
+        return self.f32[which]
+
+    def lo(self, which: int, nprod: int, fmt: int = 0) -> Optional[Tensor]:
+        if nprod == 3:
+            return self.f32[which + 1]
+        if nprod == 2:
+            t = self._bf.get((which, fmt))
+            if t is None:
+                n = self.f32.shape[1]
+                t = torch.empty((2 * n,), dtype=torch.float16 if fmt == _lib.CORR_FP16 else torch.bfloat16, device=self.f32.device)
+                call("pvg_pack_16x2", self.f32[which].data_ptr(), self.f32[which + 1].data_ptr(), t.data_ptr(), n, fmt, _stream())
+                self._bf[(which, fmt)] = t
+            return t
+        return None
+
+
+def _get_packs(weight: Tensor, cin_p: int, round_hi: bool) -> _Packs:
+    """Packed (+tf32-split) copies of a conv weight, cached ON the tensor object (so a recycled allocation can never
+    alias a stale pack) and rebuilt when the tensor's autograd version or the global weights epoch moves."""
     cache = getattr(weight, "_pvg_packs", None)
     if cache is None:
         cache = {}
@@ -107,18 +163,19 @@ def _get_packs(weight: Tensor, cin_p: int, round_hi: bool) -> Tensor:
     bufs = torch.empty((4, cout * r * s * cin_p), dtype=torch.float32, device=weight.device)
     call("pvg_pack_conv_weight", w.data_ptr(), cout, cin, r, s, cin_p, 1 if round_hi else 0,
          bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), _stream())
-    cache[key] = (ver, bufs)
-    return bufs
+    packs = _Packs(bufs)
+    cache[key] = (ver, packs)
+    return packs
 
 
-def _conv_algo(cin_phys: int, cout: int = 1 << 30, ksize: int = 3) -> Tuple[int, int]:
-    """(algo, nprod) for a conv whose A operand has cin_phys physical channels and which produces cout channels.
+def _conv_algo(cin_phys: int, cout: int = 1 << 30, ksize: int = 3, role: str = "fwd") -> Tuple[int, int, int]:
+    """(algo, nprod, corr_fmt) for a conv whose A operand has cin_phys physical channels and which produces cout channels.
     The CUDA-core path (fp32, incl. the direct kernels of conv_direct.cu) takes the image-facing layers: A operands that
     are not a multiple of 32 channels wide, and outputs of <= 4 channels (tanh heads, gradients w.r.t. images)."""
     if _precision == "fp32" or cin_phys % 32 != 0 or (cout <= 4 and ksize <= (7 if cout <= 3 else 3)
                                                        and os.environ.get("PVG_NO_DIRECT") != "1"):
-        return ALGO_SIMT, 1
-    return ALGO_UMMA, (3 if _precision == "tf32x3" else 1)
+        return ALGO_SIMT, 1, 0
+    return (ALGO_UMMA,) + _mode(role)
 
 
 def tf32_truncates() -> bool:
@@ -132,7 +189,7 @@ def tf32_truncates() -> bool:
         w[0, 0, 0, 0] = 1.0
         packs = _get_packs(w, 32, True)
         y = empty_nhwc((1, 16, 8, 16), dev)
-        _run_conv(x, None, packs[0], None, None, y, 1, 0, ACT_NONE, 0.0, ALGO_UMMA, 1)
+        _run_conv(x, None, packs.hi(0), None, None, y, 1, 0, ACT_NONE, 0.0, ALGO_UMMA, 1, 0)
         v = float(y[0, 0, 0, 0])
         if v == 1.0:
             _tf32_truncates = True
@@ -146,9 +203,9 @@ def tf32_truncates() -> bool:
 conv_profile = None     # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per tensor-core conv launch
 
 
-def _run_conv(x, x_lo, w, w_lo, bias, y, ksize, pad, act, slope, algo, nprod, alg_flops=0.0):
+def _run_conv(x, x_lo, w, w_lo, bias, y, ksize, pad, act, slope, algo, nprod, fmt, alg_flops=0.0):
     n, cin, h, wd = x.shape
-    d = ConvDesc(n, h, wd, cin, y.shape[1], ksize, ksize, pad, act, float(slope), algo, nprod)
+    d = ConvDesc(n, h, wd, cin, y.shape[1], ksize, ksize, pad, act, float(slope), algo, nprod, fmt)
     prof = conv_profile is not None and algo == ALGO_UMMA
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -159,8 +216,13 @@ def _run_conv(x, x_lo, w, w_lo, bias, y, ksize, pad, act, slope, algo, nprod, al
         conv_profile.append((e0, e1, alg_flops))
 
 
-def _split(x: Tensor) -> Tuple[Tensor, Tensor]:
-    """(hi, lo) operands of the 3xTF32 product for an activation tensor."""
+def _split(x: Tensor, nprod: int = 3, fmt: int = 0) -> Tuple[Tensor, Tensor]:
+    """(hi, lo) operands of the split product for an activation tensor: nprod == 3 -> fp32 residual plane,
+    nprod == 2 -> the 16-bit plane pair {f16((x - trunc_tf32(x)) * 2^12), f16(x)} (x itself is the hi operand)."""
+    if nprod == 2:
+        planes = torch.empty((2 * x.numel(),), dtype=torch.float16 if fmt == _lib.CORR_FP16 else torch.bfloat16, device=x.device)
+        call("pvg_split_16", x.data_ptr(), planes.data_ptr(), x.numel(), fmt, _stream())
+        return x, planes
     lo = torch.empty_like(x)
     if tf32_truncates():
         call("pvg_split_tf32", x.data_ptr(), None, lo.data_ptr(), x.numel(), _stream())
@@ -170,16 +232,17 @@ def _split(x: Tensor) -> Tuple[Tensor, Tensor]:
     return hi, lo
 
 
-def _conv_forward(x: Tensor, packs: Tensor, which: int, cout: int, ksize: int, bias, act: int, slope: float,
-                  algo: int, nprod: int, alg_flops: float = 0.0, split=None) -> Tensor:
-    """``split``: optional pre-computed (hi, lo) planes of x (shared with the weight-gradient kernel)."""
+def _conv_forward(x: Tensor, packs: _Packs, which: int, cout: int, ksize: int, bias, act: int, slope: float,
+                  algo: int, nprod: int, fmt: int, alg_flops: float = 0.0, split=None) -> Tensor:
+    """``split``: optional pre-computed (hi, lo) operands of x for this (nprod, fmt)."""
     n, cin, h, w = x.shape
     y = empty_nhwc((n, cout, h, w), x.device)
-    if algo == ALGO_UMMA and nprod == 3:
-        hi, lo = split if split is not None else _split(x)
-        _run_conv(hi, lo, packs[which], packs[which + 1], bias, y, ksize, (ksize - 1) // 2, act, slope, algo, nprod, alg_flops)
+    if algo == ALGO_UMMA and nprod >= 2:
+        hi, lo = split if split is not None else _split(x, nprod, fmt)
+        _run_conv(hi, lo, packs.hi(which), packs.lo(which, nprod, fmt), bias, y, ksize, (ksize - 1) // 2, act, slope, algo,
+                  nprod, fmt, alg_flops)
     else:
-        _run_conv(x, None, packs[which], None, bias, y, ksize, (ksize - 1) // 2, act, slope, algo, nprod, alg_flops)
+        _run_conv(x, None, packs.hi(which), None, bias, y, ksize, (ksize - 1) // 2, act, slope, algo, nprod, fmt, alg_flops)
     return y
 
 
@@ -199,11 +262,11 @@ class Conv2dFn(torch.autograd.Function):
         cin_p = x.shape[1]
         if cin_log > cin_p or r != s:
             raise _lib.PvgError(f"conv weight {tuple(weight.shape)} does not fit input with {cin_p} channels")
-        algo, nprod = _conv_algo(cin_p, cout, r)
+        algo, nprod, fmt = _conv_algo(cin_p, cout, r, "fwd")
         packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
         b = bias.detach().contiguous() if bias is not None else None
         flops = 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * cout * r * s * cin_log
-        y = _conv_forward(x, packs, 0, cout, r, b, act, slope, algo, nprod, flops)
+        y = _conv_forward(x, packs, 0, cout, r, b, act, slope, algo, nprod, fmt, flops)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.meta = (act, slope, bias is not None, cin_log)
         return y
@@ -215,55 +278,67 @@ class Conv2dFn(torch.autograd.Function):
         cout, _, r, s = weight.shape
         n, cin_p, h, w = x.shape
         dy = nhwc(dy)
-        nprod = 3 if _precision == "tf32x3" else 1
-        g_split = [None]
+        dmode = _mode("dgrad")            # (nprod, fmt) of the data-gradient kernel (conv_umma.cu)
+        wmode = _mode("wgrad")            # ... of the weight-gradient kernel (conv_wgrad_umma.cu)
+        want_dx = ctx.needs_input_grad[0] and cout % 32 == 0 and dmode[0] >= 2
+        want_dw = ctx.needs_input_grad[1] and cin_p % 32 == 0 and cout % 4 == 0 and wmode[0] >= 2
+        g_splits = {}                     # (nprod, fmt) -> (hi, lo) of g
         if act != ACT_NONE:
             g = torch.empty_like(dy)
-            wants_split = nprod == 3 and ((ctx.needs_input_grad[0] and cout % 32 == 0) or
-                                          (ctx.needs_input_grad[1] and cin_p % 32 == 0 and cout % 4 == 0))
-            if wants_split:          # activation backward and the hi/lo split of g in one pass
+            fused = dmode if want_dx else (wmode if want_dw else (0, 0))
+            if fused[0] == 2:            # activation backward and the 16-bit planes of g in one pass
+                planes = torch.empty((2 * dy.numel(),), dtype=torch.float16 if fused[1] == _lib.CORR_FP16 else torch.bfloat16,
+                                     device=dy.device)
+                call("pvg_act_bwd_split_16", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), planes.data_ptr(),
+                     dy.numel(), fused[1], _stream())
+                g_splits[fused] = (g, planes)
+            elif fused[0] == 3:          # activation backward and the fp32 residual plane of g in one pass
                 lo = torch.empty_like(dy)
                 hi = None if tf32_truncates() else torch.empty_like(dy)
                 call("pvg_act_bwd_split", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), _p(hi), lo.data_ptr(),
                      dy.numel(), _stream())
-                g_split[0] = (g if hi is None else hi, lo)
+                g_splits[(3, 0)] = (g if hi is None else hi, lo)
             else:
                 call("pvg_act_bwd", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), dy.numel(), _stream())
         else:
             g = dy
         dx = dw = db = None
 
-        def split_g():
-            if g_split[0] is None:
-                g_split[0] = _split(g)
-            return g_split[0]
+        def split_g(mode):
+            if mode not in g_splits:
+                g_splits[mode] = _split(g, *mode)
+            return g_splits[mode]
 
         if ctx.needs_input_grad[0]:
-            algo, np_ = _conv_algo(cout, cin_p, r)
+            algo, np_, fmt_ = _conv_algo(cout, cin_p, r, "dgrad")
             packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
             # data gradient = "same" convolution of g with the tap-flipped, transposed pack [CinP][R][S][Cout]
-            dx = _conv_forward(g, packs, 2, cin_p, r, None, ACT_NONE, 0.0, algo, np_, 2.0 * n * h * w * cout * r * s * cin_log,
-                               split=split_g() if (algo == ALGO_UMMA and np_ == 3) else None)
+            dx = _conv_forward(g, packs, 2, cin_p, r, None, ACT_NONE, 0.0, algo, np_, fmt_,
+                               2.0 * n * h * w * cout * r * s * cin_log,
+                               split=split_g((np_, fmt_)) if (algo == ALGO_UMMA and np_ >= 2) else None)
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-            d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod)
+            nprod, wfmt = wmode
+            d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod, wfmt)
             head7 = r == 7 and cout <= 3 and cin_p <= 32 and os.environ.get("PVG_NO_DIRECT") != "1"
             if _precision != "fp32" and cin_p % 32 == 0 and not head7:
                 # tensor-core weight gradient; dY needs a channel count that is a multiple of 4 (16-byte TMA strides):
                 # the 3-channel image heads and the 65-channel encoder tail are zero-padded (a few MB)
                 cout4 = (cout + 3) // 4 * 4
+                if nprod == 2:
+                    cout4 = (cout + 7) // 8 * 8          # bf16 planes: 16-byte strides need 8 channels
                 if cout4 != cout:
                     g4 = empty_nhwc((n, cout4, h, w), dy.device)
                     g4[:, :cout].copy_(g)
                     g4[:, cout:].zero_()
                     dw4 = torch.zeros((cout4, cin_log, r, s), dtype=torch.float32, device=dy.device)
-                    d = ConvDesc(n, h, w, cin_p, cout4, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod)
-                    g_pair = _split(g4) if nprod == 3 else (g4, None)
+                    d = ConvDesc(n, h, w, cin_p, cout4, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod, wfmt)
+                    g_pair = _split(g4, nprod, wfmt) if nprod >= 2 else (g4, None)
                 else:
                     g4, dw4 = g, dw
-                    g_pair = split_g() if nprod == 3 else (g, None)
+                    g_pair = split_g(wmode) if nprod >= 2 else (g, None)
                 scratch = torch.zeros((cout4 * r * s * cin_p,), dtype=torch.float32, device=dy.device)
-                x_hi, x_lo = _split(x) if nprod == 3 else (x, None)
+                x_hi, x_lo = _split(x, nprod, wfmt) if nprod >= 2 else (x, None)
                 g_hi, g_lo = g_pair
                 prof = wgrad_profile is not None
                 if prof:

@@ -101,14 +101,25 @@ def test_tf32_probe_reports_rounding_mode():
     assert trunc in (True, False)
 
 
+@pytest.fixture(params=["bf16", "fp16", "tf32"])
+def corr(request):
+    """Every evaluation of the two correction products of the fp32-equivalent split (C-ABI nprod = 2 with bf16 / fp16
+    planes, nprod = 3), applied to the forward, data-gradient and weight-gradient kernels alike."""
+    ops = _ops()
+    ops.set_correction(request.param, request.param, request.param)
+    yield request.param
+    ops.set_correction()
+
+
 @pytest.mark.parametrize("shape", CONV_UMMA_SHAPES)
-def test_conv_umma_forward_tf32x3(shape):
-    """3xTF32 error-compensated tensor-core conv vs fp32 CPU: fp32-equivalent (tolerance 1e-5 of the output scale)."""
+def test_conv_umma_forward_tf32x3(shape, corr):
+    """error-compensated split tensor-core conv (TF32 main product + bf16 or TF32 corrections) vs fp32 CPU:
+    fp32-equivalent (tolerance 1e-5 of the output scale)."""
     ops = _ops()
     x, wt, b, ref = _conv_case(shape)
     ops.set_precision("tf32x3")
     got = ops.conv2d(x.to(DEV), wt.to(DEV), b.to(DEV) if b is not None else None, act=shape[8])
-    _close(f"conv_umma3{shape}", got, ref, 1e-5, 1e-6)
+    _close(f"conv_umma3[{corr}]{shape}", got, ref, 1e-5, 1e-6)
 
 
 @pytest.mark.parametrize("shape", CONV_UMMA_SHAPES[:5])
@@ -130,8 +141,12 @@ def test_conv_umma_forward_tf32(shape):
                                    (2, 32, 32, 3, 40, 70, 7, True, 3), (1, 16, 16, 3, 21, 36, 7, True, 0),
                                    (8, 64, 64, 32, 64, 64, 3, False, 0), (3, 64, 64, 128, 26, 20, 3, True, 0),
                                    (2, 96, 96, 16, 16, 16, 1, False, 0), (2, 256, 256, 132, 8, 8, 3, False, 0)])
-def test_conv_backward(shape):
+def test_conv_backward(shape, corr):
     """dx (tensor-core dgrad with flipped packed weights or SIMT), dw (split-K wgrad), db vs torch autograd on CPU."""
+    _conv_backward_case(shape, corr)
+
+
+def _conv_backward_case(shape, corr):
     ops = _ops()
     n, cin, cinp, cout, h, w, k, has_bias, act = shape
     x, wt, b, _ = _conv_case(shape, seed=10)
@@ -148,10 +163,10 @@ def test_conv_backward(shape):
     bg = b.to(DEV).requires_grad_(True) if has_bias else None
     out = ops.conv2d(xg, wg, bg, act=act)
     out.backward(gy.to(DEV))
-    _close(f"conv_bwd_dx{shape}", xg.grad[:, :cin], xr.grad, 1e-5, 1e-6)
-    _close(f"conv_bwd_dw{shape}", wg.grad, wr.grad, 2e-5, 1e-6)
+    _close(f"conv_bwd_dx[{corr}]{shape}", xg.grad[:, :cin], xr.grad, 1e-5, 1e-6)
+    _close(f"conv_bwd_dw[{corr}]{shape}", wg.grad, wr.grad, 2e-5, 1e-6)
     if has_bias:
-        _close(f"conv_bwd_db{shape}", bg.grad, br.grad, 1e-5, 1e-6)
+        _close(f"conv_bwd_db[{corr}]{shape}", bg.grad, br.grad, 1e-5, 1e-6)
 
 
 @pytest.mark.parametrize("shape", [(2, 201, 224, 512, 8, 8, 3, True, 0), (2, 128, 128, 128, 16, 16, 3, False, 0),
@@ -161,7 +176,7 @@ def test_conv_backward_fp32_simt(shape):
     ops = _ops()
     ops.set_precision("fp32")
     try:
-        test_conv_backward(shape)
+        _conv_backward_case(shape, "fp32")
     finally:
         ops.set_precision("tf32x3")
 

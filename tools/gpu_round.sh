@@ -55,6 +55,17 @@ case $s in
   lb_all) run lb_all 600 python tools/layer_bench.py tf32x3 all ;;
   t_direct) run t_direct 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv_simt or conv_backward" -p no:cacheprovider ;;
   t_conv) run t_conv 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv" -p no:cacheprovider ;;
+  diag_pre) for c in "tf32 tf32 tf32" "fp16 tf32 tf32" "tf32 bf16 tf32" "fp16 bf16 bf16"; do set -- $c; PVG_CORR=$1 PVG_DGRAD_CORR=$2 PVG_WGRAD_CORR=$3 run diag_pre_$1_$2_$3 300 python -m pytest tests/test_model_gpu.py -q -m gpu -k "pretrain_bair" -p no:cacheprovider; grep pretrain_bair:cond $OUT/model_errors.jsonl | tail -1 | cut -c1-400 | tee -a $OUT/summary.txt; done ;;
+  bench_fwdtf32) PVG_CORR=tf32 run bench_fwdtf32 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline ;;
+  bench_alltf32) PVG_CORR=tf32 PVG_DGRAD_CORR=tf32 PVG_WGRAD_CORR=tf32 run bench_alltf32 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline ;;
+  lb_pairs) PVG_2CTA=1 run lb_pairs 300 python tools/layer_bench.py tf32x3 vgg; PVG_2CTA=1 run lb_pairs_model 300 python tools/layer_bench.py tf32x3 model ;;
+  lb_nopairs) PVG_2CTA=0 run lb_nopairs 300 python tools/layer_bench.py tf32x3 vgg ;;
+  lb_tf32) run lb_tf32 300 python tools/layer_bench.py tf32 vgg ;;
+  ncu_vgg3) run ncu_vgg3 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 2 -c 1 -f -o $OUT/prof_vgg3 python tools/one_conv.py 120 256 256 64 64 ;;
+  ncu_vgg1) run ncu_vgg1 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 2 -c 1 -f -o $OUT/prof_vgg1 python tools/one_conv.py 120 64 64 256 256 ;;
+  ncu_vgg3_tf32) PVG_PRECISION=tf32 run ncu_vgg3_tf32 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 2 -c 1 -f -o $OUT/prof_vgg3_tf32 python tools/one_conv.py 120 256 256 64 64 ;;
+  tile_model) PVG_2CTA=0 run tile_model0 300 python tools/tile_model.py tf32x3; PVG_2CTA=1 run tile_model1 300 python tools/tile_model.py tf32x3; PVG_2CTA=0 run tile_model0_tf32 300 python tools/tile_model.py tf32; PVG_2CTA=0 run tile_model0_64 300 python tools/tile_model.py tf32x3 64; PVG_2CTA=0 PVG_CORR=tf32 run tile_model0_c3 300 python tools/tile_model.py tf32x3 ;;
+  corr_diag) run corr_diag 300 python tools/corr_diag.py ;;
 esac
 done
 cp $OUT/summary.txt $OUT/summary_$(date +%s).txt 2>/dev/null
