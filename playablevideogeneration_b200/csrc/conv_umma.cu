@@ -708,10 +708,9 @@ static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_l
   return 0;
 }
 
-// The CTA-pair kernel pays two cluster barriers and a pair-wide TMEM allocation per tile; measured on B200
-// (profiles/r01_conv_bench_pairs.json) it wins by ~20 % on the K-deep layers (VGG conv4/conv5: 144 k-iterations) and is
-// neutral below ~70 k-iterations, so it is used for deep-K tiles with enough M tiles to fill the machine twice.
-// PVG_2CTA=1 / 0 forces it on / off.
+// The CTA-pair kernel pays two cluster barriers and a pair-wide TMEM allocation per tile (fixed cost 5.3 us per tile against
+// 3.7 us) and runs a k-iteration in 952 clk against 1149 (tools/tile_model.py on B200, 16-bit corrections): it wins from
+// 18 k-iterations on, given enough M tiles to fill the machine twice.  PVG_2CTA=1 / 0 forces it on / off.
 static bool use_pairs(const pvg_conv_desc* d) {
   static int forced = -2;
   if (forced == -2) {
@@ -721,7 +720,7 @@ static bool use_pairs(const pvg_conv_desc* d) {
   if (forced >= 0) return forced == 1;
   const int k_iters = d->R * d->S * (d->Cin / 32);
   const int64_t m_tiles = ((int64_t)d->N * d->H * d->W + 127) / 128;
-  return k_iters >= 96 && m_tiles >= 2 * kSMs;
+  return k_iters >= 18 && m_tiles >= 2 * kSMs;
 }
 
 // PVG_KC=16 selects the 16-channel (SWIZZLE_64B) stage for the 3xTF32 128-wide tiles (A/B experiment knob)
