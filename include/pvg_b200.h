@@ -45,7 +45,8 @@ extern "C" {
 
 typedef struct pvg_conv_desc {
   int32_t N, H, W;          /* output == input spatial size (all convs on the path are stride 1, "same" padding) */
-  int32_t Cin;              /* physical channels of x (== K per tap) */
+  int32_t Cin;              /* physical channels of x (tensor-core path: any multiple of 4, of 8 with 16-bit planes; the K
+                               loop runs over Cin rounded up to 32, TMA zero-fills, and w is packed with that count) */
   int32_t Cout;             /* physical channels of y */
   int32_t R, S, pad;        /* kernel height/width and zero padding (3,3,1 | 1,1,0 | 7,7,3) */
   int32_t act;              /* PVG_ACT_* fused into the epilogue (after bias) */
@@ -68,10 +69,12 @@ int pvg_has_umma(void);
  * y[n,h,w,co] = act(bias[co] + sum_{r,s,ci} x[n,h+r-pad,w+s-pad,ci] * w[co,r,s,ci]).   bias may be NULL. */
 int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo, const float* w, const void* w_lo,
                    const float* bias, float* y, void* stream);
-/* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinP] (zero padded to CinP >= Cin) and data-gradient pack
- * [CinP][R][S][Cout] with flipped taps (dgrad = pvg_conv2d_fwd(dy, bwd pack)).  *_lo = w - tf32(w); *_hi = tf32(w)
- * when round_hi != 0 (tensor-core consumers) else w (SIMT consumers); any output pointer may be NULL. */
-int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinP, int round_hi,
+/* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinK] and data-gradient pack [CinRows][R][S][CoutK] with flipped
+ * taps (dgrad = pvg_conv2d_fwd(dy, bwd pack)).  CinRows >= Cin: physical channels of the activation (zero-padded concat
+ * buffers); CinK >= CinRows, CoutK >= Cout: K-side channel counts of the consumer (tensor-core kernels: rounded up to 32,
+ * zero filled; SIMT: the unpadded counts).  *_lo = w - tf32(w); *_hi = tf32(w) when round_hi != 0 (tensor-core
+ * consumers) else w (SIMT consumers); any output pointer may be NULL. */
+int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinRows, int CinK, int CoutK, int round_hi,
                          float* fwd_hi, float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream);
 /* weight gradient (cudnnConvolutionBackwardFilter): dw_oihw[co][ci][r][s] += sum_pixels dy * x ; x has CinP
  * physical channels of which the first Cin are real.  dw must be zero-initialised by the caller. */

@@ -643,12 +643,15 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
                        const float* bias, float* y, cudaStream_t st) {
   using C = Cfg<BN, NPROD, KC>;
   ConvParams p;
-  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
+  // Cin that is not a multiple of 32 (the 16-channel encoder block): the K loop runs over the padded count, the TMA box
+  // {32 ch, ...} reads past the tensor's channel extent and gets zeros (out-of-bounds fill) - no padded copy in HBM
+  const int CinK = (d->Cin + 31) & ~31;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
-  const int K = d->R * d->S * d->Cin;
+  const int K = d->R * d->S * CinK;
   int rc;
   if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, KC, p.tw, p.th, p.tn))) return rc;
   if ((rc = encode_w_map(&tmB, w, d->Cout, K, BN, KC))) return rc;
@@ -677,12 +680,15 @@ static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_l
                         const float* bias, float* y, cudaStream_t st) {
   using C = Cfg2<NPROD>;
   ConvParams p;
-  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
+  // Cin that is not a multiple of 32 (the 16-channel encoder block): the K loop runs over the padded count, the TMA box
+  // {32 ch, ...} reads past the tensor's channel extent and gets zeros (out-of-bounds fill) - no padded copy in HBM
+  const int CinK = (d->Cin + 31) & ~31;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
-  const int K = d->R * d->S * d->Cin;
+  const int K = d->R * d->S * CinK;
   int rc;
   if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
   if ((rc = encode_w_map(&tmB, w, d->Cout, K, C::BN / 2, 32))) return rc;
@@ -718,7 +724,7 @@ static bool use_pairs(const pvg_conv_desc* d) {
     forced = e ? atoi(e) : -1;
   }
   if (forced >= 0) return forced == 1;
-  const int k_iters = d->R * d->S * (d->Cin / 32);
+  const int k_iters = d->R * d->S * ((d->Cin + 31) / 32);
   const int64_t m_tiles = ((int64_t)d->N * d->H * d->W + 127) / 128;
   return k_iters >= 18 && m_tiles >= 2 * kSMs;
 }
@@ -769,10 +775,11 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void
   PVG_CHECK_ARG(d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "only odd 'same' kernels are supported");
   cudaStream_t st = (cudaStream_t)stream;
   int algo = d->algo;
-  const bool umma_ok = (d->Cin % 32) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
+  // channel strides must be multiples of 16 bytes for TMA: Cin % 4 == 0 (fp32), % 8 == 0 with 16-bit planes
+  const bool umma_ok = (d->Cin % (d->nprod == 2 ? 8 : 4)) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
   if (algo == PVG_ALGO_AUTO) algo = (umma_ok && pvg_has_umma()) ? PVG_ALGO_UMMA : PVG_ALGO_SIMT;
   if (algo == PVG_ALGO_SIMT) return conv2d_fwd_simt(d, x, w, bias, y, st);
-  PVG_CHECK_ARG(umma_ok, "tensor-core path needs Cin % 32 == 0 and 16-byte aligned operands");
+  PVG_CHECK_ARG(umma_ok, "tensor-core path needs Cin % 4 == 0 (% 8 with 16-bit correction planes) and 16-byte aligned operands");
   if (d->nprod == 3) {
     PVG_CHECK_ARG(x_lo && w_lo, "nprod == 3 needs x_lo and w_lo");
     return dispatch_bn<3>(d, x, x_lo, w, w_lo, bias, y, st);

@@ -263,10 +263,11 @@ static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_l
                         float* dwp, cudaStream_t st) {
   using C = WCfg<BN, NPROD>;
   WgradParams p;
-  p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  const int CinK = (d->Cin + 31) & ~31;     // K-side channel count padded to whole 32-channel groups (TMA zero-fills the rest)
+  p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
   choose_patch32(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
-  p.chunks = d->Cin / 32;
+  p.chunks = CinK / 32;
   p.groups = d->R * d->S * p.chunks;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n;
   const int gx = ceil_div(p.groups, 4), gy = ceil_div(d->Cout, BN);
@@ -305,14 +306,14 @@ static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_l
 using namespace pvg;
 
 // Tensor-core weight gradient.  x: [N,H,W,CinP] (CinP % 32 == 0), g = dY: [N,H,W,Cout] (Cout % 4 == 0), *_lo their
-// 3xTF32 residual planes (nprod == 3).  scratch: float[Cout * R*S * CinP], zero-initialised by the caller.
+// 3xTF32 residual planes (nprod == 3).  scratch: float[Cout * R*S * roundup(CinP, 32)], zero-initialised by the caller.
 // dw_oihw [Cout][Cin_logical][R][S] += unpack(scratch).
 extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const void* x_lo_, const float* g,
                                      const void* g_lo_, float* scratch, float* dw_oihw, void* stream) {
   const float* x_lo = (const float*)x_lo_;      // fp32 residual planes (nprod == 3) or bf16 plane pairs (nprod == 2)
   const float* g_lo = (const float*)g_lo_;
   PVG_CHECK_ARG(d && x && g && scratch && dw_oihw, "null argument");
-  PVG_CHECK_ARG(d->Cin % 32 == 0 && d->Cout % 4 == 0, "tensor-core wgrad needs CinP % 32 == 0 and Cout % 4 == 0");
+  PVG_CHECK_ARG(d->Cin % (d->nprod == 2 ? 8 : 4) == 0 && d->Cout % 4 == 0, "tensor-core wgrad needs Cin % 4 == 0 (% 8 with 16-bit planes) and Cout % 4 == 0");
   PVG_CHECK_ARG((((uintptr_t)x | (uintptr_t)g) & 15) == 0, "operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
@@ -338,7 +339,7 @@ extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, co
   }
   if (rc) return rc;
   int64_t total = (int64_t)d->Cout * Cin_logical * d->R * d->S;
-  unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, d->Cin, dw_oihw);
+  unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, (d->Cin + 31) & ~31, dw_oihw);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -607,25 +607,37 @@ __global__ void cast_d2f_kernel(const double* in, float* out, int n) {
   if (i < n) out[i] = (float)in[i];
 }
 
-// OIHW -> [Cout][R][S][CinP] (+lo) and [CinP][R][S][Cout] with flipped taps (+lo)
+// OIHW -> forward pack [Cout][R][S][CinK] (+lo) and data-gradient pack [CinRows][R][S][CoutK] with flipped taps (+lo);
+// CinK >= Cin and CoutK >= Cout are the K-side channel counts of the consumer (padded with zeros), CinRows >= Cin the
+// physical channel count of the activation the data gradient is taken with respect to
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S,
-                                                          int CinP, int round_hi, float* fwd_hi, float* fwd_lo,
-                                                          float* bwd_hi, float* bwd_lo) {
-  const int64_t total = (int64_t)Cout * R * S * CinP;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int ci = (int)(i % CinP);
-    int64_t t = i / CinP;
-    int s = (int)(t % S); t /= S;
-    int r = (int)(t % R);
-    int co = (int)(t / R);
-    float v = ci < Cin ? __ldg(w + (((int64_t)co * Cin + ci) * R + r) * S + s) : 0.f;
-    float hi = tf32_hi(v);
-    float h = round_hi ? hi : v;          // SIMT consumers want the full fp32 value, tensor-core consumers tf32(v)
-    if (fwd_hi) fwd_hi[i] = h;
-    if (fwd_lo) fwd_lo[i] = v - hi;
-    int64_t j = (((int64_t)ci * R + (R - 1 - r)) * S + (S - 1 - s)) * Cout + co;
-    if (bwd_hi) bwd_hi[j] = h;
-    if (bwd_lo) bwd_lo[j] = v - hi;
+                                                          int CinRows, int CinK, int CoutK, int round_hi, float* fwd_hi,
+                                                          float* fwd_lo, float* bwd_hi, float* bwd_lo) {
+  const int64_t total_f = (int64_t)Cout * R * S * CinK;
+  const int64_t total_b = (int64_t)CinRows * R * S * CoutK;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_f + total_b; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool fwd = i < total_f;
+    int64_t t = fwd ? i : i - total_f;
+    int co, ci, r, s;
+    if (fwd) {
+      ci = (int)(t % CinK); t /= CinK;
+      s = (int)(t % S); t /= S;
+      r = (int)(t % R);
+      co = (int)(t / R);
+    } else {
+      co = (int)(t % CoutK); t /= CoutK;
+      s = S - 1 - (int)(t % S); t /= S;
+      r = R - 1 - (int)(t % R);
+      ci = (int)(t / R);
+    }
+    const float v = (ci < Cin && co < Cout) ? __ldg(w + (((int64_t)co * Cin + ci) * R + r) * S + s) : 0.f;
+    const float hi = tf32_hi(v);
+    const float h = round_hi ? hi : v;          // SIMT consumers want the full fp32 value, tensor-core consumers tf32(v)
+    const int64_t o = fwd ? i : i - total_f;
+    float* dh = fwd ? fwd_hi : bwd_hi;
+    float* dl = fwd ? fwd_lo : bwd_lo;
+    if (dh) dh[o] = h;
+    if (dl) dl[o] = v - hi;
   }
 }
 
@@ -901,12 +913,12 @@ int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* ou
   return 0;
 }
 
-int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinP, int round_hi, float* fwd_hi,
-                         float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream) {
-  PVG_CHECK_ARG(CinP >= Cin, "CinP < Cin");
-  int64_t total = (int64_t)Cout * R * S * CinP;
-  pack_weight_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, R, S, CinP, round_hi, fwd_hi,
-                                                                          fwd_lo, bwd_hi, bwd_lo);
+int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinRows, int CinK, int CoutK, int round_hi,
+                         float* fwd_hi, float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream) {
+  PVG_CHECK_ARG(CinRows >= Cin && CinK >= CinRows && CoutK >= Cout, "padded channel counts smaller than the real ones");
+  int64_t total = (int64_t)Cout * R * S * CinK + (int64_t)CinRows * R * S * CoutK;
+  pack_weight_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, R, S, CinRows, CinK, CoutK,
+                                                                          round_hi, fwd_hi, fwd_lo, bwd_hi, bwd_lo);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -118,34 +118,37 @@ def invalidate_weight_cache() -> None:
 
 
 class _Packs:
-    """Packed copies of one conv weight.  ``f32``: rows 0/1 = forward hi/lo [Cout][R][S][CinP], rows 2/3 = data-gradient
-    hi/lo [CinP][R][S][Cout] (flipped taps).  ``lo(which, 2, fmt)``: the 16-bit plane pair {f16(lo * 2^12), f16(hi)} of the
-    forward (which = 0) or data-gradient (which = 2) pack, built on first use (nprod == 2)."""
+    """Packed copies of one conv weight.  ``f32[0]``: forward hi/lo planes [Cout][R][S][CinK]; ``f32[2]``: data-gradient
+    hi/lo planes [CinRows][R][S][CoutK] (flipped taps).  ``lo(which, 2, fmt)``: the 16-bit plane pair
+    {f16(lo * 2^12), f16(hi)} of the forward (which = 0) or data-gradient (which = 2) pack, built on first use."""
 
-    def __init__(self, f32: Tensor):
-        self.f32 = f32
+    def __init__(self, fwd: Tensor, bwd: Tensor):
+        self.f32 = {0: fwd, 2: bwd}
         self._bf = {}
 
     def hi(self, which: int) -> Tensor:
-        return self.f32[which]
+        return self.f32[which][0]
 
     def lo(self, which: int, nprod: int, fmt: int = 0) -> Optional[Tensor]:
+        planes = self.f32[which]
         if nprod == 3:
-            return self.f32[which + 1]
+            return planes[1]
         if nprod == 2:
             t = self._bf.get((which, fmt))
             if t is None:
-                n = self.f32.shape[1]
-                t = torch.empty((2 * n,), dtype=torch.float16 if fmt == _lib.CORR_FP16 else torch.bfloat16, device=self.f32.device)
-                call("pvg_pack_16x2", self.f32[which].data_ptr(), self.f32[which + 1].data_ptr(), t.data_ptr(), n, fmt, _stream())
+                n = planes.shape[1]
+                t = torch.empty((2 * n,), dtype=torch.float16 if fmt == _lib.CORR_FP16 else torch.bfloat16, device=planes.device)
+                call("pvg_pack_16x2", planes[0].data_ptr(), planes[1].data_ptr(), t.data_ptr(), n, fmt, _stream())
                 self._bf[(which, fmt)] = t
             return t
         return None
 
 
-def _get_packs(weight: Tensor, cin_p: int, round_hi: bool) -> _Packs:
-    """Packed (+tf32-split) copies of a conv weight, cached ON the tensor object (so a recycled allocation can never
-    alias a stale pack) and rebuilt when the tensor's autograd version or the global weights epoch moves."""
+def _get_packs(weight: Tensor, cin_rows: int, tensor_core: bool) -> _Packs:
+    """Packed (+tf32-split) copies of a conv weight for an activation with ``cin_rows`` physical channels, cached ON the
+    tensor object (so a recycled allocation can never alias a stale pack) and rebuilt when the tensor's autograd version or
+    the global weights epoch moves.  Tensor-core consumers get tf32-rounded hi planes and K-side channel counts rounded up
+    to 32 (zero filled); CUDA-core consumers the exact fp32 values and the unpadded counts."""
     cache = getattr(weight, "_pvg_packs", None)
     if cache is None:
         cache = {}
@@ -153,27 +156,38 @@ def _get_packs(weight: Tensor, cin_p: int, round_hi: bool) -> _Packs:
             weight._pvg_packs = cache
         except Exception:
             pass
-    key = (cin_p, round_hi)
+    key = (cin_rows, tensor_core)
     hit = cache.get(key)
     ver = (weight._version, weights_epoch)
     if hit is not None and hit[0] == ver:
         return hit[1]
     cout, cin, r, s = weight.shape
+    cin_k, cout_k = (_pad32(cin_rows), _pad32(cout)) if tensor_core else (cin_rows, cout)
     w = weight.detach().contiguous()
-    bufs = torch.empty((4, cout * r * s * cin_p), dtype=torch.float32, device=weight.device)
-    call("pvg_pack_conv_weight", w.data_ptr(), cout, cin, r, s, cin_p, 1 if round_hi else 0,
-         bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), _stream())
-    packs = _Packs(bufs)
+    fwd = torch.empty((2, cout * r * s * cin_k), dtype=torch.float32, device=weight.device)
+    bwd = torch.empty((2, cin_rows * r * s * cout_k), dtype=torch.float32, device=weight.device)
+    call("pvg_pack_conv_weight", w.data_ptr(), cout, cin, r, s, cin_rows, cin_k, cout_k, 1 if tensor_core else 0,
+         fwd[0].data_ptr(), fwd[1].data_ptr(), bwd[0].data_ptr(), bwd[1].data_ptr(), _stream())
+    packs = _Packs(fwd, bwd)
     cache[key] = (ver, packs)
     return packs
+
+
+# channel counts the tensor-core kernels take: any multiple of 8 (16-byte TMA strides of the 16-bit planes); counts that are
+# not a multiple of 32 are completed with zeros by TMA out-of-bounds fill (weights are packed with the padded count)
+_TC_CIN_MULTIPLE = 32 if os.environ.get("PVG_NO_OOB_PAD") == "1" else 8
+
+
+def _pad32(c: int) -> int:
+    return (c + 31) // 32 * 32
 
 
 def _conv_algo(cin_phys: int, cout: int = 1 << 30, ksize: int = 3, role: str = "fwd") -> Tuple[int, int, int]:
     """(algo, nprod, corr_fmt) for a conv whose A operand has cin_phys physical channels and which produces cout channels.
     The CUDA-core path (fp32, incl. the direct kernels of conv_direct.cu) takes the image-facing layers: A operands that
     are not a multiple of 32 channels wide, and outputs of <= 4 channels (tanh heads, gradients w.r.t. images)."""
-    if _precision == "fp32" or cin_phys % 32 != 0 or (cout <= 4 and ksize <= (7 if cout <= 3 else 3)
-                                                       and os.environ.get("PVG_NO_DIRECT") != "1"):
+    if _precision == "fp32" or cin_phys % _TC_CIN_MULTIPLE != 0 or (cout <= 4 and ksize <= (7 if cout <= 3 else 3)
+                                                                      and os.environ.get("PVG_NO_DIRECT") != "1"):
         return ALGO_SIMT, 1, 0
     return (ALGO_UMMA,) + _mode(role)
 
@@ -280,8 +294,8 @@ class Conv2dFn(torch.autograd.Function):
         dy = nhwc(dy)
         dmode = _mode("dgrad")            # (nprod, fmt) of the data-gradient kernel (conv_umma.cu)
         wmode = _mode("wgrad")            # ... of the weight-gradient kernel (conv_wgrad_umma.cu)
-        want_dx = ctx.needs_input_grad[0] and cout % 32 == 0 and dmode[0] >= 2
-        want_dw = ctx.needs_input_grad[1] and cin_p % 32 == 0 and cout % 4 == 0 and wmode[0] >= 2
+        want_dx = ctx.needs_input_grad[0] and cout % _TC_CIN_MULTIPLE == 0 and dmode[0] >= 2
+        want_dw = ctx.needs_input_grad[1] and cin_p % _TC_CIN_MULTIPLE == 0 and cout % 4 == 0 and wmode[0] >= 2
         g_splits = {}                     # (nprod, fmt) -> (hi, lo) of g
         if act != ACT_NONE:
             g = torch.empty_like(dy)
@@ -321,7 +335,7 @@ class Conv2dFn(torch.autograd.Function):
             nprod, wfmt = wmode
             d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod, wfmt)
             head7 = r == 7 and cout <= 3 and cin_p <= 32 and os.environ.get("PVG_NO_DIRECT") != "1"
-            if _precision != "fp32" and cin_p % 32 == 0 and not head7:
+            if _precision != "fp32" and cin_p % _TC_CIN_MULTIPLE == 0 and not head7:
                 # tensor-core weight gradient; dY needs a channel count that is a multiple of 4 (16-byte TMA strides):
                 # the 3-channel image heads and the 65-channel encoder tail are zero-padded (a few MB)
                 cout4 = (cout + 3) // 4 * 4
@@ -337,7 +351,7 @@ class Conv2dFn(torch.autograd.Function):
                 else:
                     g4, dw4 = g, dw
                     g_pair = split_g(wmode) if nprod >= 2 else (g, None)
-                scratch = torch.zeros((cout4 * r * s * cin_p,), dtype=torch.float32, device=dy.device)
+                scratch = torch.zeros((cout4 * r * s * _pad32(cin_p),), dtype=torch.float32, device=dy.device)
                 x_hi, x_lo = _split(x, nprod, wfmt) if nprod >= 2 else (x, None)
                 g_hi, g_lo = g_pair
                 prof = wgrad_profile is not None

@@ -77,7 +77,9 @@ CONV_UMMA_SHAPES = [  # N, Cin_logical, Cin_physical, Cout, H, W, k, bias, act
     (2, 32, 32, 64, 16, 16, 3, False, 0), (1, 64, 64, 65, 32, 32, 3, False, 0), (2, 128, 128, 128, 32, 32, 3, False, 0),
     (2, 201, 224, 512, 8, 8, 3, True, 0), (3, 64, 64, 128, 12, 20, 1, False, 0), (1, 32, 32, 3, 64, 64, 7, True, 3),
     (2, 64, 64, 64, 26, 20, 3, True, 2), (1, 128, 128, 3, 16, 16, 3, True, 3), (8, 256, 256, 256, 4, 4, 3, False, 0),
-    (1, 64, 64, 64, 128, 128, 3, True, 2), (2, 521, 544, 1024, 16, 16, 3, True, 0)]
+    (1, 64, 64, 64, 128, 128, 3, True, 2), (2, 521, 544, 1024, 16, 16, 3, True, 0),
+    # channel counts that are not a multiple of 32: the K loop is completed by TMA out-of-bounds zero fill
+    (2, 16, 16, 16, 20, 24, 3, False, 0), (1, 16, 16, 32, 16, 16, 1, True, 0), (2, 40, 40, 48, 12, 12, 3, False, 2)]
 
 
 def _conv_case(shape, seed=0):
@@ -139,6 +141,8 @@ def test_conv_umma_forward_tf32(shape):
                                    (2, 3, 3, 16, 16, 16, 3, False, 0), (1, 64, 64, 65, 16, 16, 1, False, 0),
                                    (2, 32, 32, 3, 16, 16, 7, True, 3), (2, 137, 160, 256, 16, 16, 3, False, 0),
                                    (2, 32, 32, 3, 40, 70, 7, True, 3), (1, 16, 16, 3, 21, 36, 7, True, 0),
+                                   (2, 16, 16, 16, 16, 16, 3, False, 0), (2, 16, 16, 32, 12, 20, 3, True, 0),
+                                   (1, 16, 16, 32, 16, 16, 1, False, 0), (2, 40, 40, 24, 12, 12, 3, False, 0),
                                    (8, 64, 64, 32, 64, 64, 3, False, 0), (3, 64, 64, 128, 26, 20, 3, True, 0),
                                    (2, 96, 96, 16, 16, 16, 1, False, 0), (2, 256, 256, 132, 8, 8, 3, False, 0)])
 def test_conv_backward(shape, corr):
