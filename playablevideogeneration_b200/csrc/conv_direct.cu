@@ -400,8 +400,81 @@ __global__ void __launch_bounds__(KS * 32) wgrad_cout4_tiled_kernel(const float*
   }
 }
 
+// Weight gradient of a 3x3 image stem (Cin = 3 or 12 input channels, e.g. the encoder's conv1 3S -> 16): the layer is
+// HBM-bound (x and dY are each read once: 76 B per pixel for 3 -> 16), so persistent CTAs stream 8 x 32-pixel tiles: the x
+// patch (with halo) goes through shared memory, thread = (output channel, 1 of 16 pixel lanes) keeps all 9*CIN taps of its
+// channel in registers, dY is read straight from global memory (16 consecutive channels x 2 pixels per warp).  One
+// shuffle + shared-memory reduction and one global atomic per output and CTA at the end.
+template <int CIN>
+__global__ void __launch_bounds__(256) wgrad_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              float* __restrict__ dw, int N, int H, int W, int Cout) {
+  constexpr int TH = 8, TW = 32, PH = TH + 2, PW = TW + 2, KT = 9 * CIN;
+  __shared__ float xs[PH * PW * CIN];
+  __shared__ float red[16 * KT];
+  const int co = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int co_g = blockIdx.y * 16 + co;
+  const bool co_ok = co_g < Cout;
+  const int tiles_w = ceil_div(W, TW), tiles_h = ceil_div(H, TH);
+  const int tiles_total = tiles_w * tiles_h * N;
+  float acc[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+  for (int i = threadIdx.x; i < 16 * KT; i += 256) red[i] = 0.f;
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    int t = tile;
+    const int tile_w = t % tiles_w; t /= tiles_w;
+    const int tile_h = t % tiles_h;
+    const int n = t / tiles_h;
+    const int ow0 = tile_w * TW, oh0 = tile_h * TH;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PH * PW * CIN; i += 256) {
+      const int c = i % CIN, pix = i / CIN;
+      const int py = pix / PW, px = pix - py * PW;
+      const int ih = oh0 + py - 1, iw = ow0 + px - 1;
+      xs[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (((int64_t)n * H + ih) * W + iw) * CIN + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < (TH * TW) / 16; ++i) {
+      const int pix = pl + 16 * i;
+      const int py = pix / TW, px = pix - py * TW;
+      const int oh = oh0 + py, ow = ow0 + px;
+      const float g = (co_ok && oh < H && ow < W) ? __ldg(dy + (((int64_t)n * H + oh) * W + ow) * Cout + co_g) : 0.f;
+      const float* xp = xs + (py * PW + px) * CIN;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3 * CIN; ++k) acc[r * 3 * CIN + k] = fmaf(g, xp[r * PW * CIN + k], acc[r * 3 * CIN + k]);
+    }
+  }
+  // lanes l and l + 16 of a warp hold the same output channel
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    float v = acc[k] + __shfl_xor_sync(0xffffffffu, acc[k], 16);
+    if ((threadIdx.x & 16) == 0) atomicAdd(&red[co * KT + k], v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * KT; i += 256) {
+    const int c = i / KT, k = i - c * KT;          // k = (r*3 + s) * CIN + ci
+    const int cg = blockIdx.y * 16 + c;
+    if (cg < Cout) {
+      const int tap = k / CIN, ci = k - tap * CIN;
+      atomicAdd(dw + ((int64_t)cg * CIN + ci) * 9 + tap, red[i]);
+    }
+  }
+}
+
 // returns 1 when the tiled weight-gradient kernel took the problem, 0 otherwise, < 0 on error
 int conv2d_wgrad_direct(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* dy, float* dw, cudaStream_t st) {
+  if (d->R == 3 && d->S == 3 && (d->Cin == 3 || d->Cin == 12) && Cin_logical == d->Cin) {      // image stems
+    const int64_t tiles = (int64_t)ceil_div(d->W, 32) * ceil_div(d->H, 8) * d->N;
+    const int64_t cap = (int64_t)kSMs * 4;
+    dim3 grid((unsigned)(tiles < cap ? tiles : cap), ceil_div(d->Cout, 16));
+    if (d->Cin == 3) wgrad_small_cin_kernel<3><<<grid, 256, 0, st>>>(x, dy, dw, d->N, d->H, d->W, d->Cout);
+    else wgrad_small_cin_kernel<12><<<grid, 256, 0, st>>>(x, dy, dw, d->N, d->H, d->W, d->Cout);
+    PVG_LAUNCH_OK();
+    return 1;
+  }
   if (!(d->R == 7 && d->S == 7 && d->Cout <= 3 && d->Cin <= 32 && d->Cin % 4 == 0 && (((uintptr_t)x) & 15) == 0)) return 0;
   constexpr int KS = 7, PH = 4 + KS - 1, PW = 32 + KS - 1;
   const int smem = PH * PW * 32 * 4 + 4 * 32 * 16;

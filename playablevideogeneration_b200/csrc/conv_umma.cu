@@ -725,8 +725,8 @@ static bool use_pairs(const pvg_conv_desc* d) {
   }
   if (forced >= 0) return forced == 1;
   const int k_iters = d->R * d->S * ((d->Cin + 31) / 32);
-  const int64_t m_tiles = ((int64_t)d->N * d->H * d->W + 127) / 128;
-  return k_iters >= 18 && m_tiles >= 2 * kSMs;
+  const int64_t tiles = (((int64_t)d->N * d->H * d->W + 127) / 128) * ((d->Cout + 127) / 128);     // CTAs of the 1-CTA kernel
+  return k_iters >= 18 && tiles >= 2 * kSMs;
 }
 
 // PVG_KC=16 selects the 16-channel (SWIZZLE_64B) stage for the 3xTF32 128-wide tiles (A/B experiment knob)

@@ -208,24 +208,33 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
       tc_fence_before();
       mbar_arrive(&tempty_bar[b]);
     }
-    // dwp[co][tap][ci]: for a fixed co the 32 lanes of a warp hit 32 consecutive ci -> one coalesced 128-byte reduction
-    float* out = p.dwp + (int64_t)tap * p.CinP + ci;
+    // dwp[co][tap][ci]: for a fixed co the 32 lanes of a warp hit 32 consecutive ci -> one coalesced 128-byte reduction.
+    // Bounds are tested once per 16 channels and the address advances by a constant stride (the per-element form cost ~8
+    // instructions per value: with split-K CTAs of a few microseconds the epilogue was a third of the kernel).
+    // NPROD == 2: the residual planes carry a 2^12 factor (pvg_split_16), so does the correction accumulator
+    constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
     const int64_t co_stride = (int64_t)p.R * p.S * p.CinP;
+    float* out = p.dwp + (int64_t)tap * p.CinP + ci + (int64_t)co0 * co_stride;
 #pragma unroll
     for (int c = 0; c < BN; c += 16) {
       float v[16];
       if (NPROD >= 2) {
         tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], kCorrScale, acc[c + j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = acc[c + j];
       }
-      if (ok) {
-        // NPROD == 2: the residual planes carry a 2^12 factor (pvg_split_16), so does the correction accumulator
-        constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
+      if (ok && co0 + c < p.Cout) {
+        if (co0 + c + 16 <= p.Cout) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (co0 + c + j < p.Cout) atomicAdd(out + (co0 + c + j) * co_stride, acc[c + j] + v[j] * kCorrScale);
+          for (int j = 0; j < 16; ++j) atomicAdd(out + (c + j) * co_stride, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (co0 + c + j < p.Cout) atomicAdd(out + (c + j) * co_stride, v[j]);
+        }
       }
     }
   }

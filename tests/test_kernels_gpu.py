@@ -143,6 +143,8 @@ def test_conv_umma_forward_tf32(shape):
                                    (2, 32, 32, 3, 40, 70, 7, True, 3), (1, 16, 16, 3, 21, 36, 7, True, 0),
                                    (2, 16, 16, 16, 16, 16, 3, False, 0), (2, 16, 16, 32, 12, 20, 3, True, 0),
                                    (1, 16, 16, 32, 16, 16, 1, False, 0), (2, 40, 40, 24, 12, 12, 3, False, 0),
+                                   (2, 3, 3, 16, 37, 45, 3, True, 0), (1, 12, 12, 16, 12, 36, 3, False, 0),
+                                   (1, 3, 3, 64, 20, 20, 3, False, 0),
                                    (8, 64, 64, 32, 64, 64, 3, False, 0), (3, 64, 64, 128, 26, 20, 3, True, 0),
                                    (2, 96, 96, 16, 16, 16, 1, False, 0), (2, 256, 256, 132, 8, 8, 3, False, 0)])
 def test_conv_backward(shape, corr):
