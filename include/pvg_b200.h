@@ -82,9 +82,10 @@ int pvg_conv2d_wgrad(const pvg_conv_desc* d, int Cin_logical, const float* x, co
                      void* stream);
 /* Tensor-core weight gradient (tcgen05, MN-major tf32 operands, split-K over pixel patches).  x: [N,H,W,d->Cin]
  * (d->Cin % 32 == 0), g = dY: [N,H,W,d->Cout] (d->Cout % 4 == 0), *_lo their 3xTF32 residual planes (nprod == 3, else
- * NULL).  scratch: float[Cout*R*S*Cin], zero-initialised by the caller.  dw_oihw[co][ci<Cin_logical][r][s] += result. */
+ * NULL).  scratch: float[Cout*R*S*roundup(Cin,32)], zero-initialised by the caller.
+ * dw_oihw[co][ci<Cin_logical][r][s] = result (+ its previous content when accumulate != 0). */
 int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const void* x_lo, const float* g,
-                          const void* g_lo, float* scratch, float* dw_oihw, void* stream);
+                          const void* g_lo, float* scratch, float* dw_oihw, int accumulate, void* stream);
 /* out[c] = sum over M rows of x[M][C]  (bias gradient); scratch: double[C] */
 int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* out, void* stream);
 /* hi != NULL: hi = rna_tf32(x), lo = x - hi.  hi == NULL: lo = x - trunc_tf32(x) (x itself then serves as the hi
@@ -118,6 +119,11 @@ int pvg_pool2_stats(const float* x, int N, int H, int W, int C, float* y, int gr
  * exactly as `groups` successive nn.BatchNorm2d training calls would. count = elements per channel per group. */
 int pvg_bn_finalize(const double* sums, int64_t count, int groups, int C, float eps, float momentum,
                     float* running_mean, float* running_var, float* mean, float* invstd, void* stream);
+/* pvg_bn_finalize + pvg_bn_apply in one launch (training mode; needs groups * C * 8 bytes <= 48 KB of shared memory) */
+int pvg_bn_finalize_apply(const float* x, int N, int HW, int C, int groups, const double* sums, int64_t count, float eps,
+                          float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                          const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
+                          void* stream);
 /* eval mode: mean = running_mean, invstd = rsqrt(running_var + eps) */
 int pvg_bn_eval_prepare(const float* running_mean, const float* running_var, int C, float eps,
                         float* mean, float* invstd, void* stream);
@@ -133,7 +139,8 @@ int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, in
  * eval != 0: statistics are constants: dx = weight*invstd*g. */
 int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
                      const float* mean, const float* invstd, const float* weight, int act, float slope,
-                     const double* sums2, int eval, int unpool, float* dx, float* g_out, void* stream);
+                     const double* sums2, int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias,
+                     void* stream);   /* dweight / dbias (optional): pvg_bn_bwd_params folded into the same launch */
 /* dweight[c] = sum_groups sum_gx ; dbias[c] = sum_groups sum_g */
 int pvg_bn_bwd_params(const double* sums2, int groups, int C, float* dweight, float* dbias, void* stream);
 

@@ -26,7 +26,7 @@ _SIGNATURES = {
     "pvg_conv2d_fwd": [POINTER(ConvDesc), P, P, P, P, P, P, P],
     "pvg_pack_conv_weight": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P],
     "pvg_conv2d_wgrad": [POINTER(ConvDesc), c_int, P, P, P, P],
-    "pvg_conv2d_wgrad_umma": [POINTER(ConvDesc), c_int, P, P, P, P, P, P, P],
+    "pvg_conv2d_wgrad_umma": [POINTER(ConvDesc), c_int, P, P, P, P, P, P, c_int, P],
     "pvg_channel_sum": [P, c_int64, c_int, P, P, P],
     "pvg_split_tf32": [P, P, P, c_int64, P],
     "pvg_split_16": [P, P, c_int64, c_int, P],
@@ -40,7 +40,9 @@ _SIGNATURES = {
     "pvg_bn_eval_prepare": [P, P, c_int, c_float, P, P, P],
     "pvg_bn_apply": [P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_float, P, P],
     "pvg_bn_bwd_reduce": [P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P],
-    "pvg_bn_bwd_apply": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P],
+    "pvg_bn_bwd_apply": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P, P, P],
+    "pvg_bn_finalize_apply": [P, c_int, c_int, c_int, c_int, P, c_int64, c_float, c_float, P, P, P, P, P, P, P, c_int, c_float,
+                              P, P],
     "pvg_bn_bwd_params": [P, c_int, c_int, P, P, P],
     "pvg_upsample2x_fwd": [P, c_int, c_int, c_int, c_int, P, P],
     "pvg_upsample2x_bwd": [P, c_int, c_int, c_int, c_int, P, P],

@@ -414,13 +414,16 @@ class Model(nn.Module):
     # ----------------------------------------------------------------------------------------------------------
     def forward(self, batch_tuple, ground_truth_observations_init=0, pretraining=False, gumbel_temperature=None,
                 action_sampler=None, action_variation_sampler=None):
-        if pretraining:
-            return self.forward_pretraining(batch_tuple, gumbel_temperature=gumbel_temperature,
-                                            action_sampler=action_sampler, action_variation_sampler=action_variation_sampler)
-        if ground_truth_observations_init <= 0:
-            raise Exception("To forward the full model specify a number of ground truth observations > 0")
-        return self.forward_full_model(batch_tuple, ground_truth_observations_init, gumbel_temperature=gumbel_temperature,
-                                       action_sampler=action_sampler, action_variation_sampler=action_variation_sampler)
+        try:
+            if pretraining:
+                return self.forward_pretraining(batch_tuple, gumbel_temperature=gumbel_temperature,
+                                                action_sampler=action_sampler, action_variation_sampler=action_variation_sampler)
+            if ground_truth_observations_init <= 0:
+                raise Exception("To forward the full model specify a number of ground truth observations > 0")
+            return self.forward_full_model(batch_tuple, ground_truth_observations_init, gumbel_temperature=gumbel_temperature,
+                                           action_sampler=action_sampler, action_variation_sampler=action_variation_sampler)
+        finally:
+            ops.flush_deferred()          # BatchNorm num_batches_tracked increments of this forward, one launch
 
     def _encode_sequence(self, observations):
         b, t = observations.shape[:2]

@@ -244,7 +244,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
 }
 
 __global__ void __launch_bounds__(256) unpack_dw_kernel(const float* __restrict__ dwp, int Cout, int Cin, int R, int S, int CinP,
-                                                        float* __restrict__ dw) {
+                                                        float* __restrict__ dw, int accumulate) {
   const int64_t total = (int64_t)Cout * Cin * R * S;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int s = (int)(i % S);
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(256) unpack_dw_kernel(const float* __restrict_
     int r = (int)(t % R); t /= R;
     int ci = (int)(t % Cin);
     int co = (int)(t / Cin);
-    dw[i] += dwp[((int64_t)co * R * S + r * S + s) * CinP + ci];
+    const float v = dwp[((int64_t)co * R * S + r * S + s) * CinP + ci];
+    dw[i] = accumulate ? dw[i] + v : v;
   }
 }
 
@@ -316,9 +317,9 @@ using namespace pvg;
 
 // Tensor-core weight gradient.  x: [N,H,W,CinP] (CinP % 32 == 0), g = dY: [N,H,W,Cout] (Cout % 4 == 0), *_lo their
 // 3xTF32 residual planes (nprod == 3).  scratch: float[Cout * R*S * roundup(CinP, 32)], zero-initialised by the caller.
-// dw_oihw [Cout][Cin_logical][R][S] += unpack(scratch).
+// dw_oihw [Cout][Cin_logical][R][S] = (accumulate ? dw_oihw : 0) + unpack(scratch).
 extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, const float* x, const void* x_lo_, const float* g,
-                                     const void* g_lo_, float* scratch, float* dw_oihw, void* stream) {
+                                     const void* g_lo_, float* scratch, float* dw_oihw, int accumulate, void* stream) {
   const float* x_lo = (const float*)x_lo_;      // fp32 residual planes (nprod == 3) or bf16 plane pairs (nprod == 2)
   const float* g_lo = (const float*)g_lo_;
   PVG_CHECK_ARG(d && x && g && scratch && dw_oihw, "null argument");
@@ -348,7 +349,7 @@ extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, co
   }
   if (rc) return rc;
   int64_t total = (int64_t)d->Cout * Cin_logical * d->R * d->S;
-  unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, (d->Cin + 31) & ~31, dw_oihw);
+  unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, (d->Cin + 31) & ~31, dw_oihw, accumulate);
   PVG_LAUNCH_OK();
   return 0;
 }

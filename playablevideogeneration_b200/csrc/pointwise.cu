@@ -185,13 +185,83 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(const float*
                        });
 }
 
+// bn_finalize + bn_apply in one launch (training mode): every CTA derives mean / invstd of all (group, channel) pairs from
+// the fp64 sums into shared memory (groups * C divisions + rsqrt: negligible next to the apply pass), CTA 0 also publishes
+// them for the backward pass and replays the running-statistics updates.  Saves one launch per BatchNorm call.
+template <int V>
+__global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* __restrict__ x, int64_t M, int64_t rows_per_group,
+                                                                int C, int groups, const double* __restrict__ sums, double count,
+                                                                float eps, float momentum, float* running_mean,
+                                                                float* running_var, float* __restrict__ mean,
+                                                                float* __restrict__ invstd, const float* __restrict__ weight,
+                                                                const float* __restrict__ bias, const float* __restrict__ residual,
+                                                                int act, float slope, float* __restrict__ y) {
+  extern __shared__ float sm_stats[];              // [groups][C] mean, then [groups][C] invstd
+  float* s_mean = sm_stats;
+  float* s_inv = sm_stats + (size_t)groups * C;
+  for (int i = threadIdx.x; i < groups * C; i += blockDim.x) {
+    const int g = i / C, c = i - g * C;
+    const double s = sums[((size_t)g * 2 + 0) * C + c], ss = sums[((size_t)g * 2 + 1) * C + c];
+    const double m = s / count;
+    double var = ss / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)m, isf = (float)(1.0 / sqrt(var + (double)eps));
+    s_mean[i] = mf; s_inv[i] = isf;
+    if (blockIdx.x == 0) { mean[i] = mf; invstd[i] = isf; }
+  }
+  if (blockIdx.x == 0 && (running_mean || running_var)) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+      for (int g = 0; g < groups; ++g) {
+        const double s = sums[((size_t)g * 2 + 0) * C + c], ss = sums[((size_t)g * 2 + 1) * C + c];
+        const double m = s / count;
+        double var = ss / count - m * m;
+        if (var < 0.0) var = 0.0;
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        rm = (1.f - momentum) * rm + momentum * (float)m;
+        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+      }
+      if (running_mean) running_mean[c] = rm;
+      if (running_var) running_var[c] = rv;
+    }
+  }
+  __syncthreads();
+  const int U = C / V;
+  const int64_t total = M * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / U;
+    int c = (int)(i % U) * V;
+    int g = (int)(r / rows_per_group);
+    Vec<V> t = Vec<V>::load(x + r * C + c), o;
+    Vec<V> res;
+    if (residual) res = Vec<V>::load(residual + r * C + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float w = weight ? __ldg(weight + c + j) : 1.f, b = bias ? __ldg(bias + c + j) : 0.f;
+      float v = (t.v[j] - s_mean[(size_t)g * C + c + j]) * s_inv[(size_t)g * C + c + j] * w + b;
+      if (residual) v += res.v[j];
+      o.v[j] = act_fwd(v, act, slope);
+    }
+    o.store(y + r * C + c);
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                            const float* __restrict__ x, int64_t M, int64_t rows_per_group,
                                                            int OH, int OW, int C, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ weight,
                                                            int act, float slope, const double* __restrict__ sums2, int eval,
-                                                           int unpool, float* __restrict__ dx, float* __restrict__ g_out) {
+                                                           int unpool, float* __restrict__ dx, float* __restrict__ g_out,
+                                                           int groups, float* __restrict__ dweight, float* __restrict__ dbias) {
+  if (blockIdx.x == 0 && (dweight || dbias)) {       // bn_bwd_params folded in: one launch less per BatchNorm backward
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double sg = 0.0, sgx = 0.0;
+      for (int g = 0; g < groups; ++g) { sg += sums2[((size_t)g * 2 + 0) * C + c]; sgx += sums2[((size_t)g * 2 + 1) * C + c]; }
+      if (dweight) dweight[c] = (float)sgx;
+      if (dbias) dbias[c] = (float)sg;
+    }
+  }
   const int U = C / V;
   const int64_t total = M * U;
   const double inv_count = 1.0 / (double)rows_per_group;
@@ -746,6 +816,21 @@ int pvg_bn_apply(const float* x, int N, int HW, int C, int groups, const float* 
   return 0;
 }
 
+int pvg_bn_finalize_apply(const float* x, int N, int HW, int C, int groups, const double* sums, int64_t count, float eps,
+                          float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                          const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
+                          void* stream) {
+  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  const size_t smem = (size_t)groups * C * 2 * sizeof(float);
+  PVG_CHECK_ARG(smem <= 48 * 1024, "groups * C too large for the fused kernel: call pvg_bn_finalize + pvg_bn_apply");
+  int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
+  DISPATCH_V(C, (bn_finalize_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, smem, (cudaStream_t)stream>>>(
+                    x, M, rpg, C, groups, sums, (double)count, eps, momentum, running_mean, running_var, mean, invstd, weight,
+                    bias, residual, act, slope, y)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
 int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, int HW, int C, int groups, const float* mean,
                       const float* invstd, int act, float slope, double* sums2, void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
@@ -761,12 +846,13 @@ int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, in
 
 int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
                      const float* mean, const float* invstd, const float* weight, int act, float slope, const double* sums2,
-                     int eval, int unpool, float* dx, float* g_out, void* stream) {
+                     int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias, void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
   int OH = unpool ? H / 2 : H, OW = unpool ? W / 2 : W;
   int64_t M = (int64_t)N * OH * OW, rpg = (int64_t)(N / groups) * OH * OW;
   DISPATCH_V(C, (bn_bwd_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
-                    dy, y, x, M, rpg, OH, OW, C, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out)));
+                    dy, y, x, M, rpg, OH, OW, C, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out, groups, dweight,
+                    dbias)));
   PVG_LAUNCH_OK();
   return 0;
 }

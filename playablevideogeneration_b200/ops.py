@@ -107,6 +107,71 @@ def nhwc(x: Tensor) -> Tensor:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# launch-count hygiene: a training step issues ~16 k kernel launches; ~2 000 of them were one-element memsets / counters
+# ---------------------------------------------------------------------------------------------------------------
+class _ZeroPool:
+    """Zero-filled scratch for accumulators that are consumed inside the op that requests them (BatchNorm sums, split-K
+    weight-gradient scratch, loss partial sums): ONE memset per optimiser step (``begin``) instead of one fill kernel per
+    request.  Outside a step (``active`` false) or when the arena is exhausted, requests fall back to ``torch.zeros``.
+    Arenas are never freed or resized in place - a captured CUDA graph may still point into an old one."""
+
+    def __init__(self):
+        self.buf: Optional[Tensor] = None
+        self.off = 0
+        self.demand = 0
+        self.active = False
+        self._keep: List[Tensor] = []
+
+    def begin(self, device) -> None:
+        need = int(self.demand * 1.25) + 4096
+        if self.demand and (self.buf is None or self.buf.numel() < need or self.buf.device != device) \
+                and not torch.cuda.is_current_stream_capturing():
+            self.buf = torch.empty((need,), dtype=torch.uint8, device=device)
+            self._keep.append(self.buf)
+        self.demand = 0
+        self.off = 0
+        self.active = self.buf is not None and self.buf.device == device
+        if self.active:
+            self.buf.zero_()
+
+    def end(self) -> None:
+        self.active = False
+
+    def zeros(self, shape, dtype, device) -> Tensor:
+        n = int(torch.empty((), dtype=dtype).element_size())
+        for d in shape:
+            n *= int(d)
+        n_al = (n + 255) // 256 * 256
+        self.demand += n_al
+        if self.active and self.off + n_al <= self.buf.numel() and self.buf.device == device:
+            v = self.buf[self.off:self.off + n].view(dtype).view(tuple(shape))
+            self.off += n_al
+            return v
+        return torch.zeros(tuple(shape), dtype=dtype, device=device)
+
+
+zero_pool = _ZeroPool()
+_deferred_counts = {}        # id(tensor) -> [tensor, pending increment]
+
+
+def defer_count(t: Tensor, inc: int) -> None:
+    """``t += inc`` for an integer counter buffer (BatchNorm's num_batches_tracked), applied by ``flush_deferred`` in one
+    multi-tensor launch instead of one tiny kernel per BatchNorm call (762 per BAIR-256 step)."""
+    e = _deferred_counts.get(id(t))
+    if e is None:
+        _deferred_counts[id(t)] = [t, inc]
+    else:
+        e[1] += inc
+
+
+def flush_deferred() -> None:
+    if _deferred_counts:
+        items = list(_deferred_counts.values())
+        _deferred_counts.clear()
+        torch._foreach_add_([t for t, _ in items], [c for _, c in items])
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # convolution
 # ---------------------------------------------------------------------------------------------------------------
 weights_epoch = 0      # bumped by optimisers that update parameters through raw pointers (no autograd version bump)
@@ -331,11 +396,13 @@ class Conv2dFn(torch.autograd.Function):
                                2.0 * n * h * w * cout * r * s * cin_log,
                                split=split_g((np_, fmt_)) if (algo == ALGO_UMMA and np_ >= 2) else None)
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
             nprod, wfmt = wmode
             d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod, wfmt)
             head7 = r == 7 and cout <= 3 and cin_p <= 32 and os.environ.get("PVG_NO_DIRECT") != "1"
-            if _precision != "fp32" and cin_p % _TC_CIN_MULTIPLE == 0 and not head7:
+            tc_wgrad = _precision != "fp32" and cin_p % _TC_CIN_MULTIPLE == 0 and not head7
+            # the tensor-core path overwrites dw (split-K partials meet in its zero-pool scratch); the CUDA-core kernels add into it
+            dw = (torch.empty_like if tc_wgrad else torch.zeros_like)(weight, memory_format=torch.contiguous_format)
+            if tc_wgrad:
                 # tensor-core weight gradient; dY needs a channel count that is a multiple of 4 (16-byte TMA strides):
                 # the 3-channel image heads and the 65-channel encoder tail are zero-padded (a few MB)
                 cout4 = (cout + 3) // 4 * 4
@@ -345,13 +412,13 @@ class Conv2dFn(torch.autograd.Function):
                     g4 = empty_nhwc((n, cout4, h, w), dy.device)
                     g4[:, :cout].copy_(g)
                     g4[:, cout:].zero_()
-                    dw4 = torch.zeros((cout4, cin_log, r, s), dtype=torch.float32, device=dy.device)
+                    dw4 = torch.empty((cout4, cin_log, r, s), dtype=torch.float32, device=dy.device)
                     d = ConvDesc(n, h, w, cin_p, cout4, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_SIMT, nprod, wfmt)
                     g_pair = _split(g4, nprod, wfmt) if nprod >= 2 else (g4, None)
                 else:
                     g4, dw4 = g, dw
                     g_pair = split_g(wmode) if nprod >= 2 else (g, None)
-                scratch = torch.zeros((cout4 * r * s * _pad32(cin_p),), dtype=torch.float32, device=dy.device)
+                scratch = zero_pool.zeros((cout4 * r * s * _pad32(cin_p),), torch.float32, dy.device)
                 x_hi, x_lo = _split(x, nprod, wfmt) if nprod >= 2 else (x, None)
                 g_hi, g_lo = g_pair
                 prof = wgrad_profile is not None
@@ -359,7 +426,7 @@ class Conv2dFn(torch.autograd.Function):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                 call("pvg_conv2d_wgrad_umma", d, cin_log, x_hi.data_ptr(), _p(x_lo), g_hi.data_ptr(), _p(g_lo),
-                     scratch.data_ptr(), dw4.data_ptr(), _stream())
+                     scratch.data_ptr(), dw4.data_ptr(), 0, _stream())
                 if prof:
                     e1.record()
                     wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout * r * s * cin_log))
@@ -394,7 +461,7 @@ class PoolBNActFn(torch.autograd.Function):
         oh, ow = (h // 2, w // 2) if pool else (h, w)
         mean = torch.empty((groups, c), dtype=torch.float32, device=dev)
         invstd = torch.empty((groups, c), dtype=torch.float32, device=dev)
-        sums = torch.zeros((groups, 2, c), dtype=torch.float64, device=dev) if (training or pool) else None
+        sums = zero_pool.zeros((groups, 2, c), torch.float64, dev) if (training or pool) else None
         if pool:
             xp = empty_nhwc((n, c, oh, ow), dev)
             call("pvg_pool2_stats", x.data_ptr(), n, h, w, c, xp.data_ptr(), groups, sums.data_ptr(), st)
@@ -402,19 +469,24 @@ class PoolBNActFn(torch.autograd.Function):
             xp = x
             if training:
                 call("pvg_bn_stats", x.data_ptr(), n, h * w, c, groups, sums.data_ptr(), st)
-        if training:
-            call("pvg_bn_finalize", sums.data_ptr(), (n // groups) * oh * ow, groups, c, float(eps), float(momentum),
-                 _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), st)
-        else:
-            if groups != 1:
-                raise _lib.PvgError("grouped statistics only exist in training mode")
-            call("pvg_bn_eval_prepare", running_mean.data_ptr(), running_var.data_ptr(), c, float(eps), mean.data_ptr(),
-                 invstd.data_ptr(), st)
         y = empty_nhwc((n, c, oh, ow), dev)
         wd = weight.detach() if weight is not None else None
         bd = bias.detach() if bias is not None else None
-        call("pvg_bn_apply", xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(), invstd.data_ptr(), _p(wd), _p(bd),
-             _p(residual), act, float(slope), y.data_ptr(), st)
+        if training and groups * c * 8 <= 48 * 1024:      # statistics finalisation fused into the apply pass
+            call("pvg_bn_finalize_apply", xp.data_ptr(), n, oh * ow, c, groups, sums.data_ptr(), (n // groups) * oh * ow,
+                 float(eps), float(momentum), _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), _p(wd),
+                 _p(bd), _p(residual), act, float(slope), y.data_ptr(), st)
+        else:
+            if training:
+                call("pvg_bn_finalize", sums.data_ptr(), (n // groups) * oh * ow, groups, c, float(eps), float(momentum),
+                     _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), st)
+            else:
+                if groups != 1:
+                    raise _lib.PvgError("grouped statistics only exist in training mode")
+                call("pvg_bn_eval_prepare", running_mean.data_ptr(), running_var.data_ptr(), c, float(eps), mean.data_ptr(),
+                     invstd.data_ptr(), st)
+            call("pvg_bn_apply", xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(), invstd.data_ptr(), _p(wd), _p(bd),
+                 _p(residual), act, float(slope), y.data_ptr(), st)
         ctx.save_for_backward(xp, weight, mean, invstd, y if act != ACT_NONE else None)
         ctx.meta = (training, pool, act, slope, groups, residual is not None, (n, c, h, w))
         return y
@@ -427,13 +499,17 @@ class PoolBNActFn(torch.autograd.Function):
         dev = dy.device
         st = _stream()
         oh, ow = (h // 2, w // 2) if pool else (h, w)
-        sums2 = torch.zeros((groups, 2, c), dtype=torch.float64, device=dev)
+        sums2 = zero_pool.zeros((groups, 2, c), torch.float64, dev)
         need_params = weight is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         if training or need_params:
             call("pvg_bn_bwd_reduce", dy.data_ptr(), _p(y), xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(),
                  invstd.data_ptr(), act, float(slope), sums2.data_ptr(), st)
         dx = empty_nhwc((n, c, h, w), dev) if ctx.needs_input_grad[0] else None
         g_out = empty_nhwc((n, c, oh, ow), dev) if (has_res and ctx.needs_input_grad[3]) else None
+        dweight = dbias = None
+        if need_params:
+            dweight = torch.empty((c,), dtype=torch.float32, device=dev)
+            dbias = torch.empty((c,), dtype=torch.float32, device=dev)
         if dx is not None or g_out is not None:
             if dx is None:        # only the residual gradient is wanted
                 dx_buf = empty_nhwc((n, c, h, w), dev)
@@ -441,11 +517,9 @@ class PoolBNActFn(torch.autograd.Function):
                 dx_buf = dx
             call("pvg_bn_bwd_apply", dy.data_ptr(), _p(y), xp.data_ptr(), n, h, w, c, groups, mean.data_ptr(),
                  invstd.data_ptr(), _p(weight.detach() if weight is not None else None), act, float(slope),
-                 sums2.data_ptr(), 0 if training else 1, 1 if pool else 0, dx_buf.data_ptr(), _p(g_out), st)
-        dweight = dbias = None
-        if need_params:
-            dweight = torch.empty((c,), dtype=torch.float32, device=dev)
-            dbias = torch.empty((c,), dtype=torch.float32, device=dev)
+                 sums2.data_ptr(), 0 if training else 1, 1 if pool else 0, dx_buf.data_ptr(), _p(g_out), _p(dweight), _p(dbias),
+                 st)                  # dweight / dbias: the parameter gradients ride along in the same launch
+        elif need_params:
             call("pvg_bn_bwd_params", sums2.data_ptr(), groups, c, dweight.data_ptr(), dbias.data_ptr(), st)
         return (dx, dweight, dbias, g_out) + (None,) * 9
 
@@ -454,7 +528,7 @@ def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, group
     """``bn`` is an nn.BatchNorm2d used purely as the parameter/buffer container (reference state_dict names)."""
     training = bn.training
     if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(groups)
+        defer_count(bn.num_batches_tracked, groups)         # applied by flush_deferred() at the end of Model.forward
     return PoolBNActFn.apply(x, bn.weight, bias_or_none(bn), residual, bn.running_mean, bn.running_var, training, pool, act,
                              slope, bn.eps, bn.momentum if bn.momentum is not None else 0.1, groups)
 
@@ -623,7 +697,7 @@ class AbsDiffMeanFn(torch.autograd.Function):
             a, b = a.contiguous(), b.contiguous()
         n = a.shape[0]
         count = a.numel() // n
-        out = torch.zeros((n,), dtype=torch.float64, device=a.device)
+        out = zero_pool.zeros((n,), torch.float64, a.device)
         call("pvg_absdiff_mean_fwd", a.data_ptr(), b.data_ptr(), n, count, out.data_ptr(), _stream())
         ctx.save_for_backward(a, b)
         return out.float()

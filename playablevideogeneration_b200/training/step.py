@@ -228,10 +228,14 @@ class TrainStep:
 
     def step(self, batch_tuple, ground_truth_observations_count: int, gumbel_temperature: float, pretraining: bool = False):
         self.module.train()
-        total, info, _ = self.compute_losses(batch_tuple, ground_truth_observations_count, gumbel_temperature, pretraining)
-        self.arena.zero_grad()
-        total.backward()
-        self.optimizer_step()
+        ops.zero_pool.begin(self.arena.flat.device)      # one memset for every accumulator scratch of this step
+        try:
+            total, info, _ = self.compute_losses(batch_tuple, ground_truth_observations_count, gumbel_temperature, pretraining)
+            self.arena.zero_grad()
+            total.backward()
+            self.optimizer_step()
+        finally:
+            ops.zero_pool.end()
         return total.detach(), info
 
 
