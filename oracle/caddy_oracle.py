@@ -515,6 +515,23 @@ class Rollout:
         frame = decoder(self.st, h)[0].squeeze(0)
         return frame, torch.cat([frame, observation[:-3]], dim=0)
 
+    def generate_next_interpolation(self, observation: Tensor, first_action: int, second_action: int, factor: float):
+        """Model.generate_next_interpolation, model/main_model/model.py:609-655: the action whose centroid is nearer on the
+        interpolation line is selected (factor > 0.5 -> second), the variation is the offset of the interpolated point
+        from that centroid."""
+        cfg = self.cfg
+        A = cfg["data"]["actions_count"]
+        c = self.st.sd["centroid_estimator.estimated_centroids"]
+        selected = second_action if factor > 0.5 else first_action
+        point = (c[second_action] - c[first_action]) * factor + c[first_action]
+        var = (point - c[selected]).unsqueeze(0)
+        onehot = torch.zeros((1, A)); onehot[0, selected] = 1.0
+        state, _ = encoder(self.st, observation.unsqueeze(0))
+        torch.randn((1, cfg["model"]["dynamics_network"]["random_noise_size"]))
+        h = self.dyn.step(state, onehot, var)
+        frame = decoder(self.st, h)[0].squeeze(0)
+        return frame, torch.cat([frame, observation[:-3]], dim=0)
+
 
 # --------------------------------------------------------------------------------------------------------------
 # losses (training/losses.py) and the trainer's weighted sum (training/trainer.py)

@@ -133,4 +133,7 @@ CASES = {
                          actions=[0, 3, 6, 1], noise=False),
     "rollout_tennis_noise": dict(mode="rollout", config="tennis", S=4, H=32, W=64, weight_seed=6, input_seed=6,
                                  noise_seed=10, actions=[2, 2, 5], noise=True),
+    # interpolate.py: generate_next_interpolation(observation, first_action, second_action, factor) after one plain step
+    "rollout_bair_interp": dict(mode="rollout", config="bair", S=1, H=64, W=64, weight_seed=7, input_seed=8, noise_seed=12,
+                                actions=[4], noise=False, interp=[[0, 3, 0.25], [1, 5, 0.8], [6, 2, 0.5]]),
 }

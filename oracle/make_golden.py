@@ -107,6 +107,9 @@ def run_rollout_case(case: dict) -> dict:
         for i, a in enumerate(case["actions"]):
             frame, obs = model.generate_next(obs, a, noise=case.get("noise", False))
             out[f"frame.{i}"] = frame.numpy()
+        for i, (a1, a2, f) in enumerate(case.get("interp", [])):
+            frame, obs = model.generate_next_interpolation(obs, a1, a2, f)
+            out[f"iframe.{i}"] = frame.numpy()
     return out
 
 

@@ -132,6 +132,16 @@ class ParallelPerceptualLoss:
         return total.mean(), [s.mean() for s in singles]
 
 
+class KLDivergence:
+    """training/losses.py:121-143 (debug-only in the reference): KL(softmax(target) || softmax(input)), batch mean."""
+
+    def __call__(self, input_logits: torch.Tensor, target_logits: torch.Tensor) -> torch.Tensor:
+        a = input_logits.size(-1)
+        logp = F.log_softmax(input_logits.reshape(-1, a), dim=1)
+        q = F.softmax(target_logits.reshape(-1, a), dim=1)
+        return F.kl_div(logp, q, reduction="batchmean")
+
+
 class KLGaussianDivergenceLoss:
     """losses.py:146-169."""
 

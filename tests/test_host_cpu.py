@@ -137,3 +137,6 @@ def test_rollout_host_logic_with_cpu_standins(name, fake_ops):
         for i, a in enumerate(case["actions"]):
             frame, obs = model.generate_next(obs, a, noise=case.get("noise", False))
             np.testing.assert_allclose(frame.numpy(), g[f"frame.{i}"], rtol=2e-5, atol=2e-5)
+        for i, (a1, a2, f) in enumerate(case.get("interp", [])):
+            frame, obs = model.generate_next_interpolation(obs, a1, a2, f)
+            np.testing.assert_allclose(frame.numpy(), g[f"iframe.{i}"], rtol=2e-5, atol=2e-5)

@@ -166,6 +166,11 @@ def test_rollout_matches_reference_golden(name):
             err = float(np.abs(frame.cpu().numpy() - g[f"frame.{i}"]).max())
             _log(name, step=i, max_abs_err=err)
             assert err <= 1e-3, (i, err)
+        for i, (a1, a2, f) in enumerate(case.get("interp", [])):          # interpolate.py:152
+            frame, obs = model.generate_next_interpolation(obs, a1, a2, f)
+            err = float(np.abs(frame.cpu().numpy() - g[f"iframe.{i}"]).max())
+            _log(name, interp_step=i, max_abs_err=err)
+            assert err <= 1e-3, (i, err)
 
 
 def test_cuda_path_matches_cpu_oracle_on_fresh_seed():

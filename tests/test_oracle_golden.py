@@ -64,6 +64,9 @@ def test_oracle_rollout_matches_reference(name):
         for i, a in enumerate(case["actions"]):
             frame, obs = roll.generate_next(obs, a, noise=case.get("noise", False))
             np.testing.assert_allclose(frame.numpy(), g[f"frame.{i}"], rtol=2e-5, atol=2e-5)
+        for i, (a1, a2, f) in enumerate(case.get("interp", [])):
+            frame, obs = roll.generate_next_interpolation(obs, a1, a2, f)
+            np.testing.assert_allclose(frame.numpy(), g[f"iframe.{i}"], rtol=2e-5, atol=2e-5)
 
 
 def test_weight_recipe_covers_reference_state_dict():
