@@ -65,11 +65,8 @@ case $s in
   ncu_vgg1) run ncu_vgg1 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 2 -c 1 -f -o $OUT/prof_vgg1 python tools/one_conv.py 120 64 64 256 256 ;;
   ncu_vgg3_tf32) PVG_PRECISION=tf32 run ncu_vgg3_tf32 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 2 -c 1 -f -o $OUT/prof_vgg3_tf32 python tools/one_conv.py 120 256 256 64 64 ;;
   tile_model) PVG_2CTA=0 run tile_model0 300 python tools/tile_model.py tf32x3; PVG_2CTA=1 run tile_model1 300 python tools/tile_model.py tf32x3; PVG_2CTA=0 run tile_model0_tf32 300 python tools/tile_model.py tf32; PVG_2CTA=0 run tile_model0_64 300 python tools/tile_model.py tf32x3 64; PVG_2CTA=0 PVG_CORR=tf32 run tile_model0_c3 300 python tools/tile_model.py tf32x3 ;;
-  diag_oob) for c in "PVG_NO_OOB_PAD=1" "PVG_CORR=tf32" "PVG_CORR=bf16" "PVG_DGRAD_CORR=tf32" "PVG_X=1"; do echo "--- $c" | tee -a $OUT/summary.txt; env $c timeout 300 python -m pytest tests/test_model_gpu.py -q -m gpu -k "pretrain_bair" -p no:cacheprovider > $OUT/diag_oob.log 2>&1; tail -1 $OUT/diag_oob.log | tee -a $OUT/summary.txt; grep pretrain_bair:cond $OUT/model_errors.jsonl | tail -1 | cut -c1-330 | tee -a $OUT/summary.txt; done ;;
-  oob_diag) run oob_diag 300 python tools/oob_diag.py ;;
   head_stress) run head_stress 300 python tools/head_stress.py 60 ;;
   head_san) run head_race 600 compute-sanitizer --tool racecheck --print-limit 5 python tools/head_stress.py 1; run head_init 600 compute-sanitizer --tool initcheck --print-limit 5 python tools/head_stress.py 1; run head_mem 600 compute-sanitizer --tool memcheck --print-limit 5 python tools/head_stress.py 1 ;;
-  order_diag) run order_diag 300 python tools/order_diag.py ;;
   san_tests) PYTORCH_NO_CUDA_MEMORY_CACHING=1 run san_tests 500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "conv_simt or probe or umma_forward_tf32x3 or conv_backward" -p no:cacheprovider ;;
   corr_diag) run corr_diag 300 python tools/corr_diag.py ;;
 esac
