@@ -124,8 +124,8 @@ class _ZeroPool:
 
     def begin(self, device) -> None:
         need = int(self.demand * 1.25) + 4096
-        if self.demand and (self.buf is None or self.buf.numel() < need or self.buf.device != device) \
-                and not torch.cuda.is_current_stream_capturing():
+        capturing = torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if self.demand and (self.buf is None or self.buf.numel() < need or self.buf.device != device) and not capturing:
             self.buf = torch.empty((need,), dtype=torch.uint8, device=device)
             self._keep.append(self.buf)
         self.demand = 0

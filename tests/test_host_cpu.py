@@ -140,3 +140,39 @@ def test_rollout_host_logic_with_cpu_standins(name, fake_ops):
         for i, (a1, a2, f) in enumerate(case.get("interp", [])):
             frame, obs = model.generate_next_interpolation(obs, a1, a2, f)
             np.testing.assert_allclose(frame.numpy(), g[f"iframe.{i}"], rtol=2e-5, atol=2e-5)
+
+
+def test_zero_pool_and_deferred_counters():
+    """Launch hygiene helpers of ops.py (host logic only): the per-step zero pool hands out disjoint, zero-filled, correctly
+    typed views after one memset, falls back to torch.zeros outside a step or when exhausted, never resizes an arena in
+    place; deferred integer counters are applied once by flush_deferred()."""
+    from playablevideogeneration_b200 import ops
+    pool = ops._ZeroPool()
+    dev = torch.device("cpu")
+    a = pool.zeros((3, 2, 5), torch.float64, dev)                 # outside a step: plain zeros, but demand is recorded
+    assert a.dtype == torch.float64 and a.shape == (3, 2, 5) and float(a.abs().sum()) == 0.0 and pool.demand > 0
+    pool.begin(dev)                                               # sizes the arena from the recorded demand
+    first = pool.buf
+    assert pool.active and first is not None
+    x = pool.zeros((7,), torch.float32, dev)
+    y = pool.zeros((2, 2, 4), torch.float64, dev)
+    x.fill_(3.0); y.fill_(5.0)
+    assert float(x.sum()) == 21.0 and float(y.sum()) == 80.0      # disjoint regions
+    assert x.data_ptr() % 256 == first.data_ptr() % 256 and (y.data_ptr() - x.data_ptr()) % 256 == 0
+    big = pool.zeros((1 << 20,), torch.float32, dev)              # exhausted -> fallback, still zero
+    assert float(big.abs().sum()) == 0.0 and big.data_ptr() != first.data_ptr()
+    pool.end()
+    assert not pool.active
+    pool.begin(dev)                                               # demand grew: a NEW arena, the old one is kept alive
+    assert pool.buf is not first and any(b is first for b in pool._keep)
+    z = pool.zeros((7,), torch.float32, dev)
+    assert float(z.abs().sum()) == 0.0                            # the memset of begin() cleared whatever lived here
+    pool.end()
+
+    c1, c2 = torch.zeros((), dtype=torch.long), torch.tensor(4, dtype=torch.long)
+    ops.defer_count(c1, 1); ops.defer_count(c2, 2); ops.defer_count(c1, 3)
+    assert int(c1) == 0 and int(c2) == 4                          # nothing applied yet
+    ops.flush_deferred()
+    assert int(c1) == 4 and int(c2) == 6
+    ops.flush_deferred()                                          # idempotent when nothing is pending
+    assert int(c1) == 4 and int(c2) == 6
