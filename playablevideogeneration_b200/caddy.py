@@ -381,6 +381,69 @@ class CentroidEstimator(nn.Module):
         return var.reshape(tuple(lead + [-1]))
 
 
+class GraphedRollout:
+    """One CUDA graph per rollout step (E -> R -> D, eval mode) for a fixed batch and frame shape.
+
+    play.py / interpolate.py generate one frame per call at batch 1: ~150 kernel launches of a few microseconds each, i.e.
+    the step is pure launch latency.  The graph replays them with one cudaGraphLaunch.  What makes the
+    step capturable: the ConvLSTM memory lives in static buffers that the captured step reads and overwrites, the inputs
+    (observation, one-hot action, variation) are copied into static buffers before each replay, and the reference's unused
+    per-step noise draw (model.py:496) stays on the host, outside the graph, so the CPU RNG stream is unchanged.
+    Weight packs are captured by address: rebuild the graph (``Model.enable_graphed_inference``) after loading new weights."""
+
+    def __init__(self, model: "Model", obs_shape, device):
+        self.model = model
+        self.key = (tuple(obs_shape), torch.device(device))
+        b = obs_shape[0]
+        dim = model.config["model"]["action_network"]["action_space_dimension"]
+        self.obs = torch.zeros(tuple(obs_shape), dtype=torch.float32, device=device)
+        self.onehot = torch.zeros((b, model.actions_count), dtype=torch.float32, device=device)
+        self.var = torch.zeros((b, dim), dtype=torch.float32, device=device)
+        self.lstms = list(model.dynamics_network.recurrent_layers)
+        with torch.no_grad():
+            self.h = [ops.nhwc(l.initial_hidden_state.detach().unsqueeze(0).expand(b, -1, -1, -1)).clone() for l in self.lstms]
+            self.c = [ops.nhwc(l.initial_hidden_cell_state.detach().unsqueeze(0).expand(b, -1, -1, -1)).clone() for l in self.lstms]
+            rng = torch.get_rng_state()          # warm-up and capture run the host-side noise draw: not part of the rollout
+            for l in self.lstms:
+                l._w, l._b = l.cell.fused()
+            for _ in range(2):                    # eager warm-up: weight packs, kernel attributes, the tf32 probe
+                self._bind()
+                model._rollout_step(self.obs, self.onehot, self.var)
+            torch.cuda.synchronize(device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._bind()
+                frames = model._rollout_step(self.obs, self.onehot, self.var)
+                for l, h, c in zip(self.lstms, self.h, self.c):
+                    h.copy_(l._h)
+                    c.copy_(l._c)
+                self.frames = frames
+                self.next_obs = torch.cat([frames, self.obs[:, :-3]], dim=1)
+            for l in self.lstms:                  # the Python-side memory is not used while the graph drives the rollout
+                l._h = l._c = None
+            torch.set_rng_state(rng)
+        self.reset()
+
+    def _bind(self):
+        for l, h, c in zip(self.lstms, self.h, self.c):
+            l._h, l._c = h, c
+
+    def reset(self):
+        """start_inference: the recurrent memory goes back to the learned initial state."""
+        with torch.no_grad():
+            for l, h, c in zip(self.lstms, self.h, self.c):
+                h.copy_(l.initial_hidden_state.detach().unsqueeze(0).expand_as(h))
+                c.copy_(l.initial_hidden_cell_state.detach().unsqueeze(0).expand_as(c))
+
+    def step(self, observations, onehot, variations):
+        self.obs.copy_(observations)
+        self.onehot.copy_(onehot)
+        self.var.copy_(variations)
+        self.model.generate_noise(observations.shape[0])      # model.py:496, host-side draw, once per generated frame
+        self.graph.replay()
+        return self.frames.clone(), self.next_obs.clone()
+
+
 class Model(nn.Module):
     """model/main_model/model.py:19-655 (``reduced=True``: model/reduced_model/model.py)."""
 
@@ -407,6 +470,8 @@ class Model(nn.Module):
                                                     m["centroid_estimator"]["alpha"])
         self.train_forward_counts = 0
         self.noise = NoiseSource()
+        self._graph_inference = False
+        self._graphed_rollout: Optional[GraphedRollout] = None
         for net in self.action_network:
             net.noise = self.noise
         self.gumbel_softmax.noise = self.noise
@@ -561,9 +626,28 @@ class Model(nn.Module):
         return onehot
 
     # ----------------------------------------------------------------------------------------------------------
+    def enable_graphed_inference(self, enabled: bool = True):
+        """Opt-in: ``generate_next`` / ``generate_next_interpolation`` / ``generate_next_batch`` replay one CUDA graph per step
+        (eval mode, CUDA tensors, no autograd).  Call again after loading new weights (the graph captures weight packs)."""
+        self._graph_inference = enabled
+        self._graphed_rollout = None
+        return self
+
     def start_inference(self):
         """model.py:561-568."""
         self.dynamics_network.reinit_memory(batch_size=1)
+        if self._graphed_rollout is not None:
+            self._graphed_rollout.reset()
+
+    def _rollout(self, observation_batch, actions_batch, variation_batch):
+        """One rollout step, through the CUDA graph when graphed inference is enabled."""
+        if (self._graph_inference and observation_batch.is_cuda and not self.training and not torch.is_grad_enabled()):
+            key = (tuple(observation_batch.shape), observation_batch.device)
+            if self._graphed_rollout is None or self._graphed_rollout.key != key:
+                self._graphed_rollout = GraphedRollout(self, observation_batch.shape, observation_batch.device)
+            frames, _ = self._graphed_rollout.step(observation_batch, actions_batch, variation_batch)
+            return frames
+        return self._rollout_step(observation_batch, actions_batch, variation_batch)
 
     def _device(self):
         return self.estimated_device if hasattr(self, "estimated_device") else next(self.parameters()).device
@@ -585,7 +669,7 @@ class Model(nn.Module):
             variation = self.noise.sample("randn", (1, dim), dev)
         else:
             variation = torch.zeros((1, dim), dtype=torch.float32, device=dev)
-        frame = self._rollout_step(observation.unsqueeze(0), actions_batch, variation).squeeze(0)
+        frame = self._rollout(observation.unsqueeze(0), actions_batch, variation).squeeze(0)
         return frame, torch.cat([frame, observation[:-3]], dim=0)
 
     def generate_next_interpolation(self, observation, first_action, second_action, interpolation_factor):
@@ -597,7 +681,7 @@ class Model(nn.Module):
         variation = (point - c[selected]).unsqueeze(0)
         actions_batch = torch.zeros((1, self.actions_count), dtype=torch.float32, device=dev)
         actions_batch[0, selected] = 1.0
-        frame = self._rollout_step(observation.unsqueeze(0), actions_batch, variation).squeeze(0)
+        frame = self._rollout(observation.unsqueeze(0), actions_batch, variation).squeeze(0)
         return frame, torch.cat([frame, observation[:-3]], dim=0)
 
     def generate_next_batch(self, observations, actions, variations=None):
@@ -608,7 +692,7 @@ class Model(nn.Module):
         if variations is None:
             dim = self.config["model"]["action_network"]["action_space_dimension"]
             variations = torch.zeros((observations.shape[0], dim), dtype=torch.float32, device=observations.device)
-        frames = self._rollout_step(observations, onehot, variations)
+        frames = self._rollout(observations, onehot, variations)
         return frames, torch.cat([frames, observations[:, :-3]], dim=1)
 
 

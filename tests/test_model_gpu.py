@@ -232,3 +232,39 @@ def test_graphed_step_matches_eager_steps():
     _log("graph_vs_eager", eager=ref_losses, graphed=got)
     for a, b in zip(got, ref_losses[1:]):
         assert abs(a - b) <= 2e-5 * abs(b), (got, ref_losses)
+
+
+@pytest.mark.parametrize("name", ROLLOUT_CASES)
+def test_graphed_rollout_equals_eager_and_golden(name):
+    """Opt-in CUDA-graph inference (Model.enable_graphed_inference): one graph replay per generated frame must give the
+    frames of the kernel-by-kernel path bit for bit (same kernels, same order) - hence the reference's - over two rollouts
+    (start_inference resets the static recurrent memory), without moving the CPU RNG stream."""
+    case, g = load_case(name)
+    cfg, sd, _, obs0 = case_inputs(case)
+
+    def rollout(model):
+        frames = []
+        obs = obs0.to(DEV)
+        torch.manual_seed(case["noise_seed"])
+        with torch.no_grad():
+            model.start_inference()
+            for a in case["actions"]:
+                f, obs = model.generate_next(obs, a, noise=case.get("noise", False))
+                frames.append(f.clone())
+            for a1, a2, fac in case.get("interp", []):
+                f, obs = model.generate_next_interpolation(obs, a1, a2, fac)
+                frames.append(f.clone())
+        return frames, torch.get_rng_state()
+
+    model, _ = _build(case, cfg, sd, None)
+    model.eval()
+    eager, rng_eager = rollout(model)
+    model.enable_graphed_inference()
+    for attempt in range(2):                                   # the second rollout reuses the captured graph
+        graphed, rng_graphed = rollout(model)
+        assert torch.equal(rng_eager, rng_graphed), "graphed inference moved the CPU RNG stream"
+        for i, (a, b) in enumerate(zip(eager, graphed)):
+            assert torch.equal(a, b), (attempt, i, float((a - b).abs().max()))
+    keys = [f"frame.{i}" for i in range(len(case["actions"]))] + [f"iframe.{i}" for i in range(len(case.get("interp", [])))]
+    for k, f in zip(keys, graphed):
+        assert float(np.abs(f.cpu().numpy() - g[k]).max()) <= 1e-3, k
