@@ -41,7 +41,8 @@ extern "C" {
 
 #define PVG_ALGO_AUTO 0
 #define PVG_ALGO_SIMT 1     /* fp32 CUDA-core implicit GEMM (any shape) */
-#define PVG_ALGO_UMMA 2     /* tcgen05 / TMEM / TMA implicit GEMM (Cin % 32 == 0) */
+#define PVG_ALGO_UMMA 2     /* tcgen05 / TMEM / TMA implicit GEMM (Cin % 4 == 0, % 8 with 16-bit correction planes) */
+#define PVG_ALGO_UMMA_PERSISTENT 3   /* EXPERIMENTAL, opt-in: persistent-tile variant of the 1-CTA split-product kernel */
 
 typedef struct pvg_conv_desc {
   int32_t N, H, W;          /* output == input spatial size (all convs on the path are stride 1, "same" padding) */

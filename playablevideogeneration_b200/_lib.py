@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpvg_b200.so")
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
-ALGO_AUTO, ALGO_SIMT, ALGO_UMMA = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PERSISTENT = 0, 1, 2, 3
 CORR_BF16, CORR_FP16 = 0, 1
 
 

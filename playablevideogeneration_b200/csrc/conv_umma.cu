@@ -327,6 +327,213 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (opt-in: pvg_conv_desc.algo = PVG_ALGO_UMMA_PERSISTENT or PVG_PERSISTENT=1; not on the default path until it
+// has been validated on a B200): persistent variant of the 1-CTA split-product kernel.  One CTA per SM walks
+// tile = blockIdx.x, blockIdx.x + gridDim.x, ... so that (1) barrier init, TMEM allocation and tensor-map prefetch are
+// paid once per SM instead of once per tile, (2) the TMA producer prefetches the next tile's first stages while the
+// current tile drains, and (3) the bias / activation / store part of the epilogue overlaps the next tile's MMAs: the
+// epilogue warps fold the correction accumulator into their registers first (TMEM reads only), release it through the
+// `cfree` barrier, and only then do the arithmetic and the global stores.  profiles/r01_tile_model.md measures the
+// non-overlapped fixed cost this removes at 3.7 us per tile (9-16 % of a 36-72 k-iteration tile).
+// Barrier phases simply keep counting across tiles: `pg` = global period index (main-accumulator ping-pong), `it` = tiles
+// done by this CTA (correction-accumulator hand-off).
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int NPROD>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                            const ConvParams p, const int total_tiles) {
+  static_assert(NPROD >= 2, "the persistent variant implements the split-product path only");
+  constexpr int KC = 32;
+  using C = Cfg<BN, NPROD, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;      // [2] main accumulator buffer ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2] main accumulator buffer drained
+  uint64_t* cfree_bar = tempty_bar + 2;              // [1] correction accumulator read by the epilogue: next tile may overwrite it
+  uint32_t* tmem_slot = (uint32_t*)(cfree_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int chunks = p.Cin / KC;
+  const int k_iters = p.R * p.S * chunks;
+  const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 128); mbar_init(&tempty_bar[1], 128);
+    mbar_init(cfree_bar, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const uint32_t leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % n_tiles;
+      int t = tile / n_tiles;
+      const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+      const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+      const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = t * p.tn;
+      const int co0 = n_tile * BN;
+      for (int k = 0; k < k_iters; ++k) {
+        const int tap = k / chunks, cc = k - tap * chunks;
+        const int r = tap / p.S, s = tap - r * p.S;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* st = stage_base + stage * C::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_4d(st, &tmA, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma_load_2d(st + 2 * C::kABytes, &tmB, &full_bar[stage], k * KC, co0);
+          if (NPROD == 3) {
+            tma_load_4d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * KC, co0);
+          } else {
+            tma_load_5d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+            tma_load_3d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * KC, co0, 0);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_tf32<BN>();
+    const uint32_t idesc16 = make_idesc_f16<BN>(p.corr_fp16 != 0);
+    const uint64_t d32 = make_kmajor_desc<KC>(smem_u32(stage_base));
+    const uint64_t d16 = make_kmajor_desc<16>(smem_u32(stage_base));
+    constexpr uint32_t kStageU = C::kStageBytes >> 4, kAU = C::kABytes >> 4, kBU = C::kBBytes >> 4;
+    const uint32_t corr = tmem_acc + 2 * BN;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t pg = 0;                                   // global period index: main buffer = pg & 1
+    int it = 0;                                        // tiles done by this CTA
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if (it > 0) {                                    // the epilogue has folded the previous tile's corrections into registers
+        mbar_wait(cfree_bar, (uint32_t)(it - 1) & 1);
+        tc_fence_after();
+      }
+      uint32_t corr_acc = 0;
+      int k = 0;
+      for (int per = 0; per < periods; ++per, ++pg) {
+        const uint32_t b = pg & 1;
+        mbar_wait(&tempty_bar[b], ((pg >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t main_acc = tmem_acc + b * BN;
+        const int k_end = min(k + C::kDrain, k_iters);
+        uint32_t main_started = 0;
+        for (; k < k_end; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t a_hi = stage * kStageU, a_lo = a_hi + kAU, b_hi = a_hi + 2 * kAU, b_lo = b_hi + kBU;
+            if constexpr (NPROD == 2) {
+              const uint32_t a_xb = a_lo + kAU / 2, b_xb = b_lo + kBU / 2;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_bf16(corr, d16 + (a_lo + 2 * ks), d16 + (b_xb + 2 * ks), idesc16, corr_acc);
+                corr_acc = 1;
+              }
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) umma_bf16(corr, d16 + (a_xb + 2 * ks), d16 + (b_lo + 2 * ks), idesc16, 1);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < C::kKSteps; ++ks) {
+                umma_tf32(corr, d32 + (a_lo + 2 * ks), d32 + (b_hi + 2 * ks), idesc, corr_acc);
+                corr_acc = 1;
+              }
+#pragma unroll
+              for (int ks = 0; ks < C::kKSteps; ++ks) umma_tf32(corr, d32 + (a_hi + 2 * ks), d32 + (b_lo + 2 * ks), idesc, 1);
+            }
+#pragma unroll
+            for (int ks = 0; ks < C::kKSteps; ++ks) {
+              umma_tf32(main_acc, d32 + (a_hi + 2 * ks), d32 + (b_hi + 2 * ks), idesc, main_started);
+              main_started = 1;
+            }
+            umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (leader) umma_commit(&tfull_bar[b]);         // the tile's last commit also covers its correction MMAs
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int wi = row % p.tw;
+    const int hi = (row / p.tw) % p.th;
+    const int ni = row / (p.tw * p.th);
+    const bool vec_ok = (p.Cout % 4) == 0 && (((uintptr_t)p.y | (uintptr_t)p.bias) & 15) == 0;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
+    uint32_t pg = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % n_tiles;
+      int t = tile / n_tiles;
+      const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+      const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+      const int ow = tile_w * p.tw + wi, oh = tile_h * p.th + hi, on = t * p.tn + ni;
+      const int co0 = n_tile * BN;
+      const bool valid = ow < p.W && oh < p.H && on < p.N;
+      float* yrow = p.y + (((int64_t)on * p.H + oh) * p.W + ow) * p.Cout;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int per = 0; per < periods; ++per, ++pg) {
+        const uint32_t b = pg & 1;
+        mbar_wait(&tfull_bar[b], (pg >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN; c += 16) {
+          float v[16];
+          tmem_ld16(tmem_acc + lane_base + (uint32_t)(b * BN + c), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c + j] += v[j];
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[b]);
+      }
+      // TMEM reads only: fold the corrections into the registers, then hand the correction buffer back to the MMA warp
+#pragma unroll
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(v[j], kCorrScale, acc[c + j]);
+      }
+      tc_fence_before();
+      mbar_arrive(cfree_bar);
+      // bias / activation / stores overlap the next tile's main loop
+#pragma unroll
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = acc[c + j];
+        finish16(v, p.bias, co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, C::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): two CTAs of a cluster compute a 256-pixel x 128-channel tile with ONE MMA stream.
 // Each CTA stages its own 128-pixel A patch and HALF of the weight tile (64 rows), so every MMA reads 4 KB (A) + 2 KB (B)
 // of shared memory per SM instead of 4 + 4 KB and TMA fills 48 KB instead of 64 KB per k-iteration: the shared-memory
@@ -675,6 +882,51 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
   return 0;
 }
 
+template <int BN, int NPROD>
+static int launch_umma_persistent(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+                                  const float* bias, float* y, cudaStream_t st) {
+  using C = Cfg<BN, NPROD, 32>;
+  ConvParams p;
+  const int CinK = (d->Cin + 31) & ~31;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
+  p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  const int K = d->R * d->S * CinK;
+  int rc;
+  if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
+  if ((rc = encode_w_map(&tmB, w, d->Cout, K, BN, 32))) return rc;
+  if (NPROD == 3) {
+    if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, BN, 32))) return rc;
+  } else {
+    if ((rc = encode_nhwc_16x2_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_16x2_map(&tmBlo, w_lo, d->Cout, K, BN))) return rc;
+  }
+  constexpr int kSmem = C::kSmemBytes + 64;            // + the cfree barrier
+  static bool attr_set = false;
+  if (!attr_set) {
+    PVG_CUDA_OK(cudaFuncSetAttribute(conv_umma_persistent_kernel<BN, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set = true;
+  }
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n * ceil_div(d->Cout, BN);
+  dim3 grid((unsigned)(total < kSMs ? total : kSMs));
+  conv_umma_persistent_kernel<BN, NPROD><<<grid, kThreads, kSmem, st>>>(tmA, tmAlo, tmB, tmBlo, p, total);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+// experimental persistent 1-CTA kernel: explicit algo or PVG_PERSISTENT=1 (never the default)
+static bool want_persistent(const pvg_conv_desc* d) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("PVG_PERSISTENT");
+    env = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return d->algo == PVG_ALGO_UMMA_PERSISTENT || env == 1;
+}
+
 template <int NPROD>
 static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
                         const float* bias, float* y, cudaStream_t st) {
@@ -743,6 +995,11 @@ template <int NPROD>
 static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
                        const float* bias, float* y, cudaStream_t st) {
   const int co = d->Cout;
+  if constexpr (NPROD >= 2) {
+    if (want_persistent(d) && co > 32 && co <= 64) return launch_umma_persistent<64, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+    if (want_persistent(d) && co > 80 && (d->algo == PVG_ALGO_UMMA_PERSISTENT || !use_pairs(d)))
+      return launch_umma_persistent<128, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+  }
   if (co <= 16) return launch_umma<16, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   if (co <= 32) return launch_umma<32, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   if (co <= 64) {
@@ -778,6 +1035,7 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void
   // channel strides must be multiples of 16 bytes for TMA: Cin % 4 == 0 (fp32), % 8 == 0 with 16-bit planes
   const bool umma_ok = (d->Cin % (d->nprod == 2 ? 8 : 4)) == 0 && (((uintptr_t)x | (uintptr_t)w) & 15) == 0;
   if (algo == PVG_ALGO_AUTO) algo = (umma_ok && pvg_has_umma()) ? PVG_ALGO_UMMA : PVG_ALGO_SIMT;
+  if (algo == PVG_ALGO_UMMA_PERSISTENT) PVG_CHECK_ARG(d->nprod >= 2, "the persistent kernel implements the split product only (nprod 2 or 3)");
   if (algo == PVG_ALGO_SIMT) return conv2d_fwd_simt(d, x, w, bias, y, st);
   PVG_CHECK_ARG(umma_ok, "tensor-core path needs Cin % 4 == 0 (% 8 with 16-bit correction planes) and 16-byte aligned operands");
   if (d->nprod == 3) {

@@ -70,6 +70,8 @@ case $s in
   san_tests) PYTORCH_NO_CUDA_MEMORY_CACHING=1 run san_tests 500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "conv_simt or probe or umma_forward_tf32x3 or conv_backward" -p no:cacheprovider ;;
   graphed_rollout) run t_graphed_rollout 200 python -m pytest tests/test_model_gpu.py -q -m gpu -k "graphed_rollout" -p no:cacheprovider; run rollout_b1 100 python tools/rollout_bench.py 1 100 tf32x3; run rollout_b1_graph 100 python tools/rollout_bench.py 1 100 tf32x3 graph ;;
   desc_probe) run desc_probe 300 bash -c 'cd tools/probes && nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../playablevideogeneration_b200/csrc -o /tmp/umma_desc_probe umma_desc_probe.cu && /tmp/umma_desc_probe' ;;
+  persist_t) PVG_PERSISTENT=1 PVG_2CTA=0 run persist_t 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv" -p no:cacheprovider ;;
+  persist_b) PVG_PERSISTENT=1 PVG_2CTA=0 run persist_b 300 python tools/tile_model.py tf32x3; PVG_PERSISTENT=1 PVG_2CTA=0 run persist_b64 300 python tools/tile_model.py tf32x3 64 ;;
   corr_diag) run corr_diag 300 python tools/corr_diag.py ;;
 esac
 done
