@@ -758,6 +758,208 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem2_dealloc(tmem_acc, C::kTmemCols);
 }
 
+// EXPERIMENTAL (opt-in like conv_umma_persistent_kernel, not yet validated on a GPU): persistent variant of the CTA-pair
+// kernel.  One cluster per SM pair walks work items cid = cluster, cluster + #clusters, ...; the hand-off of the correction
+// accumulators (one per CTA, both written by the leader's cta_group::2 MMAs) goes through the leader's `cfree` barrier with
+// 256 arrivals, exactly like `tempty`.
+template <int NPROD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_umma2_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                             const ConvParams p, const int total_items) {
+  static_assert(NPROD >= 2, "the persistent variant implements the split-product path only");
+  using C = Cfg2<NPROD>;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* cfree_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(cfree_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int first_item = blockIdx.x >> 1, item_stride = gridDim.x >> 1;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int chunks = p.Cin / 32;
+  const int k_iters = p.R * p.S * chunks;
+  const int periods = (k_iters + C::kDrain - 1) / C::kDrain;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo);
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 256); mbar_init(&tempty_bar[1], 256);
+    mbar_init(cfree_bar, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem2_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    const uint32_t elected = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int cid = first_item; cid < total_items; cid += item_stride) {
+      const int n_tile = cid % n_tiles;
+      int t = (cid / n_tiles) * 2 + (int)rank;               // this CTA's 128-pixel tile (may lie past the end: all OOB)
+      const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+      const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+      const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = t * p.tn;
+      const int co0 = n_tile * BN;
+      for (int k = 0; k < k_iters; ++k) {
+        const int tap = k / chunks, cc = k - tap * chunks;
+        const int r = tap / p.S, s = tap - r * p.S;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elected) {
+          uint8_t* st = stage_base + stage * C::kStageBytes;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+          tma2_load_4d(st, &tmA, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma2_load_2d(st + 2 * C::kABytes, &tmB, &full_bar[stage], k * 32, co0 + (int)rank * (BN / 2));
+          if (NPROD == 3) {
+            tma2_load_4d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma2_load_2d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * 32, co0 + (int)rank * (BN / 2));
+          } else {
+            tma2_load_5d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * 32, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+            tma2_load_3d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * 32, co0 + (int)rank * (BN / 2), 0);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      const uint32_t elected = elect_one();
+      constexpr uint32_t idesc = make_idesc_tf32_m256<BN>();
+      const uint32_t idesc16 = make_idesc_f16<BN>(p.corr_fp16 != 0, false, false, 256);
+      const uint64_t d32 = make_kmajor_desc<32>(smem_u32(stage_base));
+      const uint64_t d16 = make_kmajor_desc<16>(smem_u32(stage_base));
+      constexpr uint32_t kStageU = C::kStageBytes >> 4, kAU = C::kABytes >> 4, kBU = C::kBBytes >> 4;
+      const uint32_t corr = tmem_acc + 2 * BN;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t pg = 0;
+      int it = 0;
+      for (int cid = first_item; cid < total_items; cid += item_stride, ++it) {
+        if (it > 0) {                                   // both CTAs' epilogues have folded the previous corrections into registers
+          mbar_wait(cfree_bar, (uint32_t)(it - 1) & 1);
+          tc_fence_after();
+        }
+        uint32_t corr_acc = 0;
+        int k = 0;
+        for (int per = 0; per < periods; ++per, ++pg) {
+          const uint32_t b = pg & 1;
+          mbar_wait(&tempty_bar[b], ((pg >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t main_acc = tmem_acc + b * BN;
+          const int k_end = min(k + C::kDrain, k_iters);
+          uint32_t main_started = 0;
+          for (; k < k_end; ++k) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elected) {
+              const uint32_t a_hi = stage * kStageU, a_lo = a_hi + kAU, b_hi = a_hi + 2 * kAU, b_lo = b_hi + kBU;
+              if constexpr (NPROD == 2) {
+                const uint32_t a_xb = a_lo + kAU / 2, b_xb = b_lo + kBU / 2;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  umma2_bf16(corr, d16 + (a_lo + 2 * ks), d16 + (b_xb + 2 * ks), idesc16, corr_acc);
+                  corr_acc = 1;
+                }
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) umma2_bf16(corr, d16 + (a_xb + 2 * ks), d16 + (b_lo + 2 * ks), idesc16, 1);
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  umma2_tf32(corr, d32 + (a_lo + 2 * ks), d32 + (b_hi + 2 * ks), idesc, corr_acc);
+                  corr_acc = 1;
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma2_tf32(corr, d32 + (a_hi + 2 * ks), d32 + (b_lo + 2 * ks), idesc, 1);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma2_tf32(main_acc, d32 + (a_hi + 2 * ks), d32 + (b_hi + 2 * ks), idesc, main_started);
+                main_started = 1;
+              }
+              umma2_commit_both(&empty_bar[stage]);
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          if (elected) umma2_commit_both(&tfull_bar[b]);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int wi = row % p.tw;
+    const int hi = (row / p.tw) % p.th;
+    const int ni = row / (p.tw * p.th);
+    const bool vec_ok = (p.Cout % 4) == 0 && (((uintptr_t)p.y | (uintptr_t)p.bias) & 15) == 0;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
+    uint32_t pg = 0;
+    for (int cid = first_item; cid < total_items; cid += item_stride) {
+      const int n_tile = cid % n_tiles;
+      int t = (cid / n_tiles) * 2 + (int)rank;
+      const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+      const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+      const int ow = tile_w * p.tw + wi, oh = tile_h * p.th + hi, on = t * p.tn + ni;
+      const int co0 = n_tile * BN;
+      const bool valid = ow < p.W && oh < p.H && on < p.N;
+      float* yrow = p.y + (((int64_t)on * p.H + oh) * p.W + ow) * p.Cout;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int per = 0; per < periods; ++per, ++pg) {
+        const uint32_t b = pg & 1;
+        mbar_wait(&tfull_bar[b], (pg >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN; c += 16) {
+          float v[16];
+          tmem_ld16(tmem_acc + lane_base + (uint32_t)(b * BN + c), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c + j] += v[j];
+        }
+        tc_fence_before();
+        mbar_arrive_leader(&tempty_bar[b]);
+      }
+#pragma unroll
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(v[j], kCorrScale, acc[c + j]);
+      }
+      tc_fence_before();
+      mbar_arrive_leader(cfree_bar);
+#pragma unroll
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = acc[c + j];
+        finish16(v, p.bias, co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // the peer's shared memory / TMEM must stay alive until every MMA that reads it has retired
+  if (warp == 1) tmem2_dealloc(tmem_acc, C::kTmemCols);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -917,6 +1119,42 @@ static int launch_umma_persistent(const pvg_conv_desc* d, const float* x, const 
   return 0;
 }
 
+template <int NPROD>
+static int launch_umma2_persistent(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
+                                   const float* bias, float* y, cudaStream_t st) {
+  using C = Cfg2<NPROD>;
+  ConvParams p;
+  const int CinK = (d->Cin + 31) & ~31;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
+  p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  const int K = d->R * d->S * CinK;
+  int rc;
+  if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
+  if ((rc = encode_w_map(&tmB, w, d->Cout, K, C::BN / 2, 32))) return rc;
+  if (NPROD == 3) {
+    if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, C::BN / 2, 32))) return rc;
+  } else {
+    if ((rc = encode_nhwc_16x2_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_16x2_map(&tmBlo, w_lo, d->Cout, K, C::BN / 2))) return rc;
+  }
+  constexpr int kSmem = C::kSmemBytes + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PVG_CUDA_OK(cudaFuncSetAttribute(conv_umma2_persistent_kernel<NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set = true;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int items = ceil_div(m_tiles, 2) * ceil_div(d->Cout, C::BN);        // (pair of M tiles) x N tile
+  const int clusters = items < kSMs / 2 ? items : kSMs / 2;
+  conv_umma2_persistent_kernel<NPROD><<<dim3((unsigned)(clusters * 2)), kThreads, kSmem, st>>>(tmA, tmAlo, tmB, tmBlo, p, items);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
 // experimental persistent 1-CTA kernel: explicit algo or PVG_PERSISTENT=1 (never the default)
 static bool want_persistent(const pvg_conv_desc* d) {
   static int env = -1;
@@ -997,8 +1235,10 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
   const int co = d->Cout;
   if constexpr (NPROD >= 2) {
     if (want_persistent(d) && co > 32 && co <= 64) return launch_umma_persistent<64, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
-    if (want_persistent(d) && co > 80 && (d->algo == PVG_ALGO_UMMA_PERSISTENT || !use_pairs(d)))
+    if (want_persistent(d) && co > 80) {
+      if (use_pairs(d)) return launch_umma2_persistent<NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
       return launch_umma_persistent<128, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
+    }
   }
   if (co <= 16) return launch_umma<16, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
   if (co <= 32) return launch_umma<32, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);

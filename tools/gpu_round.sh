@@ -72,6 +72,8 @@ case $s in
   desc_probe) run desc_probe 300 bash -c 'cd tools/probes && nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../playablevideogeneration_b200/csrc -o /tmp/umma_desc_probe umma_desc_probe.cu && /tmp/umma_desc_probe' ;;
   persist_t) PVG_PERSISTENT=1 PVG_2CTA=0 run persist_t 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv" -p no:cacheprovider ;;
   persist_b) PVG_PERSISTENT=1 PVG_2CTA=0 run persist_b 300 python tools/tile_model.py tf32x3; PVG_PERSISTENT=1 PVG_2CTA=0 run persist_b64 300 python tools/tile_model.py tf32x3 64 ;;
+  persist2_t) PVG_PERSISTENT=1 run persist2_t 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv" -p no:cacheprovider ;;
+  persist2_b) PVG_PERSISTENT=1 PVG_2CTA=1 run persist2_b 300 python tools/tile_model.py tf32x3; PVG_PERSISTENT=1 run persist2_lb 300 python tools/layer_bench.py tf32x3 vgg ;;
   corr_diag) run corr_diag 300 python tools/corr_diag.py ;;
 esac
 done
