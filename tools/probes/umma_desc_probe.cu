@@ -10,6 +10,8 @@
 // X is filled once with its row index (X[r][c] = r) and once with its column index (X[r][c] = c): D then tells, for every
 // MMA row m and every k, WHICH shared-memory row and column the tensor core actually read.  The host prints, per
 // configuration, whether the mapping is the wanted "row = row_off + (m / 8) * sbo_rows + m % 8, column = k".
+// A second table does the same for the MN-major tf32 operand of the weight-gradient kernel (pixel-row offsets = tap shifts
+// along K inside a {32 ch x many px} tile).
 //
 // build + run (on a B200):  nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../playablevideogeneration_b200/csrc \
 //                                -o /tmp/umma_desc_probe umma_desc_probe.cu -lcuda && /tmp/umma_desc_probe
@@ -36,7 +38,7 @@ constexpr int kTileBytes = kRows * 128;
 
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ bsel, int row_off, int sbo_rows, int base_off,
-             float* __restrict__ out /* [128][8] */) {
+             int mn_major, float* __restrict__ out /* [128][8] */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_tile = smem;                        // [256 rows][128 B], SWIZZLE_128B
@@ -77,7 +79,21 @@ probe_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ 
       ad |= (uint64_t)(base_off & 7) << 49;      // matrix base offset
       ad |= (uint64_t)2 << 61;                   // SWIZZLE_128B
       const uint64_t bd = make_kmajor_desc<32>(smem_u32(b_tile));
-      umma_tf32(tmem_acc, ad, bd, make_idesc_tf32<16>(), 0);
+      if (mn_major) {
+        // A = MN-major tf32 operand as in conv_wgrad_umma.cu: M = channels (32 per group, next group LBO = 4096 B further),
+        // K = pixel rows, 4-row SWIZZLE_128B_BASE32B atoms (SBO = sbo_rows * 128, 512 B in the kernel); the tile was loaded
+        // with the 32-byte-atom TMA swizzle.  D[m][n] = X[row_off + n][m % 32 (+ group * 32 rows further)].
+        uint64_t md = 0;
+        md |= (uint64_t)((a_addr & 0x3FFFF) >> 4);
+        md |= (uint64_t)((4096 >> 4) & 0x3FFF) << 16;
+        md |= (uint64_t)(((uint32_t)sbo_rows * 128u) >> 4) << 32;
+        md |= (uint64_t)1 << 46;
+        md |= (uint64_t)(base_off & 7) << 49;
+        md |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
+        umma_tf32(tmem_acc, md, bd, make_idesc_tf32_ex<16>(true, false), 0);
+      } else {
+        umma_tf32(tmem_acc, ad, bd, make_idesc_tf32<16>(), 0);
+      }
       umma_commit(done);
     }
     __syncwarp();
@@ -108,13 +124,14 @@ int main() {
   CK(cudaMemcpy(d_b, bsel.data(), bsel.size() * 4, cudaMemcpyHostToDevice));
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { fprintf(stderr, "no cuTensorMapEncodeTiled\n"); return 1; }
-  auto make_map = [&](float* p, CUtensorMap* m) {
+  auto make_map = [&](float* p, CUtensorMap* m, bool atom32 = false) {
     cuuint64_t dims[2] = {32, (cuuint64_t)kRows};
     cuuint64_t strides[1] = {128};
     cuuint32_t box[2] = {32, (cuuint32_t)kRows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "encode failed %d\n", (int)r); exit(1); }
   };
   CUtensorMap mr, mc;
@@ -130,10 +147,10 @@ int main() {
       for (int bo = 0; bo < 8; ++bo) {
         if (bo != 0 && bo != (ro & 7)) continue;               // the two candidates: no base offset / base offset = start phase
         CK(cudaMemset(d_out, 0, 128 * 8 * 4));
-        probe_kernel<<<1, 128, smem>>>(mr, d_b, ro, sbo, bo, d_out);
+        probe_kernel<<<1, 128, smem>>>(mr, d_b, ro, sbo, bo, 0, d_out);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(rows.data(), d_out, rows.size() * 4, cudaMemcpyDeviceToHost));
-        probe_kernel<<<1, 128, smem>>>(mc, d_b, ro, sbo, bo, d_out);
+        probe_kernel<<<1, 128, smem>>>(mc, d_b, ro, sbo, bo, 0, d_out);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(cols.data(), d_out, cols.size() * 4, cudaMemcpyDeviceToHost));
         int bad_r = 0, bad_c = 0, fm = -1, fk = -1;
@@ -151,5 +168,34 @@ int main() {
                  ro + (fm / 8) * sbo + fm % 8, fk, bad_r, bad_c);
         printf("\n");
       }
+  // ---- MN-major operand (weight-gradient kernel): pixel-row offsets inside a 32-channel x many-pixel tile --------------
+  CUtensorMap mr32, mc32;
+  make_map(d_xr, &mr32, true); make_map(d_xc, &mc32, true);
+  printf("\nMN-major tf32 (SWIZZLE_128B_BASE32B, TMA ATOM_32B): D[m][n] should be X[row_off + n][m] for m < 32\n");
+  printf("row_off sbo_rows base_off | rows_ok cols_ok | first mismatching (m,n): got row/col, wanted row/col\n");
+  const int mn_offs[] = {0, 1, 2, 3, 4, 5, 8, 34, 35};
+  for (int ro : mn_offs)
+    for (int bo = 0; bo < 8; ++bo) {
+      if (bo != 0 && bo != (ro & 3) && bo != (ro & 7)) continue;
+      CK(cudaMemset(d_out, 0, 128 * 8 * 4));
+      probe_kernel<<<1, 128, smem>>>(mr32, d_b, ro, 4, bo, 1, d_out);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(rows.data(), d_out, rows.size() * 4, cudaMemcpyDeviceToHost));
+      probe_kernel<<<1, 128, smem>>>(mc32, d_b, ro, 4, bo, 1, d_out);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(cols.data(), d_out, cols.size() * 4, cudaMemcpyDeviceToHost));
+      int bad_r = 0, bad_c = 0, fm = -1, fk = -1;
+      for (int m = 0; m < 32; ++m)                       // first channel group only (the others sit LBO = 32 rows further)
+        for (int n = 0; n < 8; ++n) {
+          const bool br = (int)rows[m * 8 + n] != ro + n, bc = (int)cols[m * 8 + n] != m;
+          bad_r += br; bad_c += bc;
+          if ((br || bc) && fm < 0) { fm = m; fk = n; }
+        }
+      printf("%7d %8d %8d | %7s %7s |", ro, 4, bo, bad_r ? "NO" : "yes", bad_c ? "NO" : "yes");
+      if (fm >= 0)
+        printf(" (%d,%d): got %d/%d, wanted %d/%d   [%d row, %d col mismatches]", fm, fk, (int)rows[fm * 8 + fk], (int)cols[fm * 8 + fk],
+               ro + fk, fm, bad_r, bad_c);
+      printf("\n");
+    }
   return 0;
 }
