@@ -226,6 +226,86 @@ class TrainStep:
         self._hyper_host[:len(rows)].copy_(torch.tensor(rows, dtype=torch.float32))
         self._hyper_dev.copy_(self._hyper_host[:len(rows)], non_blocking=True)
 
+    # ---- checkpoint interoperability: the reference's latest.pth.tar (training/trainer.py:80-122, ------------------
+    #      training/smooth_mi_trainer.py:23-68) = {"model", "optimizer", "lr_scheduler", "step"[, "mi_estimator"]} ----------
+    def _adam_index(self) -> List[int]:
+        """Position of every arena parameter in ``model.parameters()`` - the index torch.optim.Adam's state_dict uses (the
+        reference hands ALL parameters to Adam, trainer.py:36, including the gradient-free centroid buffer-parameter)."""
+        where = {id(p): i for i, p in enumerate(self.module.parameters())}
+        return [where[id(p)] for p in self.arena.params]
+
+    def optimizer_state_dict(self) -> dict:
+        """The flat-arena Adam state in ``torch.optim.Adam(model.parameters(), ...).state_dict()`` layout (parameter index =
+        position in ``model.parameters()``, which follows the reference's registration order; parameters that never
+        received a gradient have no entry, exactly like torch.optim.Adam)."""
+        a = self.arena
+        state = {}
+        for k, (p, o, i) in enumerate(zip(a.params, a.offsets, self._adam_index())):
+            if a.steps[k] > 0:
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(a.steps[k])),
+                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).detach().clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).detach().clone()}
+        group = {"lr": self.current_lr(), "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "initial_lr": self.lr, "params": list(range(sum(1 for _ in self.module.parameters())))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Accepts what ``torch.optim.Adam.state_dict()`` produced for the same model (``step`` as int - PyTorch 1.4, the
+        reference's pin - or as a tensor)."""
+        a = self.arena
+        saved_ids = [i for g in sd["param_groups"] for i in g["params"]]
+        n_all = sum(1 for _ in self.module.parameters())
+        if len(saved_ids) != n_all:
+            raise ValueError(f"optimizer state covers {len(saved_ids)} parameters, the model has {n_all}")
+        pos = {saved: k for k, saved in enumerate(saved_ids)}            # saved id -> position in model.parameters()
+        arena_of = {i: k for k, i in enumerate(self._adam_index())}      # position in model.parameters() -> arena slot
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        a.steps = [0] * len(a.params)
+        for saved, st in sd["state"].items():
+            i = pos[int(saved)]
+            if i not in arena_of:
+                raise ValueError(f"optimizer state for parameter {i}, which does not require a gradient")
+            k = arena_of[i]
+            p, o = a.params[k], a.offsets[k]
+            n = p.numel()
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {saved}: shape {tuple(st['exp_avg'].shape)} does not match {tuple(p.shape)}")
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            a.steps[k] = int(float(st["step"]))
+
+    def lr_scheduler_state_dict(self) -> dict:
+        """``MultiStepLR(optimizer, milestones, gamma).state_dict()`` after ``global_step`` scheduler steps."""
+        import collections
+        return {"milestones": collections.Counter(int(m) for m in self.lr_schedule), "gamma": self.lr_gamma, "base_lrs": [self.lr],
+                "last_epoch": self.global_step, "_step_count": self.global_step + 1, "_get_lr_called_within_step": False,
+                "_last_lr": [self.current_lr()]}
+
+    def state_dict(self) -> dict:
+        """The reference trainer's checkpoint dictionary."""
+        ckpt = {"model": self.module.state_dict(), "optimizer": self.optimizer_state_dict(),
+                "lr_scheduler": self.lr_scheduler_state_dict(), "step": self.global_step}
+        if isinstance(self.mutual_information_loss, L.SmoothMutualInformationLoss):      # smooth_mi_trainer.py:43-45
+            ckpt["mi_estimator"] = self.mutual_information_loss.state_dict()
+        return ckpt
+
+    def load_state_dict(self, ckpt: dict) -> None:
+        self.module.load_state_dict(ckpt["model"])
+        ops.invalidate_weight_cache()
+        self.load_optimizer_state_dict(ckpt["optimizer"])
+        self.global_step = int(ckpt["step"])
+        if "mi_estimator" in ckpt and isinstance(self.mutual_information_loss, L.SmoothMutualInformationLoss):
+            self.mutual_information_loss.load_state_dict(ckpt["mi_estimator"])
+
+    def save_checkpoint(self, path: str) -> None:
+        torch.save(self.state_dict(), path)
+
+    def load_checkpoint(self, path: str) -> None:
+        self.load_state_dict(torch.load(path, map_location=self.arena.flat.device, weights_only=False))
+
     def step(self, batch_tuple, ground_truth_observations_count: int, gumbel_temperature: float, pretraining: bool = False):
         self.module.train()
         ops.zero_pool.begin(self.arena.flat.device)      # one memset for every accumulator scratch of this step

@@ -176,3 +176,68 @@ def test_zero_pool_and_deferred_counters():
     assert int(c1) == 4 and int(c2) == 6
     ops.flush_deferred()                                          # idempotent when nothing is pending
     assert int(c1) == 4 and int(c2) == 6
+
+
+def test_trainstep_checkpoint_is_the_reference_trainers(tmp_path):
+    """TrainStep.state_dict() is the dictionary Trainer.save_checkpoint writes (training/trainer.py:100,
+    smooth_mi_trainer.py:43-45): the flat-arena Adam state round-trips through torch.optim.Adam's own state_dict layout
+    (same parameter order, parameters without a gradient have no entry, per-parameter step counts), the learning-rate
+    state loads into a real MultiStepLR, and a checkpoint file written by one TrainStep resumes another."""
+    from playablevideogeneration_b200.caddy import Model
+    from playablevideogeneration_b200.training.step import TrainStep
+    from playablevideogeneration_b200.vgg import Vgg19
+    cfg = build_config(dict(config="bair", H=64, W=64, S=1))
+    torch.manual_seed(0)
+    model = Model(cfg)
+    step = TrainStep(cfg, model, Vgg19(O.make_vgg_weights()))
+    params = list(model.parameters())
+    tr = cfg["training"]
+    # a real torch.optim.Adam on the same parameters, two steps, some parameters never receive a gradient
+    opt = torch.optim.Adam(params, lr=tr["learning_rate"], weight_decay=tr["weight_decay"])
+    g = torch.Generator().manual_seed(1)
+    skipped = {0, 5} | {i for i, p in enumerate(params) if not p.requires_grad}
+    for it in range(2):
+        for i, p in enumerate(params):
+            p.grad = None if (i in skipped or (it == 0 and i == 7)) else torch.randn(p.shape, generator=g) * 1e-2
+        opt.step()
+    ref = opt.state_dict()
+    step.load_optimizer_state_dict(ref)
+    a = step.arena
+    index = step._adam_index()
+    assert len(index) == len(params) - 1                      # the centroid parameter has requires_grad = False (no arena slot)
+    for k, (p, o, i) in enumerate(zip(a.params, a.offsets, index)):
+        n = p.numel()
+        assert p is params[i]
+        if i in ref["state"]:
+            st = ref["state"][i]
+            assert a.steps[k] == int(float(st["step"])) == (1 if i == 7 else 2)
+            assert torch.equal(step.exp_avg[o:o + n].view(p.shape), st["exp_avg"])
+            assert torch.equal(step.exp_avg_sq[o:o + n].view(p.shape), st["exp_avg_sq"])
+        else:
+            assert i in skipped and a.steps[k] == 0 and float(step.exp_avg[o:o + n].abs().sum()) == 0.0
+    mine = step.optimizer_state_dict()
+    assert sorted(mine["state"]) == sorted(ref["state"]) and mine["param_groups"][0]["params"] == ref["param_groups"][0]["params"]
+    opt2 = torch.optim.Adam(params, lr=tr["learning_rate"], weight_decay=tr["weight_decay"])
+    opt2.load_state_dict(mine)                                        # torch accepts it as its own
+    for i, st in ref["state"].items():
+        assert torch.equal(opt2.state[params[i]]["exp_avg_sq"], st["exp_avg_sq"])
+        assert float(opt2.state[params[i]]["step"]) == float(st["step"])
+    # learning-rate schedule
+    step.global_step = 7
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt2, milestones=[int(m) for m in tr["lr_schedule"]], gamma=tr["lr_gamma"])
+    sched.load_state_dict(step.lr_scheduler_state_dict())
+    assert sched.last_epoch == 7 and abs(sched.get_last_lr()[0] - step.current_lr()) < 1e-12
+    # file round trip with the reference's keys
+    path = str(tmp_path / "latest.pth.tar")
+    step.save_checkpoint(path)
+    ckpt = torch.load(path, weights_only=False)
+    assert set(ckpt) == {"model", "optimizer", "lr_scheduler", "step", "mi_estimator"} and ckpt["step"] == 7
+    assert list(ckpt["model"].keys()) == [k for k, _, _ in O.model_param_spec(cfg, False)]
+    torch.manual_seed(5)
+    model2 = Model(cfg)
+    step2 = TrainStep(cfg, model2, Vgg19(O.make_vgg_weights()))
+    step2.load_checkpoint(path)
+    assert step2.global_step == 7 and step2.arena.steps == a.steps
+    assert torch.equal(step2.exp_avg, step.exp_avg) and torch.equal(step2.arena.flat, a.flat)
+    for (k1, v1), (k2, v2) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
