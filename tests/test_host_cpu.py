@@ -32,6 +32,31 @@ def test_library_exports_every_declared_symbol():
     _lib.load()
 
 
+def test_header_is_plain_c_and_matches_the_ctypes_struct():
+    """include/pvg_b200.h is the boundary: it must compile as C99 on its own (no C++ or torch types), and the ctypes mirror
+    of pvg_conv_desc must have the layout the C compiler gives the struct."""
+    import shutil
+    import subprocess
+    import tempfile
+    from playablevideogeneration_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "probe.c")
+        exe = os.path.join(td, "probe")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include <stddef.h>\n#include "pvg_b200.h"\n'
+                    'int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(pvg_conv_desc), offsetof(pvg_conv_desc, slope), '
+                    'offsetof(pvg_conv_desc, nprod), offsetof(pvg_conv_desc, corr_fmt)); return 0; }\n')
+        subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe, src],
+                       check=True)
+        size, o_slope, o_nprod, o_fmt = (int(v) for v in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split())
+    D = _lib.ConvDesc
+    assert ctypes.sizeof(D) == size
+    assert (D.slope.offset, D.nprod.offset, D.corr_fmt.offset) == (o_slope, o_nprod, o_fmt)
+
+
 def test_ops_have_no_cpu_fallback():
     from playablevideogeneration_b200 import ops
     from playablevideogeneration_b200._lib import PvgError
