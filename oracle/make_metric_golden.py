@@ -1,0 +1,58 @@
+"""Golden values of the reference's cheap evaluation metrics (TEST INFRASTRUCTURE; needs /root/reference).
+
+Runs the UNMODIFIED ``evaluation/metrics/{mse,psnr,motion_masked_mse,vgg_cosine_similarity}.py`` on seeded inputs (VGG19
+with the seeded stand-in weights of ``caddy_oracle.make_vgg_weights``) -> tests/golden/metrics.npz.
+usage: python oracle/make_metric_golden.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import caddy_oracle as O          # noqa: E402
+from oracle import ref_harness as R           # noqa: E402
+
+SEED, SHAPE = 123, (2, 4, 3, 32, 48)
+
+
+def inputs():
+    g = torch.Generator().manual_seed(SEED)
+    ref = torch.rand(SHAPE, generator=g)
+    gen = (ref + 0.1 * torch.randn(SHAPE, generator=g)).clamp(0, 1)
+    return ref, gen
+
+
+def main():
+    R.install_shims()
+    sys.path.insert(0, R.REF_ROOT)
+    from evaluation.metrics.mse import MSE
+    from evaluation.metrics.psnr import PSNR
+    from evaluation.metrics.motion_masked_mse import MotionMaskedMSE
+    from evaluation.metrics.vgg_cosine_similarity import VGGCosineSimilarity
+    ref, gen = inputs()
+    out = {"mse": MSE()(ref, gen).numpy(), "psnr": PSNR()(ref, gen).numpy(), "psnr_range255": PSNR()(ref * 255, gen * 255, range=255.0).numpy(),
+           "motion_masked_mse": MotionMaskedMSE()(ref, gen).numpy()}
+    vcs = VGGCosineSimilarity()
+    sd = O.make_vgg_weights()
+    vcs.vgg.load_state_dict({k: v for k, v in _slice_names(vcs.vgg, sd).items()}, strict=True)
+    with torch.no_grad():
+        out["vgg_cosine"] = vcs(ref, gen).numpy()
+    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "metrics.npz")
+    np.savez_compressed(path, **out)
+    print({k: v.reshape(-1)[:3] for k, v in out.items()})
+
+
+def _slice_names(vgg, features_sd):
+    """The reference's Vgg19 regroups torchvision's features into slice1..slice5 keeping the layer indices."""
+    want = vgg.state_dict()
+    out = {}
+    for k in want:
+        idx = k.split(".")[1]
+        out[k] = features_sd[f"features.{idx}.{k.split('.')[2]}"]
+    return out
+
+
+if __name__ == "__main__":
+    main()

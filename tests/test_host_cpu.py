@@ -266,3 +266,29 @@ def test_trainstep_checkpoint_is_the_reference_trainers(tmp_path):
     assert torch.equal(step2.exp_avg, step.exp_avg) and torch.equal(step2.arena.flat, a.flat)
     for (k1, v1), (k2, v2) in zip(model.state_dict().items(), model2.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
+
+
+def _metric_inputs():
+    g = torch.Generator().manual_seed(123)
+    shape = (2, 4, 3, 32, 48)
+    ref = torch.rand(shape, generator=g)
+    gen = (ref + 0.1 * torch.randn(shape, generator=g)).clamp(0, 1)
+    return ref, gen
+
+
+def test_evaluation_metrics_match_the_reference(fake_ops):
+    """evaluation/metrics/{mse,psnr,motion_masked_mse,vgg_cosine_similarity}.py: golden values produced by the unmodified
+    reference classes (oracle/make_metric_golden.py) on the same seeded inputs; VGG through the CPU stand-ins here, through
+    the CUDA kernels in tests/test_model_gpu.py."""
+    from playablevideogeneration_b200.evaluation.metrics import MSE, PSNR, MotionMaskedMSE, VGGCosineSimilarity
+    from playablevideogeneration_b200.vgg import Vgg19
+    g = np.load(os.path.join(ROOT, "tests", "golden", "metrics.npz"))
+    ref, gen = _metric_inputs()
+    np.testing.assert_allclose(MSE()(ref, gen).numpy(), g["mse"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(PSNR()(ref, gen).numpy(), g["psnr"], rtol=1e-6)
+    np.testing.assert_allclose(PSNR()(ref * 255, gen * 255, range=255.0).numpy(), g["psnr_range255"], rtol=1e-5)
+    np.testing.assert_allclose(MotionMaskedMSE()(ref, gen).numpy(), g["motion_masked_mse"], rtol=1e-6, atol=1e-9)
+    vcs = VGGCosineSimilarity(Vgg19(O.make_vgg_weights()))
+    got = vcs(ref, gen)
+    assert got.shape == (2, 4)
+    np.testing.assert_allclose(got.numpy(), g["vgg_cosine"], rtol=2e-5)

@@ -268,3 +268,21 @@ def test_graphed_rollout_equals_eager_and_golden(name):
     keys = [f"frame.{i}" for i in range(len(case["actions"]))] + [f"iframe.{i}" for i in range(len(case.get("interp", [])))]
     for k, f in zip(keys, graphed):
         assert float(np.abs(f.cpu().numpy() - g[k]).max()) <= 1e-3, k
+
+
+def test_evaluation_metrics_match_reference_golden():
+    """The evaluator's cheap metrics on the device (VGG cosine similarity through the tensor-core conv kernels) against the
+    values of the unmodified reference classes (tests/golden/metrics.npz, oracle/make_metric_golden.py)."""
+    from playablevideogeneration_b200.evaluation.metrics import MSE, PSNR, MotionMaskedMSE, VGGCosineSimilarity
+    from playablevideogeneration_b200.vgg import Vgg19
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.npz"))
+    gen_ = torch.Generator().manual_seed(123)
+    shape = (2, 4, 3, 32, 48)
+    ref = torch.rand(shape, generator=gen_)
+    gen = (ref + 0.1 * torch.randn(shape, generator=gen_)).clamp(0, 1)
+    ref, gen = ref.to(DEV), gen.to(DEV)
+    np.testing.assert_allclose(MSE()(ref, gen).cpu().numpy(), g["mse"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(PSNR()(ref, gen).cpu().numpy(), g["psnr"], rtol=1e-5)
+    np.testing.assert_allclose(MotionMaskedMSE()(ref, gen).cpu().numpy(), g["motion_masked_mse"], rtol=1e-5, atol=1e-9)
+    vcs = VGGCosineSimilarity(Vgg19(O.make_vgg_weights()).to(DEV))
+    np.testing.assert_allclose(vcs(ref, gen).cpu().numpy(), g["vgg_cosine"], rtol=1e-4)
