@@ -39,6 +39,15 @@ def main():
     vcs.vgg.load_state_dict({k: v for k, v in _slice_names(vcs.vgg, sd).items()}, strict=True)
     with torch.no_grad():
         out["vgg_cosine"] = vcs(ref, gen).numpy()
+    # sequence helpers of training/losses.py used by the evaluator
+    from training.losses import MotionLossWeightMaskCalculator, SequenceLossEvaluator, StatesLoss
+    out["weight_mask_same"] = MotionLossWeightMaskCalculator(0.3).compute_weight_mask(ref, gen).numpy()
+    out["weight_mask_short"] = MotionLossWeightMaskCalculator(0.0).compute_weight_mask(ref, gen[:, 1:]).numpy()
+    ev = SequenceLossEvaluator(StatesLoss())
+    avg, terms = ev(ref, gen)
+    out["seq_same_avg"], out["seq_same_terms"] = avg.numpy(), terms.numpy()
+    avg, terms = ev(ref, gen[:, 1:])
+    out["seq_short_avg"], out["seq_short_terms"] = avg.numpy(), terms.numpy()
     path = os.path.join(os.path.dirname(HERE), "tests", "golden", "metrics.npz")
     np.savez_compressed(path, **out)
     print({k: v.reshape(-1)[:3] for k, v in out.items()})

@@ -254,3 +254,48 @@ class SmoothMutualInformationLoss(MutualInformationLoss):
 
     def compute_joint_probability_matrix(self, distribution_1, distribution_2):
         return self.matrix_estimator(super().compute_joint_probability_matrix(distribution_1, distribution_2))
+
+
+class MotionLossWeightMaskCalculator:
+    """training/losses.py:591-647: per-pixel loss weights |frame_t - frame_{t-1}| of the ground truth plus the same of the
+    reconstruction, summed over the 3 channels, + ``weight_bias``; ones for the first frame.  No gradient flows."""
+
+    def __init__(self, weight_bias: float = 0.0):
+        self.weight_bias = weight_bias
+
+    def compute_weight_mask(self, observations: torch.Tensor, reconstructed_observations: torch.Tensor) -> torch.Tensor:
+        observations = observations.detach()[:, :, :3]
+        reconstructed_observations = reconstructed_observations.detach()
+        t, tr = observations.size(1), reconstructed_observations.size(1)
+        if tr != t:
+            if tr != t - 1:
+                raise Exception(f"Received an input batch with sequence length {t}, but got a reconstructed batch of {tr}")
+            reconstructed_observations = torch.cat([observations[:, 0:1], reconstructed_observations], dim=1)
+        mask = torch.abs(observations[:, 1:] - observations[:, :-1]) + \
+            torch.abs(reconstructed_observations[:, 1:] - reconstructed_observations[:, :-1])
+        assert mask.size(2) == 3
+        mask = mask.sum(dim=2, keepdim=True) + self.weight_bias
+        return torch.cat([torch.ones_like(mask[:, 0:1]), mask], dim=1)
+
+
+class SequenceLossEvaluator:
+    """training/losses.py:650-713 (used by evaluation/evaluator.py:191-203): evaluates ``loss`` at every sequence position;
+    a reconstruction that is one element shorter is aligned to the right and position 0 scores 0 (and is left out of the
+    average).  Returns (average, per-position tensor)."""
+
+    def __init__(self, loss):
+        self.loss = loss
+
+    def __call__(self, ground_truth_sequence: torch.Tensor, reconstructed_sequence: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        t, tr = ground_truth_sequence.size(1), reconstructed_sequence.size(1)
+        if tr != t and tr != t - 1:
+            raise Exception(f"Received an input batch with sequence length {t}, but got a reconstructed batch of {tr}")
+        shift = t - tr
+        terms = [torch.zeros((), dtype=torch.float32, device=ground_truth_sequence.device)] * shift
+        for i in range(tr):
+            cur = self.loss(ground_truth_sequence[:, i + shift:i + shift + 1], reconstructed_sequence[:, i:i + 1])
+            if type(cur) == tuple:                  # losses that return several tensors: the first is the term of interest
+                cur = cur[0]
+            terms.append(cur.reshape(()).float())
+        loss_terms = torch.stack(terms)             # one stack instead of T scalar writes (each a host-visible op)
+        return (loss_terms.mean() if shift == 0 else loss_terms[1:].mean()), loss_terms

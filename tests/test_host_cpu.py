@@ -292,3 +292,15 @@ def test_evaluation_metrics_match_the_reference(fake_ops):
     got = vcs(ref, gen)
     assert got.shape == (2, 4)
     np.testing.assert_allclose(got.numpy(), g["vgg_cosine"], rtol=2e-5)
+    # sequence helpers of training/losses.py:591-713 (evaluator.py:191-203)
+    from playablevideogeneration_b200.training.losses import MotionLossWeightMaskCalculator, SequenceLossEvaluator, StatesLoss
+    np.testing.assert_allclose(MotionLossWeightMaskCalculator(0.3).compute_weight_mask(ref, gen).numpy(), g["weight_mask_same"], rtol=1e-6)
+    np.testing.assert_allclose(MotionLossWeightMaskCalculator(0.0).compute_weight_mask(ref, gen[:, 1:]).numpy(), g["weight_mask_short"],
+                               rtol=1e-6, atol=1e-7)
+    ev = SequenceLossEvaluator(StatesLoss())
+    for tag, rec in (("same", gen), ("short", gen[:, 1:])):
+        avg, terms = ev(ref, rec)
+        np.testing.assert_allclose(terms.numpy(), g[f"seq_{tag}_terms"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(float(avg), float(g[f"seq_{tag}_avg"]), rtol=1e-6)
+    with pytest.raises(Exception):
+        ev(ref, gen[:, 2:])
