@@ -133,6 +133,9 @@ CASES = {
                          actions=[0, 3, 6, 1], noise=False),
     "rollout_tennis_noise": dict(mode="rollout", config="tennis", S=4, H=32, W=64, weight_seed=6, input_seed=6,
                                  noise_seed=10, actions=[2, 2, 5], noise=True),
+    # build_evaluation_dataset.py: eval-mode forward with the evaluation sampler plug-ins
+    "eval_bair_builder": dict(mode="eval", config="bair", B=2, T=5, S=1, H=64, W=64, gt_init=2, gumbel_temperature=0.7,
+                              weight_seed=9, input_seed=9, noise_seed=13),
     # interpolate.py: generate_next_interpolation(observation, first_action, second_action, factor) after one plain step
     "rollout_bair_interp": dict(mode="rollout", config="bair", S=1, H=64, W=64, weight_seed=7, input_seed=8, noise_seed=12,
                                 actions=[4], noise=False, interp=[[0, 3, 0.25], [1, 5, 0.8], [6, 2, 0.5]]),

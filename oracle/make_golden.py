@@ -92,6 +92,28 @@ def run_train_case(case: dict) -> dict:
     return out
 
 
+def run_eval_case(case: dict) -> dict:
+    """evaluation/evaluation_dataset_builder.py:47-54: model(batch, ground_truth_observations_init, OneHotActionSampler,
+    ZeroActionVariationSampler, gumbel_temperature) in eval mode under no_grad."""
+    cfg = build_config(case)
+    R.install_shims()
+    sys.path.insert(0, R.REF_ROOT)
+    from evaluation.action_sampler import OneHotActionSampler
+    from evaluation.action_variation_sampler import ZeroActionVariationSampler
+    sd = O.make_weights(cfg, case["weight_seed"], False)
+    model = R.build_model(cfg, sd, False)
+    model.eval()
+    obs = O.make_observations(case["B"], case["T"], 3 * case["S"], case["H"], case["W"], case["input_seed"])
+    batch = R.make_batch(obs)
+    torch.manual_seed(case["noise_seed"]); random.seed(case["noise_seed"])
+    with torch.no_grad():
+        res = model(batch.to_tuple(), ground_truth_observations_init=case["gt_init"], action_sampler=OneHotActionSampler(),
+                    action_variation_sampler=ZeroActionVariationSampler(), gumbel_temperature=case["gumbel_temperature"])
+    out = {}
+    _record_results(out, RESULT_NAMES_FULL, res)
+    return out
+
+
 def run_rollout_case(case: dict) -> dict:
     cfg = build_config(case)
     reduced = case.get("reduced", False)
@@ -120,7 +142,8 @@ def main(argv):
         if want and name not in want:
             continue
         torch.set_num_threads(os.cpu_count())
-        out = run_rollout_case(case) if case["mode"] == "rollout" else run_train_case(case)
+        out = (run_rollout_case(case) if case["mode"] == "rollout" else run_eval_case(case) if case["mode"] == "eval"
+               else run_train_case(case))
         out["case_json"] = np.array(json.dumps(case))
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **out)

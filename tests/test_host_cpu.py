@@ -304,3 +304,33 @@ def test_evaluation_metrics_match_the_reference(fake_ops):
         np.testing.assert_allclose(float(avg), float(g[f"seq_{tag}_avg"]), rtol=1e-6)
     with pytest.raises(Exception):
         ev(ref, gen[:, 2:])
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["mode"] == "eval"])
+def test_eval_forward_with_samplers_host_logic(name, fake_ops):
+    """build_evaluation_dataset.py path (evaluation_dataset_builder.py:47-54) through the module mirror with CPU stand-ins:
+    eval mode, OneHotActionSampler + ZeroActionVariationSampler plug-ins, against the unmodified reference's outputs; and
+    the builder's frame conversion against numpy."""
+    from playablevideogeneration_b200.caddy import Model
+    from playablevideogeneration_b200.evaluation.samplers import (GroundTruthActionSampler, OneHotActionSampler,
+                                                                  ZeroActionVariationSampler, frames_to_uint8_hwc)
+    case, g = load_case(name)
+    cfg, sd, _, obs = case_inputs(case)
+    model = Model(cfg)
+    model.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    model.eval()
+    torch.manual_seed(case["noise_seed"]); random.seed(case["noise_seed"])
+    with torch.no_grad():
+        res = model(batch_tuple(obs), ground_truth_observations_init=case["gt_init"], action_sampler=OneHotActionSampler(),
+                    action_variation_sampler=ZeroActionVariationSampler(), gumbel_temperature=case["gumbel_temperature"])
+    compare_results(g, RESULT_NAMES_FULL, res, rtol=2e-5, atol=2e-5)
+    # frame conversion of the builder: pad with the first ground-truth frame, [-1, 1] -> [0, 1], channels last, uint8
+    rec = torch.cat([obs[:, 0:1, 0:3], res[0]], dim=1)
+    want = (np.moveaxis(((rec + 1) / 2).numpy(), 2, -1) * 255).clip(0, 255).astype(np.uint8)
+    got = frames_to_uint8_hwc(rec)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == want.shape and np.array_equal(got.numpy(), want)
+    # GroundTruthActionSampler: one-hot of the translated ground-truth action
+    logp = torch.log_softmax(torch.randn(5, 4), dim=1)
+    oh = GroundTruthActionSampler({0: 2, 1: 0, 2: 1})(logp, torch.tensor([0, 1, 2, 3, 1]))
+    assert oh.argmax(dim=1).tolist() == [2, 0, 1, 3, 0] and float(oh.sum()) == 5.0
+    assert OneHotActionSampler()(logp, None).argmax(dim=1).tolist() == logp.argmax(dim=1).tolist()

@@ -286,3 +286,21 @@ def test_evaluation_metrics_match_reference_golden():
     np.testing.assert_allclose(MotionMaskedMSE()(ref, gen).cpu().numpy(), g["motion_masked_mse"], rtol=1e-5, atol=1e-9)
     vcs = VGGCosineSimilarity(Vgg19(O.make_vgg_weights()).to(DEV))
     np.testing.assert_allclose(vcs(ref, gen).cpu().numpy(), g["vgg_cosine"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["mode"] == "eval"])
+def test_eval_forward_with_samplers_matches_reference_golden(name):
+    """build_evaluation_dataset.py path on the device: eval-mode forward with the evaluation sampler plug-ins against the
+    unmodified reference's outputs (argmax-selected actions must agree exactly; tensors to 1e-3)."""
+    from playablevideogeneration_b200.evaluation.samplers import OneHotActionSampler, ZeroActionVariationSampler, frames_to_uint8_hwc
+    case, g = load_case(name)
+    cfg, sd, _, obs = case_inputs(case)
+    model, _ = _build(case, cfg, sd, None)
+    model.eval()
+    torch.manual_seed(case["noise_seed"]); random.seed(case["noise_seed"])
+    with torch.no_grad():
+        res = model(_to_dev(batch_tuple(obs)), ground_truth_observations_init=case["gt_init"], action_sampler=OneHotActionSampler(),
+                    action_variation_sampler=ZeroActionVariationSampler(), gumbel_temperature=case["gumbel_temperature"])
+    compare_results(g, RESULT_NAMES_FULL, res, rtol=1e-3, atol=1e-3)
+    frames = frames_to_uint8_hwc(torch.cat([obs[:, 0:1, 0:3].to(DEV), res[0]], dim=1))
+    assert frames.dtype == torch.uint8 and tuple(frames.shape) == (case["B"], case["T"], case["H"], case["W"], 3)

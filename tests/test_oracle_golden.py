@@ -76,3 +76,19 @@ def test_weight_recipe_covers_reference_state_dict():
     spec = O.model_param_spec(cfg)
     n = sum(int(np.prod(s)) for name, s, kind in spec if kind not in ("rmean", "rvar", "nbt"))
     assert n == 9856367       # SURVEY.md 8b (includes the (7,2) requires_grad=False centroid Parameter)
+
+
+EVAL_CASES = [n for n, c in CASES.items() if c["mode"] == "eval"]
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_oracle_eval_forward_with_samplers_matches_reference(name):
+    """build_evaluation_dataset.py path: eval-mode forward_full_model with OneHotActionSampler / ZeroActionVariationSampler."""
+    from playablevideogeneration_b200.evaluation.samplers import OneHotActionSampler, ZeroActionVariationSampler
+    case, g = load_case(name)
+    cfg, sd, _, obs = case_inputs(case)
+    torch.manual_seed(case["noise_seed"]); random.seed(case["noise_seed"])
+    with torch.no_grad():
+        res = O.forward_full_model({k: v.clone() for k, v in sd.items()}, cfg, batch_tuple(obs), case["gt_init"],
+                                   case["gumbel_temperature"], OneHotActionSampler(), ZeroActionVariationSampler(), train=False)
+    compare_results(g, RESULT_NAMES_FULL, res, rtol=2e-5, atol=2e-5)
