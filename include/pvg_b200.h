@@ -145,6 +145,12 @@ int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int
 /* dweight[c] = sum_groups sum_gx ; dbias[c] = sum_groups sum_g */
 int pvg_bn_bwd_params(const double* sums2, int groups, int C, float* dweight, float* dbias, void* stream);
 
+/* ---- input pipeline: PIL crop + transforms.ToTensor + transforms.Normalize(0.5, 0.5) of dataset/transforms.py:15-32,
+ *      90-108 for frames that already have the target size (every shipped config).  src: [N][Hs][Ws][3] uint8 RGB,
+ *      dst: [N][H][W][3] fp32 = ((u8 / 255) - mean) / std of the box at (left, top); bit-identical to the CPU transform. */
+int pvg_frames_u8_to_nhwc(const uint8_t* src, int N, int Hs, int Ws, int left, int top, int H, int W, float mean, float std,
+                          float* dst, void* stream);
+
 /* ---- resampling: F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) at up_block.py:35,43;
  *      F.interpolate(size, 'bilinear') of the ground truth at losses.py:92,450; nn.MaxPool2d(2) of VGG19 -------- */
 int pvg_upsample2x_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream);

@@ -2,7 +2,7 @@
 
 Runs the UNMODIFIED ``evaluation/metrics/{mse,psnr,motion_masked_mse,vgg_cosine_similarity}.py`` on seeded inputs (VGG19
 with the seeded stand-in weights of ``caddy_oracle.make_vgg_weights``) -> tests/golden/metrics.npz.
-usage: python oracle/make_metric_golden.py"""
+usage: python oracle/make_metric_golden.py [--input-pipeline]   (the flag writes tests/golden/input_pipeline.npz instead)"""
 import os
 import sys
 
@@ -63,5 +63,26 @@ def _slice_names(vgg, features_sd):
     return out
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--input-pipeline" not in sys.argv:
     main()
+
+
+def input_pipeline_golden():
+    """dataset/transforms.py:90-108 (get_final_transforms) on seeded uint8 frames: crop + ToTensor + Normalize(0.5, 0.5)."""
+    from PIL import Image
+    R.install_shims()
+    sys.path.insert(0, R.REF_ROOT)
+    from dataset.transforms import TransformsGenerator
+    rng = np.random.RandomState(7)
+    frames = rng.randint(0, 256, size=(3, 60, 90, 3), dtype=np.uint8)
+    crop = [10, 5, 74, 53]                                  # left, upper, right, lower -> 64 x 48
+    cfg = {"data": {"crop": crop}, "model": {"representation_network": {"target_input_size": [64, 48]}}}
+    tf = TransformsGenerator.get_final_transforms(cfg)["train"]
+    out = np.stack([tf(Image.fromarray(f)).numpy() for f in frames])
+    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "input_pipeline.npz")
+    np.savez_compressed(path, frames=frames, crop=np.array(crop), out=out)
+    print("input pipeline golden", out.shape, float(out.min()), float(out.max()))
+
+
+if __name__ == "__main__" and "--input-pipeline" in sys.argv:
+    input_pipeline_golden()

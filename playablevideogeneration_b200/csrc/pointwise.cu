@@ -754,6 +754,26 @@ static int red_grid_x(int64_t rows, int lanes, int groups) {
   return (int)(want < cap ? want : cap);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// input pipeline: crop + ToTensor + Normalize of uint8 RGB frames, on the device
+// ---------------------------------------------------------------------------------------------------------------
+// src: [N][Hs][Ws][3] uint8 (what PIL / the PNG decoder produces), dst: [N][H][W][3] fp32 = ((u8 / 255) - mean) / std of the
+// crop box whose top-left corner is (left, top).  Same operation order as torchvision's ToTensor + Normalize
+// (dataset/transforms.py:90-108), IEEE divisions: bit-identical to the reference's CPU transform.  15 bytes per pixel.
+__global__ void __launch_bounds__(256) frames_u8_kernel(const uint8_t* __restrict__ src, int64_t total, int Hs, int Ws, int left,
+                                                        int top, int H, int W, float mean, float stdv, float* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int64_t t = i / W;
+    const int y = (int)(t % H);
+    const int64_t n = t / H;
+    const uint8_t* p = src + ((n * Hs + (y + top)) * Ws + (x + left)) * 3;
+    float* o = dst + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = __fdiv_rn(__fdiv_rn((float)p[c], 255.f) - mean, stdv);
+  }
+}
+
 extern "C" {
 
 const char* pvg_last_error(void) { return pvg::g_last_error.c_str(); }
@@ -1005,6 +1025,17 @@ int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, i
   int64_t total = (int64_t)Cout * R * S * CinK + (int64_t)CinRows * R * S * CoutK;
   pack_weight_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, R, S, CinRows, CinK, CoutK,
                                                                           round_hi, fwd_hi, fwd_lo, bwd_hi, bwd_lo);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_frames_u8_to_nhwc(const uint8_t* src, int N, int Hs, int Ws, int left, int top, int H, int W, float mean, float stdv,
+                          float* dst, void* stream) {
+  PVG_CHECK_ARG(src && dst && N > 0 && H > 0 && W > 0, "empty problem");
+  PVG_CHECK_ARG(left >= 0 && top >= 0 && left + W <= Ws && top + H <= Hs, "crop box outside the source frame");
+  PVG_CHECK_ARG(stdv != 0.f, "std must not be zero");
+  const int64_t total = (int64_t)N * H * W;
+  frames_u8_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, total, Hs, Ws, left, top, H, W, mean, stdv, dst);
   PVG_LAUNCH_OK();
   return 0;
 }

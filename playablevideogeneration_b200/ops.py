@@ -680,6 +680,25 @@ def concat_pad(parts: Sequence[Tensor], multiple: int = 32) -> Tensor:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# input pipeline
+# ---------------------------------------------------------------------------------------------------------------
+def frames_from_uint8(frames: Tensor, crop: Optional[Sequence[int]] = None, mean: float = 0.5, std: float = 0.5) -> Tensor:
+    """PIL ``crop`` + ``ToTensor`` + ``Normalize(mean, std)`` of dataset/transforms.py:15-32,90-108 on the device.
+    frames: (N, Hs, Ws, 3) uint8 CUDA tensor (decoded RGB frames); crop = [left, upper, right, lower] as in the YAML
+    (``data.crop``).  Returns the (N, 3, H, W) fp32 observation tensor (channels_last storage, what the kernels consume),
+    bit-identical to the reference's CPU transform for frames that already have the target size."""
+    if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+        raise _lib.PvgError("frames_from_uint8 takes a (N, H, W, 3) uint8 CUDA tensor")
+    frames = frames.contiguous()
+    n, hs, ws, _ = frames.shape
+    left, top, right, bottom = (0, 0, ws, hs) if crop is None else (int(v) for v in crop)
+    h, w = bottom - top, right - left
+    out = empty_nhwc((n, 3, h, w), frames.device)
+    call("pvg_frames_u8_to_nhwc", frames.data_ptr(), n, hs, ws, left, top, h, w, float(mean), float(std), out.data_ptr(), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # losses
 # ---------------------------------------------------------------------------------------------------------------
 class AbsDiffMeanFn(torch.autograd.Function):

@@ -334,3 +334,15 @@ def test_eval_forward_with_samplers_host_logic(name, fake_ops):
     oh = GroundTruthActionSampler({0: 2, 1: 0, 2: 1})(logp, torch.tensor([0, 1, 2, 3, 1]))
     assert oh.argmax(dim=1).tolist() == [2, 0, 1, 3, 0] and float(oh.sum()) == 5.0
     assert OneHotActionSampler()(logp, None).argmax(dim=1).tolist() == logp.argmax(dim=1).tolist()
+
+
+def test_input_pipeline_formula_is_the_reference_transform():
+    """tests/golden/input_pipeline.npz holds the output of the unmodified TransformsGenerator.get_final_transforms (PIL crop +
+    ToTensor + Normalize, dataset/transforms.py:90-108) on seeded uint8 frames.  The formula the CUDA kernel implements -
+    ((u8 / 255) - 0.5) / 0.5 in fp32 on the crop box - must reproduce it bit for bit (the GPU test then holds the kernel
+    to the same formula)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "input_pipeline.npz"))
+    left, top, right, bottom = (int(v) for v in g["crop"])
+    u8 = torch.from_numpy(g["frames"])[:, top:bottom, left:right]                   # (N, H, W, 3)
+    got = ((u8.float() / 255.0) - 0.5) / 0.5
+    assert np.array_equal(got.permute(0, 3, 1, 2).numpy(), g["out"])

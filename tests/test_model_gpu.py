@@ -304,3 +304,19 @@ def test_eval_forward_with_samplers_matches_reference_golden(name):
     compare_results(g, RESULT_NAMES_FULL, res, rtol=1e-3, atol=1e-3)
     frames = frames_to_uint8_hwc(torch.cat([obs[:, 0:1, 0:3].to(DEV), res[0]], dim=1))
     assert frames.dtype == torch.uint8 and tuple(frames.shape) == (case["B"], case["T"], case["H"], case["W"], 3)
+
+
+def test_input_pipeline_kernel_matches_reference_transform():
+    """ops.frames_from_uint8 (crop + ToTensor + Normalize on the device) against the unmodified reference transform's output
+    (tests/golden/input_pipeline.npz): bit-identical."""
+    from playablevideogeneration_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_pipeline.npz"))
+    frames = torch.from_numpy(g["frames"]).to(DEV)
+    out = ops.frames_from_uint8(frames, crop=[int(v) for v in g["crop"]])
+    assert tuple(out.shape) == g["out"].shape and out.dtype == torch.float32
+    assert np.array_equal(out.cpu().numpy(), g["out"])
+    full = ops.frames_from_uint8(frames)                                              # no crop: the whole frame
+    want = ((torch.from_numpy(g["frames"]).float() / 255.0) - 0.5) / 0.5
+    assert torch.equal(full.cpu(), want.permute(0, 3, 1, 2))
+    with pytest.raises(Exception):
+        ops.frames_from_uint8(frames, crop=[0, 0, 1000, 10])
