@@ -43,7 +43,45 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-frames", type=int, default=8, help="frames (B=1 x T) of the CPU baseline sample")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (rollout) measurements")
     return ap.parse_args()
+
+
+def rollout_secondary(dev):
+    """Secondary metric of SURVEY.md 8d (BASELINE configs[4] family): eval-mode autoregressive rollout at BAIR 256x256,
+    E -> R -> D per generated frame.  Batch 64 kernel by kernel, batch 1 (play.py's own case) kernel by kernel and with one
+    CUDA graph per step.  CUDA events around the timed steps, after 3 warm-up steps."""
+    import torch
+    from oracle.cases import build_config
+    from playablevideogeneration_b200.caddy import Model
+    cfg = build_config(dict(config="bair", H=256, W=256, S=1))
+    torch.manual_seed(0)
+    model = Model(cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(0)
+    out = {}
+    with torch.no_grad():
+        for batch, graphed, steps in ((64, False, 20), (1, False, 50), (1, True, 50)):
+            model.enable_graphed_inference(graphed)
+            obs = (torch.rand((batch, 3, 256, 256), generator=g) * 2 - 1).to(dev)
+            actions = torch.randint(0, 7, (steps + 3, batch), generator=g).to(dev)
+            model.start_inference()
+            model.dynamics_network.reinit_memory(batch)
+            for t in range(3):
+                _, obs = model.generate_next_batch(obs, actions[t])
+            model.start_inference()
+            model.dynamics_network.reinit_memory(batch)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for t in range(steps):
+                frames, obs = model.generate_next_batch(obs, actions[3 + t])
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[f"rollout_b{batch}" + ("_cuda_graph" if graphed else "")] = dict(
+                ms_per_generated_step=ms, frames_per_s=batch / (ms * 1e-3), steps=steps, finite=bool(torch.isfinite(frames).all()))
+    out["workload"] = "BAIR 256x256 eval-mode rollout (generate_next_batch), fp32-equivalent split product"
+    return out
 
 
 def load_peaks():
@@ -331,6 +369,12 @@ def main():
                 e2e=dict(value=frames_per_step / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d * world,
                          d2h_bytes_per_step=8 * world, ms_per_step=ms_e2e, last_loss=loss_host),
                 gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu_base)
+    if world == 1 and not args.no_secondary:
+        # after every headline number is final: a failure here cannot touch them
+        try:
+            line["secondary"] = rollout_secondary(dev)
+        except BaseException as e:          # noqa: BLE001 - report, never lose the headline line
+            line["secondary"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(line), flush=True)
     _hard_exit(world)
 
