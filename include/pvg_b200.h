@@ -38,11 +38,16 @@ extern "C" {
 
 #define PVG_CORR_BF16 0
 #define PVG_CORR_FP16 1
+#define PVG_CORR_FP16_ALL 2 /* fp16 planes { f16((X - f16(X)) * 2^12), f16(X) }: the pair alone carries X to 22 bits, so ALL three
+                               products of the split run as kind::f16 MMAs on the planes and the convolution never reads the
+                               fp32 tensor (x / w may be NULL).  For O(1) operands (forward activations, weights); gradients keep
+                               the TF32 main product with bf16 corrections (fp16 has no range for 1e-6..1e-12). */
 
 #define PVG_ALGO_AUTO 0
 #define PVG_ALGO_SIMT 1     /* fp32 CUDA-core implicit GEMM (any shape) */
 #define PVG_ALGO_UMMA 2     /* tcgen05 / TMEM / TMA implicit GEMM (Cin % 4 == 0, % 8 with 16-bit correction planes) */
-#define PVG_ALGO_UMMA_PERSISTENT 3   /* EXPERIMENTAL, opt-in: persistent-tile variant of the 1-CTA split-product kernel */
+#define PVG_ALGO_UMMA_PERSISTENT 3   /* force the persistent-tile variant of the split-product kernels (the default for 64/128-wide
+                                        tiles; PVG_PERSISTENT=0 in the environment selects one tile per CTA instead) */
 
 typedef struct pvg_conv_desc {
   int32_t N, H, W;          /* output == input spatial size (all convs on the path are stride 1, "same" padding) */
@@ -55,7 +60,7 @@ typedef struct pvg_conv_desc {
   int32_t algo;             /* PVG_ALGO_* */
   int32_t nprod;            /* 1 = single TF32 product, 3 = 3xTF32 (fp32-equivalent), 2 = TF32 + 2 bf16 corrections
                                (fp32-equivalent, see above); SIMT ignores it */
-  int32_t corr_fmt;         /* PVG_CORR_BF16 / PVG_CORR_FP16: format of the 16-bit correction planes (nprod == 2) */
+  int32_t corr_fmt;         /* PVG_CORR_BF16 / PVG_CORR_FP16 / PVG_CORR_FP16_ALL: format of the 16-bit planes (nprod == 2) */
 } pvg_conv_desc;
 
 const char* pvg_last_error(void);

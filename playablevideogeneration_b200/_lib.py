@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libpvg_b200.so")
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PERSISTENT = 0, 1, 2, 3
-CORR_BF16, CORR_FP16 = 0, 1
+CORR_BF16, CORR_FP16, CORR_FP16_ALL = 0, 1, 2
 
 
 class ConvDesc(Structure):

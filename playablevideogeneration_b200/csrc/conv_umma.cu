@@ -42,7 +42,9 @@ constexpr int kSmemBudget = 200 * 1024;
 // stage -> twice the stages in the same shared memory, i.e. a deeper TMA prefetch for the latency-bound 3xTF32 tiles)
 template <int BN, int NPROD, int KC>
 struct Cfg {
-  static constexpr int kPlanes = NPROD >= 2 ? 2 : 1;         // NPROD == 2: the second 'plane' holds the two bf16 half-width tiles
+  // NPROD == 2: the second 'plane' holds the two 16-bit half-width tiles.  NPROD == 4 (all three products as kind::f16 MMAs on
+  // the fp16 plane pair, PVG_CORR_FP16_ALL): the ONLY plane is that pair - 2 x 64-byte rows = the bytes of one fp32 row
+  static constexpr int kPlanes = (NPROD == 2 || NPROD == 3) ? 2 : 1;
   static constexpr int kRowBytes = KC * 4;
   static constexpr int kABytes = kTileM * kRowBytes;
   static constexpr int kBBytes = BN * kRowBytes;
@@ -59,7 +61,7 @@ struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
   static_assert(KC == 32 || KC == 16, "KC must be 16 or 32");
-  static_assert(NPROD != 2 || KC == 32, "bf16 corrections use 32-channel stages");
+  static_assert((NPROD != 2 && NPROD != 4) || KC == 32, "16-bit planes use 32-channel stages");
 };
 
 struct ConvParams {
@@ -176,8 +178,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (leader) {
         uint8_t* st = stage_base + stage * C::kStageBytes;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        if (NPROD == 4) {             // fp16 plane pairs only: [f16(lo * 2^12) | f16(x)] tiles of A, then of B
+          tma_load_5d(st, &tmAlo, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+          tma_load_3d(st + C::kABytes, &tmBlo, &full_bar[stage], k * KC, co0, 0);
+        } else {
         tma_load_4d(st, &tmA, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
         tma_load_2d(st + C::kPlanes * C::kABytes, &tmB, &full_bar[stage], k * KC, co0);
+        }
         if (NPROD == 3) {
           tma_load_4d(st + C::kABytes, &tmAlo, &full_bar[stage], cc * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
           tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &tmBlo, &full_bar[stage], k * KC, co0);
@@ -216,6 +223,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           if (leader) {
             const uint32_t a_hi = stage * kStageU, a_lo = a_hi + kAU, b_hi = a_hi + 2 * kAU, b_lo = b_hi + kBU;
+            if constexpr (NPROD == 4) {
+              // stage = [f16(x_lo * 2^12) | f16(x)] tiles of A, then [f16(w_lo * 2^12) | f16(w)] tiles of B (64-byte rows):
+              // corrections and main product are all kind::f16 MMAs with K = 16
+              const uint32_t pa_lo = a_hi, pa_x = a_hi + kAU / 2, pb_lo = a_hi + kAU, pb_x = pb_lo + kBU / 2;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_bf16(corr, d16 + (pa_lo + 2 * ks), d16 + (pb_x + 2 * ks), idesc16, corr_acc);
+                corr_acc = 1;
+              }
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) umma_bf16(corr, d16 + (pa_x + 2 * ks), d16 + (pb_lo + 2 * ks), idesc16, 1);
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_bf16(main_acc, d16 + (pa_x + 2 * ks), d16 + (pb_x + 2 * ks), idesc16, main_started);
+                main_started = 1;
+              }
+            } else {
             if constexpr (NPROD == 2) {
               // a_lo region: [f16(x_lo * 2^12) | f16(x)] tiles, b_lo region: [f16(w_lo * 2^12) | f16(w_hi)] tiles, 64-byte rows,
               // K = 16 per MMA; the accumulator holds 2^12 x the correction
@@ -240,6 +264,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int ks = 0; ks < C::kKSteps; ++ks) {
               umma_tf32(main_acc, d32 + (a_hi + 2 * ks), d32 + (b_hi + 2 * ks), idesc, main_started);
               main_started = 1;
+            }
             }
             umma_commit(&empty_bar[stage]);     // slot reusable once these MMAs have read it
           }
@@ -301,7 +326,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_arrive(&tempty_bar[b]);
       }
       // the last tfull commit also covers the correction MMAs (NPROD == 2: accumulated at 2^12 x their value)
-      constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
+      constexpr float kCorrScale = (NPROD == 2 || NPROD == 4) ? 0x1p-12f : 1.f;
 #pragma unroll
       for (int c = 0; c < BN; c += 16) {
         float v[16];
@@ -327,8 +352,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in: pvg_conv_desc.algo = PVG_ALGO_UMMA_PERSISTENT or PVG_PERSISTENT=1; not on the default path until it
-// has been validated on a B200): persistent variant of the 1-CTA split-product kernel.  One CTA per SM walks
+// Persistent variant of the 1-CTA split-product kernel (the default for 64- and 128-wide tiles; PVG_PERSISTENT=0 disables).  One CTA per SM walks
 // tile = blockIdx.x, blockIdx.x + gridDim.x, ... so that (1) barrier init, TMEM allocation and tensor-map prefetch are
 // paid once per SM instead of once per tile, (2) the TMA producer prefetches the next tile's first stages while the
 // current tile drains, and (3) the bias / activation / store part of the epilogue overlaps the next tile's MMAs: the
@@ -758,8 +782,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem2_dealloc(tmem_acc, C::kTmemCols);
 }
 
-// EXPERIMENTAL (opt-in like conv_umma_persistent_kernel, not yet validated on a GPU): persistent variant of the CTA-pair
-// kernel.  One cluster per SM pair walks work items cid = cluster, cluster + #clusters, ...; the hand-off of the correction
+// Persistent variant of the CTA-pair kernel (default, like conv_umma_persistent_kernel).  One cluster per SM pair walks work items cid = cluster, cluster + #clusters, ...; the hand-off of the correction
 // accumulators (one per CTA, both written by the leader's cta_group::2 MMAs) goes through the leader's `cfree` barrier with
 // 256 arrivals, exactly like `tempty`.
 template <int NPROD>
@@ -1056,20 +1079,23 @@ static int launch_umma(const pvg_conv_desc* d, const float* x, const float* x_lo
   // {32 ch, ...} reads past the tensor's channel extent and gets zeros (out-of-bounds fill) - no padded copy in HBM
   const int CinK = (d->Cin + 31) & ~31;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
-  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt != PVG_CORR_BF16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
   const int K = d->R * d->S * CinK;
   int rc;
-  if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, KC, p.tw, p.th, p.tn))) return rc;
-  if ((rc = encode_w_map(&tmB, w, d->Cout, K, BN, KC))) return rc;
+  if (NPROD != 4) {
+    if ((rc = encode_act_map(&tmA, x, d->N, d->H, d->W, d->Cin, KC, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_w_map(&tmB, w, d->Cout, K, BN, KC))) return rc;
+  }
   if (NPROD == 3) {
     if ((rc = encode_act_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, KC, p.tw, p.th, p.tn))) return rc;
     if ((rc = encode_w_map(&tmBlo, w_lo, d->Cout, K, BN, KC))) return rc;
-  } else if (NPROD == 2) {
+  } else if (NPROD == 2 || NPROD == 4) {
     if ((rc = encode_nhwc_16x2_map(&tmAlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
     if ((rc = encode_w_16x2_map(&tmBlo, w_lo, d->Cout, K, BN))) return rc;
+    if (NPROD == 4) { tmA = tmAlo; tmB = tmBlo; }      // the fp32 tensors are not read
   } else {
     tmAlo = tmA; tmBlo = tmB;
   }
@@ -1091,7 +1117,7 @@ static int launch_umma_persistent(const pvg_conv_desc* d, const float* x, const 
   ConvParams p;
   const int CinK = (d->Cin + 31) & ~31;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
-  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt != PVG_CORR_BF16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
@@ -1126,7 +1152,7 @@ static int launch_umma2_persistent(const pvg_conv_desc* d, const float* x, const
   ConvParams p;
   const int CinK = (d->Cin + 31) & ~31;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
-  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt != PVG_CORR_BF16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
@@ -1155,12 +1181,14 @@ static int launch_umma2_persistent(const pvg_conv_desc* d, const float* x, const
   return 0;
 }
 
-// experimental persistent 1-CTA kernel: explicit algo or PVG_PERSISTENT=1 (never the default)
+// Persistent tile loop (validated on B200, round 2: 120 conv parity cases; fixed cost per tile 3.7 -> 1.3 us for the 1-CTA
+// kernel and 5.3 -> 1.3 us for the CTA pair, same time per k-iteration): the default for the split-product kernels.
+// PVG_PERSISTENT=0 selects the one-tile-per-CTA kernels (A/B knob).
 static bool want_persistent(const pvg_conv_desc* d) {
   static int env = -1;
   if (env < 0) {
     const char* e = getenv("PVG_PERSISTENT");
-    env = (e && atoi(e) == 1) ? 1 : 0;
+    env = (e && atoi(e) == 0) ? 0 : 1;
   }
   return d->algo == PVG_ALGO_UMMA_PERSISTENT || env == 1;
 }
@@ -1174,7 +1202,7 @@ static int launch_umma2(const pvg_conv_desc* d, const float* x, const float* x_l
   // {32 ch, ...} reads past the tensor's channel extent and gets zeros (out-of-bounds fill) - no padded copy in HBM
   const int CinK = (d->Cin + 31) & ~31;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
-  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = d->corr_fmt != PVG_CORR_BF16;
   choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
@@ -1233,6 +1261,13 @@ template <int NPROD>
 static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* w, const float* w_lo,
                        const float* bias, float* y, cudaStream_t st) {
   const int co = d->Cout;
+  if constexpr (NPROD == 4) {        // all-fp16 split product: 1-CTA kernel (experiment; superseded by conv_h3.cu)
+    if (co <= 16) return launch_umma<16, 4, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+    if (co <= 32) return launch_umma<32, 4, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+    if (co <= 64) return launch_umma<64, 4, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+    if (co <= 80) return launch_umma<80, 4, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+    return launch_umma<128, 4, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+  } else {
   if constexpr (NPROD >= 2) {
     if (want_persistent(d) && co > 32 && co <= 64) return launch_umma_persistent<64, NPROD>(d, x, x_lo, w, w_lo, bias, y, st);
     if (want_persistent(d) && co > 80) {
@@ -1257,6 +1292,7 @@ static int dispatch_bn(const pvg_conv_desc* d, const float* x, const float* x_lo
     if (stage_channels() == 16) return launch_umma<128, NPROD, 16>(d, x, x_lo, w, w_lo, bias, y, st);
   }
   return launch_umma<128, NPROD, 32>(d, x, x_lo, w, w_lo, bias, y, st);
+  }
 }
 
 }  // namespace pvg
@@ -1267,7 +1303,8 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void
                               const float* bias, float* y, void* stream) {
   const float* x_lo = (const float*)x_lo_;      // fp32 residual plane (nprod == 3) or bf16 plane pair (nprod == 2)
   const float* w_lo = (const float*)w_lo_;
-  PVG_CHECK_ARG(d && x && w && y, "null argument");
+  const bool h3 = d && d->nprod == 2 && d->corr_fmt == PVG_CORR_FP16_ALL;      // reads the fp16 plane pairs only
+  PVG_CHECK_ARG(d && y && (h3 || (x && w)), "null argument");
   PVG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "empty problem");
   PVG_CHECK_ARG(d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "only odd 'same' kernels are supported");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1285,6 +1322,7 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void
   if (d->nprod == 2) {      // x_lo / w_lo: bf16 plane pairs [2][numel] (pvg_split_16 / pvg_pack_16x2)
     PVG_CHECK_ARG(x_lo && w_lo, "nprod == 2 needs the bf16 plane pairs of x and w");
     PVG_CHECK_ARG((((uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0, "bf16 planes must be 16-byte aligned");
+    if (h3) return dispatch_bn<4>(d, x, x_lo, w, w_lo, bias, y, st);
     return dispatch_bn<2>(d, x, x_lo, w, w_lo, bias, y, st);
   }
   return dispatch_bn<1>(d, x, nullptr, w, nullptr, bias, y, st);

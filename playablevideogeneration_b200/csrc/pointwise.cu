@@ -585,41 +585,58 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 // that is coherent over the batch (with bf16 weights that error measured 30x the fp32 CPU oracle's on cancellation-heavy
 // gradients); bf16 keeps fp32's exponent range and is what gradients (1e-6..1e-12) need.  kind::f16 cannot mix the two
 // formats in one MMA (illegal instruction on sm_100a), so a conv uses one format for both operands.
-template <bool FP16>
+// FMT: PVG_CORR_BF16 (0) | PVG_CORR_FP16 (1) | PVG_CORR_FP16_ALL (2, fp16 planes whose residual is taken w.r.t. f16(x), so
+// that the plane pair alone carries x to 22 bits: ALL three products of the split then run as kind::f16 MMAs on the planes
+// and the fp32 tensor is not read by the convolution at all)
+template <int FMT>
 __device__ __forceinline__ uint32_t f16x2_bits(float a, float b) {
-  if (FP16) {
+  if (FMT != PVG_CORR_BF16) {
     __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
     return *reinterpret_cast<uint32_t*>(&v);
   }
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-template <bool FP16>
+// the part of v that the "hi" operand of the main product carries: trunc_tf32(v) (the tensor core truncates the raw fp32
+// operand) or, in the all-fp16 evaluation, f16(v)
+template <int FMT>
+__device__ __forceinline__ float hi_part(float v) {
+  if (FMT == PVG_CORR_FP16_ALL) return __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+  return tf32_part(v, false);
+}
+template <int FMT>
 __device__ __forceinline__ void store_16_planes(uint16_t* planes, int64_t n, int64_t i4, float4 v) {
-  const float4 h = make_float4(tf32_part(v.x, false), tf32_part(v.y, false), tf32_part(v.z, false), tf32_part(v.w, false));
+  const float4 h = make_float4(hi_part<FMT>(v.x), hi_part<FMT>(v.y), hi_part<FMT>(v.z), hi_part<FMT>(v.w));
   constexpr float kS = 4096.f;
-  uint2 lo = make_uint2(f16x2_bits<FP16>((v.x - h.x) * kS, (v.y - h.y) * kS), f16x2_bits<FP16>((v.z - h.z) * kS, (v.w - h.w) * kS));
-  uint2 xb = make_uint2(f16x2_bits<FP16>(v.x, v.y), f16x2_bits<FP16>(v.z, v.w));
+  uint2 lo = make_uint2(f16x2_bits<FMT>((v.x - h.x) * kS, (v.y - h.y) * kS), f16x2_bits<FMT>((v.z - h.z) * kS, (v.w - h.w) * kS));
+  uint2 xb = make_uint2(f16x2_bits<FMT>(v.x, v.y), f16x2_bits<FMT>(v.z, v.w));
   *reinterpret_cast<uint2*>(planes + 4 * i4) = lo;
   *reinterpret_cast<uint2*>(planes + n + 4 * i4) = xb;
 }
-template <bool FP16>
+template <int FMT>
 __global__ void __launch_bounds__(256) split_16_kernel(const float* __restrict__ x, uint16_t* __restrict__ planes, int64_t n) {
   const int64_t q = n / 4;                      // n % 8 == 0 (checked by the host wrapper)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x)
-    store_16_planes<FP16>(planes, n, i, ldg4(x + 4 * i));
+    store_16_planes<FMT>(planes, n, i, ldg4(x + 4 * i));
 }
-// the same for a packed weight given its tf32 hi / residual lo planes: planes = { f16(lo * 2^12), f16(hi) }
-template <bool FP16>
+// the same for a packed weight given its tf32 hi / residual lo planes (w = hi + lo exactly):
+// planes = { f16(lo * 2^12), f16(hi) }, or { f16((w - f16(w)) * 2^12), f16(w) } in the all-fp16 evaluation
+template <int FMT>
 __global__ void __launch_bounds__(256) pack_16x2_kernel(const float* __restrict__ hi, const float* __restrict__ lo,
                                                         uint16_t* __restrict__ planes, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t v = f16x2_bits<FP16>(lo[i] * 4096.f, hi[i]);
+    float h = hi[i], l = lo[i];
+    if (FMT == PVG_CORR_FP16_ALL) {
+      const float w = h + l;
+      h = hi_part<FMT>(w);
+      l = w - h;
+    }
+    const uint32_t v = f16x2_bits<FMT>(l * 4096.f, h);
     planes[i] = (uint16_t)(v & 0xffffu);
     planes[n + i] = (uint16_t)(v >> 16);
   }
 }
-template <bool FP16>
+template <int FMT>
 __global__ void __launch_bounds__(256) act_bwd_split_16_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                                int act, float slope, float* __restrict__ g,
                                                                uint16_t* __restrict__ planes, int64_t n) {
@@ -629,7 +646,7 @@ __global__ void __launch_bounds__(256) act_bwd_split_16_kernel(const float* __re
     float4 v = make_float4(d.x * act_bwd_from_out(o.x, act, slope), d.y * act_bwd_from_out(o.y, act, slope),
                            d.z * act_bwd_from_out(o.z, act, slope), d.w * act_bwd_from_out(o.w, act, slope));
     stg4(g + 4 * i, v);
-    store_16_planes<FP16>(planes, n, i, v);
+    store_16_planes<FMT>(planes, n, i, v);
   }
 }
 
@@ -967,16 +984,20 @@ int pvg_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream
 
 int pvg_split_16(const float* x, void* planes, int64_t n, int fmt, void* stream) {
   PVG_CHECK_ARG(n % 8 == 0 && (((uintptr_t)x | (uintptr_t)planes) & 15) == 0, "n % 8 == 0 and 16-byte aligned pointers required");
-  if (fmt == PVG_CORR_FP16) split_16_kernel<true><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n);
-  else split_16_kernel<false><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n);
+  PVG_CHECK_ARG(fmt >= 0 && fmt <= 2, "unknown 16-bit plane format");
+  if (fmt == PVG_CORR_FP16_ALL) split_16_kernel<2><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n);
+  else if (fmt == PVG_CORR_FP16) split_16_kernel<1><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n);
+  else split_16_kernel<0><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n);
   PVG_LAUNCH_OK();
   return 0;
 }
 
 int pvg_pack_16x2(const float* hi, const float* lo, void* planes, int64_t n, int fmt, void* stream) {
   PVG_CHECK_ARG(hi && lo && planes, "null argument");
-  if (fmt == PVG_CORR_FP16) pack_16x2_kernel<true><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(hi, lo, (uint16_t*)planes, n);
-  else pack_16x2_kernel<false><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(hi, lo, (uint16_t*)planes, n);
+  PVG_CHECK_ARG(fmt >= 0 && fmt <= 2, "unknown 16-bit plane format");
+  if (fmt == PVG_CORR_FP16_ALL) pack_16x2_kernel<2><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(hi, lo, (uint16_t*)planes, n);
+  else if (fmt == PVG_CORR_FP16) pack_16x2_kernel<1><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(hi, lo, (uint16_t*)planes, n);
+  else pack_16x2_kernel<0><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(hi, lo, (uint16_t*)planes, n);
   PVG_LAUNCH_OK();
   return 0;
 }
@@ -985,10 +1006,13 @@ int pvg_act_bwd_split_16(const float* dy, const float* y, int act, float slope, 
                          void* stream) {
   PVG_CHECK_ARG(n % 8 == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)g | (uintptr_t)planes) & 15) == 0,
                 "n % 8 == 0 and 16-byte aligned pointers required");
-  if (fmt == PVG_CORR_FP16)
-    act_bwd_split_16_kernel<true><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
+  PVG_CHECK_ARG(fmt >= 0 && fmt <= 2, "unknown 16-bit plane format");
+  if (fmt == PVG_CORR_FP16_ALL)
+    act_bwd_split_16_kernel<2><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
+  else if (fmt == PVG_CORR_FP16)
+    act_bwd_split_16_kernel<1><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
   else
-    act_bwd_split_16_kernel<false><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
+    act_bwd_split_16_kernel<0><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -32,8 +32,12 @@ _precision = os.environ.get("PVG_PRECISION", "tf32x3")
 #           cancellation-heavy gradients of the ill-conditioned training graph - and suits the O(1) forward activations;
 #           bf16 has fp32's exponent range, which the gradients (1e-6 .. 1e-12) need.  The weight gradient multiplies two
 #           activation tensors (no weight operand): bf16.
-CORR_MODES = ("tf32", "bf16", "fp16")
-DEFAULT_CORR = {"fwd": os.environ.get("PVG_CORR", "fp16"), "dgrad": os.environ.get("PVG_DGRAD_CORR", "bf16"),
+#   "h3": ALL three products as kind::f16 MMAs on fp16 plane pairs {f16((x - f16(x)) * 2^12), f16(x)} (PVG_CORR_FP16_ALL): the
+#           pair carries 22 bits of x, products are exact, accumulation is fp32 - the same arithmetic as TF32 + fp16
+#           corrections at 3/4 of its tensor time and half of its shared-memory traffic (the conv never reads the fp32 tensor).
+#           Needs operands inside fp16's range: forward activations and weights (default for "fwd"); not gradients.
+CORR_MODES = ("tf32", "bf16", "fp16", "h3")
+DEFAULT_CORR = {"fwd": os.environ.get("PVG_CORR", "h3"), "dgrad": os.environ.get("PVG_DGRAD_CORR", "bf16"),
                 "wgrad": os.environ.get("PVG_WGRAD_CORR", "bf16")}
 _corr = dict(DEFAULT_CORR)
 _tf32_truncates: Optional[bool] = None     # does tcgen05 kind::tf32 truncate raw fp32 operands? (probed lazily)
@@ -64,9 +68,15 @@ def _mode(role: str) -> Tuple[int, int]:
     if _precision != "tf32x3":
         return 1, 0
     c = _corr[role]
-    if c == "tf32" or not tf32_truncates():
+    if c == "h3" and role == "wgrad":       # the weight-gradient kernel (MN-major operands) has no all-fp16 evaluation
+        c = "bf16"
+    if c == "tf32" or (c != "h3" and not tf32_truncates()):
         return 3, 0
-    return 2, (_lib.CORR_FP16 if c == "fp16" else _lib.CORR_BF16)
+    return 2, {"fp16": _lib.CORR_FP16, "bf16": _lib.CORR_BF16, "h3": _lib.CORR_FP16_ALL}[c]
+
+
+def _plane_dtype(fmt: int):
+    return torch.bfloat16 if fmt == _lib.CORR_BF16 else torch.float16
 
 
 def _stream() -> int:
@@ -202,7 +212,7 @@ class _Packs:
             t = self._bf.get((which, fmt))
             if t is None:
                 n = planes.shape[1]
-                t = torch.empty((2 * n,), dtype=torch.float16 if fmt == _lib.CORR_FP16 else torch.bfloat16, device=planes.device)
+                t = torch.empty((2 * n,), dtype=_plane_dtype(fmt), device=planes.device)
                 call("pvg_pack_16x2", planes[0].data_ptr(), planes[1].data_ptr(), t.data_ptr(), n, fmt, _stream())
                 self._bf[(which, fmt)] = t
             return t
@@ -299,7 +309,7 @@ def _split(x: Tensor, nprod: int = 3, fmt: int = 0) -> Tuple[Tensor, Tensor]:
     """(hi, lo) operands of the split product for an activation tensor: nprod == 3 -> fp32 residual plane,
     nprod == 2 -> the 16-bit plane pair {f16((x - trunc_tf32(x)) * 2^12), f16(x)} (x itself is the hi operand)."""
     if nprod == 2:
-        planes = torch.empty((2 * x.numel(),), dtype=torch.float16 if fmt == _lib.CORR_FP16 else torch.bfloat16, device=x.device)
+        planes = torch.empty((2 * x.numel(),), dtype=_plane_dtype(fmt), device=x.device)
         call("pvg_split_16", x.data_ptr(), planes.data_ptr(), x.numel(), fmt, _stream())
         return x, planes
     lo = torch.empty_like(x)
@@ -366,8 +376,7 @@ class Conv2dFn(torch.autograd.Function):
             g = torch.empty_like(dy)
             fused = dmode if want_dx else (wmode if want_dw else (0, 0))
             if fused[0] == 2:            # activation backward and the 16-bit planes of g in one pass
-                planes = torch.empty((2 * dy.numel(),), dtype=torch.float16 if fused[1] == _lib.CORR_FP16 else torch.bfloat16,
-                                     device=dy.device)
+                planes = torch.empty((2 * dy.numel(),), dtype=_plane_dtype(fused[1]), device=dy.device)
                 call("pvg_act_bwd_split_16", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), planes.data_ptr(),
                      dy.numel(), fused[1], _stream())
                 g_splits[fused] = (g, planes)

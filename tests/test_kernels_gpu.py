@@ -110,7 +110,7 @@ def test_tf32_probe_reports_rounding_mode():
     assert trunc in (True, False)
 
 
-@pytest.fixture(params=["bf16", "fp16", "tf32"])
+@pytest.fixture(params=["bf16", "fp16", "tf32", "h3"])
 def corr(request):
     """Every evaluation of the two correction products of the fp32-equivalent split (C-ABI nprod = 2 with bf16 / fp16
     planes, nprod = 3), applied to the forward, data-gradient and weight-gradient kernels alike."""

@@ -75,6 +75,8 @@ case $s in
   persist2_t) PVG_PERSISTENT=1 run persist2_t 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv" -p no:cacheprovider ;;
   persist2_b) PVG_PERSISTENT=1 PVG_2CTA=1 run persist2_b 300 python tools/tile_model.py tf32x3; PVG_PERSISTENT=1 run persist2_lb 300 python tools/layer_bench.py tf32x3 vgg ;;
   corr_diag) run corr_diag 300 python tools/corr_diag.py ;;
+  t_umma) run t_umma 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
+  tm_h3) PVG_2CTA=0 PVG_PERSISTENT=0 run tm_h3 300 python tools/tile_model.py tf32x3; PVG_2CTA=0 PVG_PERSISTENT=0 run tm_h3_64 300 python tools/tile_model.py tf32x3 64; PVG_2CTA=0 PVG_PERSISTENT=0 PVG_CORR=fp16 run tm_fp16 300 python tools/tile_model.py tf32x3 ;;
 esac
 done
 cp $OUT/summary.txt $OUT/summary_$(date +%s).txt 2>/dev/null
