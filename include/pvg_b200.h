@@ -75,6 +75,13 @@ int pvg_has_umma(void);
  * y[n,h,w,co] = act(bias[co] + sum_{r,s,ci} x[n,h+r-pad,w+s-pad,ci] * w[co,r,s,ci]).   bias may be NULL. */
 int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo, const float* w, const void* w_lo,
                    const float* bias, float* y, void* stream);
+/* The same convolution with x and w given ONLY as fp16 plane pairs (PVG_CORR_FP16_ALL: pvg_split_16 / pvg_pack_16x2 with that
+ * format, or the y_planes of a previous call): all three products of the split run as kind::f16 MMAs; 3x3 convolutions reuse
+ * one haloed shared-memory tile for their 9 taps; persistent CTAs (CTA pairs on large problems).  d->Cin % 8 == 0.
+ * y_planes (optional, Cout % 8 == 0): fp16 [2][N*H*W*Cout], the plane pair of y, written by the epilogue so that the next
+ * convolution needs no separate split pass (vgg.py:48-52 conv -> relu -> conv chains, residual_block.py:52-57). */
+int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
+                          void* y_planes, void* stream);
 /* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinK] and data-gradient pack [CinRows][R][S][CoutK] with flipped
  * taps (dgrad = pvg_conv2d_fwd(dy, bwd pack)).  CinRows >= Cin: physical channels of the activation (zero-padded concat
  * buffers); CinK >= CinRows, CoutK >= Cout: K-side channel counts of the consumer (tensor-core kernels: rounded up to 32,

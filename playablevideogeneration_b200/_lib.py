@@ -24,6 +24,7 @@ P = c_void_p
 # name -> (argtypes); every function returns int (0 = ok) except pvg_last_error / pvg_version / pvg_has_umma
 _SIGNATURES = {
     "pvg_conv2d_fwd": [POINTER(ConvDesc), P, P, P, P, P, P, P],
+    "pvg_conv2d_fwd_planes": [POINTER(ConvDesc), P, P, P, P, P, P],
     "pvg_pack_conv_weight": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P],
     "pvg_conv2d_wgrad": [POINTER(ConvDesc), c_int, P, P, P, P],
     "pvg_conv2d_wgrad_umma": [POINTER(ConvDesc), c_int, P, P, P, P, P, P, c_int, P],

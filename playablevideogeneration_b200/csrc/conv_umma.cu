@@ -33,6 +33,8 @@
 namespace pvg {
 
 int conv2d_fwd_simt(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int conv2d_fwd_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
+                  void* y_planes, cudaStream_t st);      // conv_h3.cu
 
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
@@ -63,66 +65,6 @@ struct Cfg {
   static_assert(KC == 32 || KC == 16, "KC must be 16 or 32");
   static_assert((NPROD != 2 && NPROD != 4) || KC == 32, "16-bit planes use 32-channel stages");
 };
-
-struct ConvParams {
-  int N, H, W, Cin, Cout, R, S, pad, act;
-  float slope;
-  int tw, th, tn;               // M-tile patch (tw*th*tn == 128)
-  int tiles_w, tiles_h, tiles_n;
-  const float* bias;
-  float* y;
-  int corr_fp16;                // NPROD == 2: the 16-bit correction planes are fp16 (else bf16)
-};
-
-// bias + activation of 16 consecutive output channels and their NHWC store.  Everything that is uniform over the tile (bias
-// pointer, activation kind, Cout bounds) is tested once per 16 channels, not per element: the straightforward per-element
-// form compiled to ~66 instructions per output value and made the final epilogue 30 % of a 72-k-iteration tile (ncu).
-__device__ __forceinline__ void finish16(float (&v)[16], const float* __restrict__ bias, int co, int Cout, int act, float slope,
-                                         float* __restrict__ yrow, bool valid, bool vec_ok) {
-  if (co >= Cout) return;
-  const bool full = co + 16 <= Cout;
-  if (bias != nullptr) {
-    if (full && vec_ok) {                         // Cout % 4 == 0 and 16-byte aligned rows => bias + co is 16-byte aligned too
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 b = ldg4(bias + co + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (co + j < Cout) v[j] += __ldg(bias + co + j);
-    }
-  }
-  switch (act) {
-    case PVG_ACT_LRELU:
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
-      break;
-    case PVG_ACT_RELU:
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-      break;
-    case PVG_ACT_TANH:
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
-      break;
-    case PVG_ACT_SIGMOID:
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
-      break;
-    default: break;
-  }
-  if (!valid) return;
-  if (full && vec_ok) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (co + j < Cout) yrow[co + j] = v[j];
-  }
-}
 
 template <int BN, int NPROD, int KC>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -1058,7 +1000,7 @@ static int encode_w_map(CUtensorMap* m, const float* w, int Cout, int K, int bn,
 }
 
 // choose the 128-pixel patch (tw, th, tn) that wastes the fewest MMA rows
-static void choose_patch(int N, int H, int W, int* tw, int* th, int* tn) {
+void choose_patch(int N, int H, int W, int* tw, int* th, int* tn) {
   static const int cand[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {4, 32, 1}, {64, 2, 1}, {128, 1, 1}, {16, 4, 2},
                                 {8, 8, 2},  {4, 16, 2}, {16, 2, 4}, {8, 4, 4},  {4, 8, 4},  {4, 4, 8},   {8, 2, 8},
                                 {2, 8, 8},  {2, 2, 32}, {4, 2, 16}, {2, 4, 16}, {1, 1, 128}, {2, 1, 64}, {1, 2, 64}};
@@ -1322,7 +1264,11 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void
   if (d->nprod == 2) {      // x_lo / w_lo: bf16 plane pairs [2][numel] (pvg_split_16 / pvg_pack_16x2)
     PVG_CHECK_ARG(x_lo && w_lo, "nprod == 2 needs the bf16 plane pairs of x and w");
     PVG_CHECK_ARG((((uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0, "bf16 planes must be 16-byte aligned");
-    if (h3) return dispatch_bn<4>(d, x, x_lo, w, w_lo, bias, y, st);
+    if (h3) {        // all-fp16 split product: conv_h3.cu (PVG_H3_LEGACY=1: the one-tile-per-CTA kernel of this file, A/B knob)
+      static const bool legacy = getenv("PVG_H3_LEGACY") && atoi(getenv("PVG_H3_LEGACY")) == 1;
+      if (!legacy) return conv2d_fwd_h3(d, x_lo, w_lo, bias, y, nullptr, st);
+      return dispatch_bn<4>(d, x, x_lo, w, w_lo, bias, y, st);
+    }
     return dispatch_bn<2>(d, x, x_lo, w, w_lo, bias, y, st);
   }
   return dispatch_bn<1>(d, x, nullptr, w, nullptr, bias, y, st);

@@ -275,5 +275,74 @@ int encode_nhwc_map(CUtensorMap* m, const float* x, int N, int H, int W, int C, 
 int encode_nhwc_16x2_map(CUtensorMap* m, const void* planes, int N, int H, int W, int C, int tw, int th, int tn);
 // 3-D map over the two 16-bit planes [2][rows][K] of a packed weight: box {32, box_rows, 2}, SWIZZLE_64B
 int encode_w_16x2_map(CUtensorMap* m, const void* planes, int rows, int K, int box_rows);
+// the 128-pixel patch (tw, th, tn) that wastes the fewest MMA rows
+void choose_patch(int N, int H, int W, int* tw, int* th, int* tn);
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared by the implicit-GEMM forward kernels (conv_umma.cu, conv_h3.cu)
+// ---------------------------------------------------------------------------------------------------------------
+struct ConvParams {
+  int N, H, W, Cin, Cout, R, S, pad, act;
+  float slope;
+  int tw, th, tn;               // M-tile patch (tw*th*tn == 128)
+  int tiles_w, tiles_h, tiles_n;
+  const float* bias;
+  float* y;
+  int corr_fp16;                // NPROD == 2: the 16-bit correction planes are fp16 (else bf16)
+  uint16_t* y_planes;           // conv_h3.cu, optional: fp16 plane pair [2][N*H*W*Cout] of y (PVG_CORR_FP16_ALL), written by the
+  int64_t y_numel;              //   epilogue so that the next convolution needs no separate split pass; y_numel = N*H*W*Cout
+  int dbg;                      // conv_h3.cu timing experiments
+};
+
+// bias + activation of 16 consecutive output channels and their NHWC store.  Everything that is uniform over the tile (bias
+// pointer, activation kind, Cout bounds) is tested once per 16 channels, not per element: the straightforward per-element
+// form compiled to ~66 instructions per output value and made the final epilogue 30 % of a 72-k-iteration tile (ncu).
+__device__ __forceinline__ void finish16(float (&v)[16], const float* __restrict__ bias, int co, int Cout, int act, float slope,
+                                         float* __restrict__ yrow, bool valid, bool vec_ok) {
+  if (co >= Cout) return;
+  const bool full = co + 16 <= Cout;
+  if (bias != nullptr) {
+    if (full && vec_ok) {                         // Cout % 4 == 0 and 16-byte aligned rows => bias + co is 16-byte aligned too
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = ldg4(bias + co + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (co + j < Cout) v[j] += __ldg(bias + co + j);
+    }
+  }
+  switch (act) {
+    case PVG_ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+      break;
+    case PVG_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case PVG_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+      break;
+    case PVG_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+      break;
+    default: break;
+  }
+  if (!valid) return;
+  if (full && vec_ok) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) stg4(yrow + co + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (co + j < Cout) yrow[co + j] = v[j];
+  }
+}
+
 
 }  // namespace pvg

@@ -75,6 +75,13 @@ case $s in
   persist2_t) PVG_PERSISTENT=1 run persist2_t 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv" -p no:cacheprovider ;;
   persist2_b) PVG_PERSISTENT=1 PVG_2CTA=1 run persist2_b 300 python tools/tile_model.py tf32x3; PVG_PERSISTENT=1 run persist2_lb 300 python tools/layer_bench.py tf32x3 vgg ;;
   corr_diag) run corr_diag 300 python tools/corr_diag.py ;;
+  h3_ab) for rep in 1 2; do PVG_H3_LEGACY=1 PVG_PERSISTENT=0 run h3ab_legacy_$rep 200 python tools/tile_model.py tf32x3; for hp in "0 0" "1 0" "0 1" "1 1"; do set -- $hp; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3ab_$1$2_$rep 200 python tools/tile_model.py tf32x3; done; nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu --format=csv | tee -a $OUT/summary.txt; done ;;
+  h3_ab2) PVG_H3_LEGACY=1 PVG_PERSISTENT=0 run h3ab_legacy 200 python tools/tile_model.py tf32x3; for hpd in "0 0 0" "1 0 0" "1 0 1" "0 1 0" "1 1 0" "1 1 1"; do set -- $hpd; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 PVG_H3_DBG=$3 run h3ab_$1$2$3 200 python tools/tile_model.py tf32x3; done ;;
+  ncu_h3) PVG_H3_HALO=1 PVG_H3_PAIR=0 run ncu_h3_10 400 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 2 -c 1 -f -o $OUT/prof_h3_10 python tools/one_conv.py 120 256 128 64 64; PVG_H3_HALO=1 PVG_H3_PAIR=1 run ncu_h3_11 400 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 2 -c 1 -f -o $OUT/prof_h3_11 python tools/one_conv.py 120 256 128 64 64; PVG_H3_LEGACY=1 PVG_PERSISTENT=0 run ncu_h3_legacy 400 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 2 -c 1 -f -o $OUT/prof_h3_legacy python tools/one_conv.py 120 256 128 64 64 ;;
+  h3_ab3) PVG_H3_LEGACY=1 PVG_PERSISTENT=0 run h3ab_legacy 200 python tools/tile_model.py tf32x3; for hp in "0 0" "1 0" "0 1" "1 1"; do set -- $hp; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3_t_$1$2 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "umma_forward_tf32x3 and h3" -p no:cacheprovider; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3ab_$1$2 200 python tools/tile_model.py tf32x3; done; PVG_H3_HALO=1 PVG_H3_PAIR=1 run h3ab64_11 200 python tools/tile_model.py tf32x3 64; PVG_H3_HALO=1 PVG_H3_PAIR=0 run h3ab64_10 200 python tools/tile_model.py tf32x3 64 ;;
+  h3_ab4) for hpd in "1 0 0" "1 0 1" "0 0 0"; do set -- $hpd; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 PVG_H3_DBG=$3 run h3ab_$1$2$3 200 python tools/tile_model.py tf32x3; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 PVG_H3_DBG=$3 run h3ab64_$1$2$3 200 python tools/tile_model.py tf32x3 64; done ;;
+  ncu_h3b) PVG_H3_HALO=1 PVG_H3_PAIR=0 run ncu_h3b_10 400 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 2 -c 1 -f -o $OUT/prof_h3b_10 python tools/one_conv.py 120 256 64 64 64; PVG_H3_HALO=0 PVG_H3_PAIR=0 run ncu_h3b_00 400 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 2 -c 1 -f -o $OUT/prof_h3b_00 python tools/one_conv.py 120 256 64 64 64 ;;
+  h3_matrix) for hp in "0 0" "1 0" "0 1" "1 1"; do set -- $hp; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3_t_$1$2 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "umma_forward_tf32x3 and h3" -p no:cacheprovider; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3_tm_$1$2 200 python tools/tile_model.py tf32x3; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3_tm64_$1$2 200 python tools/tile_model.py tf32x3 64; done ;;
   t_umma) run t_umma 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
   tm_h3) PVG_2CTA=0 PVG_PERSISTENT=0 run tm_h3 300 python tools/tile_model.py tf32x3; PVG_2CTA=0 PVG_PERSISTENT=0 run tm_h3_64 300 python tools/tile_model.py tf32x3 64; PVG_2CTA=0 PVG_PERSISTENT=0 PVG_CORR=fp16 run tm_fp16 300 python tools/tile_model.py tf32x3 ;;
 esac
