@@ -26,8 +26,13 @@ sys.path.insert(0, ROOT)
 METRIC = "frames/sec (train step, 256x256x3, seq=16)"
 
 WORKLOADS = {
-    # name: (config kind, reduced, H, W, S, B per GPU, T, gt_init)
+    # name: config kind (configs/0N_*.yaml), reduced model?, frame H x W, observation stacking S, sequences per GPU B, frames T,
+    # ground-truth context gt_init.  BASELINE.json configs[1] is the headline; configs[2] (Breakout: 208 x 160 frames, reduced
+    # model, 26 x 20 state maps - BASELINE's "160x160" is a simplification) and configs[3] (Tennis: 96 x 256 frames,
+    # S = 4, batch 32 over 8 GPUs = 4 per GPU) are selectable; configs[0] is the reference's CPU-runnable case.
     "bair256_b8_t16": dict(config="bair", reduced=False, H=256, W=256, S=1, B=8, T=16, gt_init=6),
+    "breakout208x160_b16_t32": dict(config="breakout", reduced=True, H=208, W=160, S=1, B=16, T=32, gt_init=6),
+    "tennis96x256_b4_t16": dict(config="tennis", reduced=False, H=96, W=256, S=4, B=4, T=16, gt_init=6),
     "bair64_b2_t4": dict(config="bair", reduced=False, H=64, W=64, S=1, B=2, T=4, gt_init=3),
 }
 
@@ -44,6 +49,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-frames", type=int, default=8, help="frames (B=1 x T) of the CPU baseline sample")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (rollout) measurements")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true", help="skip the PyTorch-eager + cuDNN leg (same box, same batch)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the pre-run loss check against the CPU oracle")
     return ap.parse_args()
 
 
@@ -52,15 +59,15 @@ def rollout_secondary(dev):
     E -> R -> D per generated frame.  Batch 64 kernel by kernel, batch 1 (play.py's own case) kernel by kernel and with one
     CUDA graph per step.  CUDA events around the timed steps, after 3 warm-up steps."""
     import torch
-    from oracle.cases import build_config
     from playablevideogeneration_b200.caddy import Model
+    from playablevideogeneration_b200.configs import build_config
     cfg = build_config(dict(config="bair", H=256, W=256, S=1))
     torch.manual_seed(0)
     model = Model(cfg).to(dev).eval()
     g = torch.Generator().manual_seed(0)
     out = {}
     with torch.no_grad():
-        for batch, graphed, steps in ((64, False, 20), (1, False, 50), (1, True, 50)):
+        for batch, graphed, steps in ((64, False, 100), (1, False, 50), (1, True, 50)):      # configs[4]: batch 64, 100 steps
             model.enable_graphed_inference(graphed)
             obs = (torch.rand((batch, 3, 256, 256), generator=g) * 2 - 1).to(dev)
             actions = torch.randint(0, 7, (steps + 3, batch), generator=g).to(dev)
@@ -132,30 +139,151 @@ def synthetic_batch(w, seed=0):
             torch.zeros((w["B"], w["T"]), dtype=torch.bool))
 
 
-def _best_thread_count():
-    """torch's CPU convolutions do not scale to every core of a 128-core host (the full-width run is slower than 16
-    threads), so the CPU arm uses the thread count that is fastest on a representative conv fwd+bwd."""
+def _cpu_threads():
+    """Threads of the CPU arm: every host core up to 32 (torch's CPU convolutions stop scaling beyond that on the 128-core
+    hosts of this pool).  Fixed, not auto-tuned: round 1's timing-based pick moved the denominator by 35 % between boxes."""
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+def _mi_alpha(cfg):
+    """EMA factor of the smooth mutual-information estimator (training/smooth_mi_trainer.py); None for the plain trainer."""
+    return cfg["training"]["mutual_information_estimation_alpha"] if "smooth" in cfg["training"]["trainer"] else None
+
+
+def gpu_eager_baseline(w, dev, steps=3, warmup=2):
+    """The bar of SURVEY.md 8(d) / BASELINE.md 3.4: the reference ALGORITHM as plain PyTorch eager ops (F.conv2d -> cuDNN,
+    F.batch_norm, autograd, the trainer's loss sum, Adam) on the same B200, same batch, ``cudnn.benchmark = True`` as train.py:19
+    sets it.  The oracle port stands in for the reference files (they do not travel to the GPU box); it IS the reference's op
+    sequence, pinned op for op by tests/test_oracle_golden.py.  Two numbers: TF32 convolutions allowed (what the reference gets
+    by default on any Ampere+ GPU) and strict fp32 (``allow_tf32 = False``: the precision this repo's fp32-equivalent split
+    product delivers).  Reported next to ``cpu_baseline``; nothing on the product path touches it."""
     import torch
-    import torch.nn.functional as F
-    total = os.cpu_count() or 1
-    x = torch.randn(4, 128, 64, 64, requires_grad=True)
-    wt = torch.randn(128, 128, 3, 3, requires_grad=True)
-    best, best_t = 1, float("inf")
-    n = 1
-    cands = []
-    while n < total:
-        cands.append(n); n *= 2
-    cands.append(total)
-    for n in cands:
-        torch.set_num_threads(n)
-        F.conv2d(x, wt, padding=1).sum().backward()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            F.conv2d(x, wt, padding=1).sum().backward()
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
-    return best
+    from oracle import caddy_oracle as O
+    from playablevideogeneration_b200.configs import build_config
+    cfg = build_config(dict(config=w["config"], H=w["H"], W=w["W"], S=w["S"]))
+    sd = O.make_weights(cfg, 0, w["reduced"])
+    vgg_sd = {k: v.to(dev) for k, v in O.make_vgg_weights().items()}
+    bt = tuple(t.to(dev) for t in synthetic_batch(w))
+    out = dict(kind="port (oracle/caddy_oracle.py on cuda: PyTorch eager + cuDNN, cudnn.benchmark=True)", batch=w["B"], seq_len=w["T"],
+               steps=steps, warmup=warmup)
+    prev = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for label, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            params = {k: (v.to(dev).requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))
+                          and "centroid" not in k else v.to(dev)) for k, v in sd.items()}
+            train = [v for v in params.values() if v.requires_grad]
+            m = [torch.zeros_like(p) for p in train]
+            v2 = [torch.zeros_like(p) for p in train]
+            mi = O.MutualInformation(cfg["data"]["actions_count"], _mi_alpha(cfg))
+            mi.matrix = mi.matrix.to(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            loss = None
+            with torch.device(dev):                   # the oracle draws its noise with bare torch.randn / torch.rand
+                for it in range(warmup + steps):
+                    if it == warmup:
+                        torch.cuda.synchronize(dev)
+                        e0.record()
+                    total, _, _ = O.compute_losses(params, vgg_sd, cfg, mi, bt, w["gt_init"], 1.0)
+                    for p in train:
+                        p.grad = None
+                    total.backward()
+                    with torch.no_grad():
+                        live = [(p, p.grad, a, b) for p, a, b in zip(train, m, v2) if p.grad is not None]
+                        O.adam_step([x[0] for x in live], [x[1] for x in live], [x[2] for x in live], [x[3] for x in live], it + 1, 4e-4, 1e-6)
+                    loss = total.detach()
+                e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[label] = dict(ms_per_step=ms, frames_per_s=w["B"] * w["T"] / (ms * 1e-3), last_loss=float(loss.cpu()[0]))
+            del params, train, m, v2, total, loss
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
+def parity_check(w, cfg, model, step, vgg, dev):
+    """Before anything is timed: one forward + losses of THIS model on a B=1, T=4 slice of the bench batch at the bench's frame
+    size, through the CUDA path and through the fp32 CPU oracle with the same weights, inputs and noise seeds.  The bench line
+    carries both losses; a relative difference above the contract's 1e-5 fails the run."""
+    import random
+    import torch
+    from oracle import caddy_oracle as O
+    t = min(4, w["T"])
+    bt = synthetic_batch(dict(w, B=1, T=t), seed=7)
+    gt = min(2, t - 1)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    vgg_sd = {f"features.{i}.{n}": getattr(vgg.convs[str(i)], n).detach().cpu().clone() for i in vgg.convs for n in ("weight", "bias")}
+    mi = O.MutualInformation(cfg["data"]["actions_count"], _mi_alpha(cfg))
+    mil = step.mutual_information_loss
+    mil_sd = {k: v.detach().clone() for k, v in mil.state_dict().items()} if hasattr(mil, "state_dict") else None
+    torch.set_num_threads(_cpu_threads())
+    torch.manual_seed(11); random.seed(11)
+    with torch.no_grad():
+        ref_total, _, _ = O.compute_losses(sd, vgg_sd, cfg, mi, bt, gt, 1.0)
+    model.train()
+    torch.manual_seed(11); random.seed(11)
+    with torch.no_grad():
+        total, _, _ = step.compute_losses(tuple(x.to(dev) for x in bt), gt, 1.0)
+    got, ref = float(total.cpu()[0]), float(ref_total[0])
+    # the check ran a train-mode forward: put the BatchNorm / EMA state back so the timed run starts from the seeded model
+    model.load_state_dict({k: v.to(dev) for k, v in sd.items()})
+    if mil_sd is not None:
+        step.mutual_information_loss.load_state_dict(mil_sd)
+    from playablevideogeneration_b200 import ops
+    ops.invalidate_weight_cache()
+    return dict(sample=f"B=1 x T={t} of {w['H']}x{w['W']}, gt_init={gt}, this model's weights", cuda_loss=got, oracle_fp32_loss=ref,
+                rel_err=abs(got - ref) / abs(ref), tolerance=1e-5)
+
+
+# algorithmic HBM bytes of the bandwidth-bound entry points (fp32 NHWC tensors read / written once per launch), from their
+# C-ABI arguments (include/pvg_b200.h); the classes bench.py reports under "roofline_hbm"
+def _hbm_bytes(name, a):
+    f = 4
+    if name == "pvg_bn_stats":                       # x, N, HW, C
+        return "bn_stats", a[1] * a[2] * a[3] * f
+    if name == "pvg_pool2_stats":                    # x, N, H, W, C, y: read x, write y / 4
+        return "bn_stats", a[1] * a[2] * a[3] * a[4] * f * 1.25
+    if name == "pvg_bn_finalize_apply":              # x, N, HW, C, ..., residual at 15
+        return "bn_apply", a[1] * a[2] * a[3] * f * (3 if a[15] else 2)
+    if name == "pvg_bn_apply":                       # x, N, HW, C, groups, mean, invstd, w, b, residual
+        return "bn_apply", a[1] * a[2] * a[3] * f * (3 if a[9] else 2)
+    if name == "pvg_bn_bwd_reduce":                  # dy, y, x, N, HW, C, ..., act at 9
+        return "bn_bwd", a[3] * a[4] * a[5] * f * (3 if a[9] else 2)
+    if name == "pvg_bn_bwd_apply":                   # dy, y, x, N, H, W, C, groups, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out
+        full = a[3] * a[4] * a[5] * a[6] * f
+        small = full / 4 if a[15] else full
+        return "bn_bwd", small * (3 if a[11] else 2) + full + (small if a[17] else 0)
+    if name == "pvg_split_16":                       # x, planes, n
+        return "split_16", a[2] * 8
+    if name == "pvg_act_bwd_split_16":               # dy, y, act, slope, g, planes, n
+        return "split_16", a[6] * 16
+    if name == "pvg_act_bwd":
+        return "split_16", a[5] * 12
+    if name == "pvg_absdiff_mean_fwd":               # a, b, N, count
+        return "absdiff", a[2] * a[3] * 8
+    if name == "pvg_absdiff_mean_bwd":               # a, b, gout, N, count, db
+        return "absdiff", a[3] * a[4] * 12
+    if name == "pvg_upsample2x_fwd":                 # x, N, H, W, C
+        return "resample", a[1] * a[2] * a[3] * a[4] * f * 5
+    if name == "pvg_upsample2x_bwd":
+        return "resample", a[1] * a[2] * a[3] * a[4] * f * 5
+    if name == "pvg_resize_bilinear":                # x, N, H, W, C, y, OH, OW
+        return "resample", a[1] * a[4] * f * (a[2] * a[3] + a[6] * a[7])
+    if name == "pvg_maxpool2_fwd":
+        return "maxpool", a[1] * a[2] * a[3] * a[4] * f * 1.25
+    if name == "pvg_maxpool2_bwd":                   # dy, x, y, N, H, W, C
+        return "maxpool", a[3] * a[4] * a[5] * a[6] * f * 2.5
+    if name == "pvg_lstm_fwd":                       # gates, c_prev, M, C
+        return "lstm_pointwise", a[2] * a[3] * 28
+    if name == "pvg_lstm_bwd":                       # gates, c_prev, c_new, dh, dc, M, C
+        return "lstm_pointwise", a[5] * a[6] * 52
+    if name in ("pvg_adam_step", "pvg_adam_step_dev"):
+        return "adam", a[4] * 28
+    return None, 0
 
 
 def cpu_reference_step_time(w, frames, steps, warmup):
@@ -163,8 +291,8 @@ def cpu_reference_step_time(w, frames, steps, warmup):
     all host cores: forward + all losses + backward + Adam on a B=1 slice of the workload."""
     import torch
     from oracle import caddy_oracle as O
-    from oracle.cases import build_config
-    cores = _best_thread_count()
+    from playablevideogeneration_b200.configs import build_config
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     cfg = build_config(dict(config=w["config"], H=w["H"], W=w["W"], S=w["S"]))
     t = max(3, min(w["T"], frames))
@@ -175,7 +303,7 @@ def cpu_reference_step_time(w, frames, steps, warmup):
     m = [torch.zeros_like(p) for p in train]
     v2 = [torch.zeros_like(p) for p in train]
     vgg_sd = O.make_vgg_weights()
-    mi = O.MutualInformation(cfg["data"]["actions_count"], cfg["training"]["mutual_information_estimation_alpha"])
+    mi = O.MutualInformation(cfg["data"]["actions_count"], _mi_alpha(cfg))
     bt = synthetic_batch(dict(w, B=1, T=t))
     times = []
     for s in range(warmup + steps):
@@ -193,7 +321,7 @@ def cpu_reference_step_time(w, frames, steps, warmup):
     mean = sum(times) / len(times)
     return dict(value=t / mean, unit="frames/s", cores=cores, kind="port",
                 sample=f"B=1 x T={t} of {w['H']}x{w['W']} (one sequence of the batch), {len(times)} timed step(s), "
-                       f"{mean:.2f} s/step, torch CPU fp32, {cores} threads (fastest of 1..{os.cpu_count()} on a conv microbenchmark)"), mean
+                       f"{mean:.2f} s/step, torch CPU fp32, {cores} threads of {os.cpu_count()} host cores"), mean
 
 
 def run_reference(args, w):
@@ -231,8 +359,8 @@ def main():
     import torch.distributed as dist
     import __graft_entry__ as ge
     ge.build()
-    from oracle.cases import build_config            # config dict only (plain data; no oracle compute on this path)
     from playablevideogeneration_b200 import _lib, ops
+    from playablevideogeneration_b200.configs import build_config
     from playablevideogeneration_b200.caddy import Model
     from playablevideogeneration_b200.training.step import GraphedTrainStep, TrainStep
     from playablevideogeneration_b200.vgg import Vgg19
@@ -251,7 +379,7 @@ def main():
     cfg = build_config(dict(config=w["config"], H=w["H"], W=w["W"], S=w["S"]))
     torch.manual_seed(0); random.seed(0)
     model = Model(cfg, reduced=w["reduced"]).to(dev)
-    vgg = Vgg19()
+    vgg = Vgg19(allow_random_init=True)               # no network for the ImageNet checkpoint: seeded He-init weights, timing only
     g = torch.Generator().manual_seed(1234)
     with torch.no_grad():                                # He-init stand-in for the ImageNet weights (no network)
         for conv in vgg.convs.values():
@@ -262,6 +390,11 @@ def main():
     host = tuple(t.pin_memory() for t in host)
     resident = tuple(t.to(dev) for t in host)
     frames_per_step = w["B"] * w["T"] * world
+    parity = None
+    if world == 1 and not args.no_parity_check and args.precision == "tf32x3":
+        parity = parity_check(w, cfg, model, step, vgg, dev)
+        if parity["rel_err"] > parity["tolerance"]:
+            raise SystemExit(f"bench.py: the CUDA path disagrees with the CPU oracle before timing: {parity}")
     torch.manual_seed(100 + rank); random.seed(100 + rank)
 
     def barrier():
@@ -312,12 +445,33 @@ def main():
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3) / args.steps)
-    # ---- one more step launched kernel by kernel with CUDA events around every tensor-core conv / wgrad launch: the
-    #      per-kernel durations behind `roofline` (events cannot be timed inside a graph replay); also counts launches ----
+    # ---- one more step launched kernel by kernel with CUDA events around EVERY C-ABI call: the per-kernel durations behind
+    #      `roofline` (tensor-core convs, from their algorithmic FLOPs) and `roofline_hbm` (bandwidth-bound kernel classes,
+    #      from their algorithmic bytes); events cannot be timed inside a graph replay.  Also counts launches. ----------------
     ops.conv_profile, ops.wgrad_profile = [], []
+    hbm_events = []
+    orig_call = _lib.call
+
+    def timed_call(name, *cargs):
+        cls, nbytes = _hbm_bytes(name, cargs)
+        if cls is None:
+            return orig_call(name, *cargs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = orig_call(name, *cargs)
+        b.record()
+        hbm_events.append((cls, a, b, float(nbytes)))
+        return rc
+
+    _lib.call = ops.call = timed_call
+    from playablevideogeneration_b200.training import losses as _losses_mod
+    _losses_mod.ops.call = timed_call
     launches0 = _lib.launch_count
     torch.cuda._sleep(int(2.5e9))      # ~1.3 s of GPU spin: lets the host run ahead so that events bracket pure kernel time
-    step.step(resident, w["gt_init"], 1.0)
+    try:
+        step.step(resident, w["gt_init"], 1.0)
+    finally:
+        _lib.call = ops.call = orig_call
     barrier()
     launches = (_lib.launch_count - launches0) * args.steps
     prof, ops.conv_profile = ops.conv_profile, None
@@ -325,31 +479,54 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(t.numel() * t.element_size() for t in host)
 
-    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv) from CUDA events recorded around its launches --
+    # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convs) from CUDA events recorded around its launches,
+    #      per family: conv_h3_kernel (forward, all-fp16 split) and conv_umma*_kernel (data gradient, TF32 main + bf16 corrections)
     peaks = load_peaks()
     roof = None
+    roof_hbm = None
     if prof:
-        tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-        flops = sum(f for _, _, f in prof)
-        ach = flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        fams = {}
+        for a_, b_, f_, kind in prof:
+            e = fams.setdefault(kind, [0, 0.0, 0.0])
+            e[0] += 1; e[1] += a_.elapsed_time(b_); e[2] += f_
+        names = {"h3": "conv_h3_kernel (forward convs: 3 kind::f16 tcgen05 MMAs per product on fp16 plane pairs, halo-reuse, persistent)",
+                 "tf32": "conv_umma_persistent / conv_umma2_persistent (data gradients: kind::tf32 main product + 2 bf16 corrections)",
+                 "single": "conv_umma_kernel (single TF32 product)"}
+        ceil_note = {"h3": "3 f16 MMAs per product: ceiling 1/3 of the bf16 peak", "tf32": "1 TF32 + 2 16-bit MMAs per product (2 TF32 MMA times): ceiling 1/4 of the bf16 peak",
+                     "single": "TF32: ceiling 1/2 of the bf16 peak"}
+        ceil_frac = {"h3": 1.0 / 3.0, "tf32": 0.25, "single": 0.5}
+        tpath = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
+        tdata = json.load(open(tpath)) if (args.precision == "tf32x3" and args.workload == "bair256_b8_t16" and os.path.isfile(tpath)) else {}
+        fam_rows = []
+        for kind, (n_, ms_, fl_) in sorted(fams.items(), key=lambda kv: -kv[1][1]):
+            ach = fl_ / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
+            fam_rows.append(dict(bound="tensor", kernel=names.get(kind, kind), achieved=ach, peak=peaks["tflops"], unit="TFLOP/s",
+                                 frac=ach / peaks["tflops"], frac_of_arithmetic_ceiling=ach / (peaks["tflops"] * ceil_frac.get(kind, 1.0)),
+                                 ceiling=ceil_note.get(kind), traffic=tdata.get(kind, {}).get("traffic_bytes_per_launch"),
+                                 launches_per_step=n_, avg_launch_us=ms_ * 1e3 / n_, ms_per_step=ms_, share_of_step=ms_ / ms_dev))
         wg = None
         if wprof:
-            wms = sum(a.elapsed_time(b) for a, b, _ in wprof)
-            wg = dict(kernel="conv_wgrad_umma_kernel", launches_per_step=len(wprof), ms_per_step=wms,
-                      achieved=sum(f for _, _, f in wprof) / (wms * 1e-3) / 1e12 if wms > 0 else 0.0, unit="TFLOP/s")
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-        if args.precision == "tf32x3" and args.workload == "bair256_b8_t16" and os.path.isfile(tpath):
-            traffic = json.load(open(tpath))["traffic_bytes_per_launch"]      # from the committed ncu capture of this command
-        roof = dict(bound="tensor", kernel="conv_umma_kernel (tcgen05 kind::tf32" + (" main product + 2 correction products: " + json.dumps(ops._corr) if args.precision == "tf32x3" else "") + ")",
-                    achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=traffic,
-                    traffic_source="profiles/r01_conv_traffic.json (ncu dram__bytes_read+write per launch, averaged over the step's launches)" if traffic else None,
-                    launches_per_step=len(prof), avg_launch_us=tot_ms * 1e3 / len(prof), ms_per_step=tot_ms,
-                    share_of_step=tot_ms / ms_dev, peak_source=peaks["source"], weight_gradient=wg,
+            wms = sum(a_.elapsed_time(b_) for a_, b_, _ in wprof)
+            wfl = sum(f_ for _, _, f_ in wprof)
+            wg = dict(bound="tensor", kernel="conv_wgrad_umma_kernel (weight gradients: MN-major kind::tf32 + 2 bf16 corrections, split-K)",
+                      launches_per_step=len(wprof), ms_per_step=wms, achieved=wfl / (wms * 1e-3) / 1e12 if wms > 0 else 0.0,
+                      peak=peaks["tflops"], unit="TFLOP/s", frac=(wfl / (wms * 1e-3) / 1e12 / peaks["tflops"]) if wms > 0 else 0.0,
+                      traffic=tdata.get("wgrad", {}).get("traffic_bytes_per_launch"), share_of_step=wms / ms_dev)
+        roof = dict(fam_rows[0])
+        roof.update(peak_source=peaks["source"], other_tensor_kernels=fam_rows[1:], weight_gradient=wg,
+                    traffic_source="profiles/r02_conv_traffic.json (ncu dram__bytes_read+write per launch, averaged over the step's launches of the family)" if roof.get("traffic") else None,
                     measured="CUDA events around each launch in one extra eager (non-graph) step after the timed region",
-                    note="achieved = algorithmic conv FLOPs (2*N*H*W*Cout*R*S*Cin, unpadded) / CUDA-event time of the launches; "
-                         "peak is the measured bf16 cuBLAS figure - kind::tf32 tops out at half of it; the fp32-equivalent split costs "
-                         "1 TF32 + 2 16-bit MMAs (= 2 TF32 MMA times) per product, i.e. a ceiling of a quarter of the peak")
+                    note="achieved = algorithmic conv FLOPs (2*N*H*W*Cout*R*S*Cin, unpadded) / CUDA-event time of the family's launches; "
+                         "peak is the measured bf16 cuBLAS figure; fp32-equivalent results need 3 tensor-core products per multiply")
+    if hbm_events:
+        cls = {}
+        for c_, a_, b_, nb in hbm_events:
+            e = cls.setdefault(c_, [0, 0.0, 0.0])
+            e[0] += 1; e[1] += a_.elapsed_time(b_); e[2] += nb
+        roof_hbm = [dict(kernel_class=c_, bound="hbm", launches_per_step=n_, bytes_per_step=nb, ms_per_step=ms_,
+                         achieved=nb / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0, peak=peaks["hbm_gbs"], unit="GB/s",
+                         frac=(nb / (ms_ * 1e-3) / 1e9 / peaks["hbm_gbs"]) if ms_ > 0 else 0.0, share_of_step=ms_ / ms_dev)
+                    for c_, (n_, ms_, nb) in sorted(cls.items(), key=lambda kv: -kv[1][1])]
     if rank != 0:
         _hard_exit(world)
         return
@@ -368,13 +545,29 @@ def main():
                             l2="inputs (100.7 MB/step) and per-step activations (>10 GB) exceed the 126 MB L2; no explicit flush"),
                 e2e=dict(value=frames_per_step / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d * world,
                          d2h_bytes_per_step=8 * world, ms_per_step=ms_e2e, last_loss=loss_host),
-                gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu_base)
+                gpu_launches=launches, clocks=clocks, roofline=roof, roofline_hbm=roof_hbm, cpu_baseline=cpu_base,
+                parity_check=parity)
     if world == 1 and not args.no_secondary:
         # after every headline number is final: a failure here cannot touch them
         try:
             line["secondary"] = rollout_secondary(dev)
         except BaseException as e:          # noqa: BLE001 - report, never lose the headline line
             line["secondary"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if world == 1 and not args.no_gpu_eager_baseline:
+        # last: frees this implementation's graph and buffers first; a failure cannot touch the numbers above
+        try:
+            del gstep
+        except NameError:
+            pass
+        try:
+            del step, model, resident
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(w, dev)
+            for k in ("tf32", "fp32"):
+                if k in line["gpu_eager_baseline"]:
+                    line["gpu_eager_baseline"][k]["this_repo_speedup"] = line["gpu_eager_baseline"][k]["ms_per_step"] / ms_dev
+        except BaseException as e:          # noqa: BLE001
+            line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(line), flush=True)
     _hard_exit(world)
 

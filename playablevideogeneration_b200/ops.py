@@ -289,7 +289,7 @@ def tf32_truncates() -> bool:
     return _tf32_truncates
 
 
-conv_profile = None     # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per tensor-core conv launch
+conv_profile = None     # bench.py sets this to a list: (start_event, end_event, algorithmic_flops, kernel family) per tensor-core conv launch
 
 
 def _run_conv(x, x_lo, w, w_lo, bias, y, ksize, pad, act, slope, algo, nprod, fmt, alg_flops=0.0):
@@ -302,7 +302,8 @@ def _run_conv(x, x_lo, w, w_lo, bias, y, ksize, pad, act, slope, algo, nprod, fm
     call("pvg_conv2d_fwd", d, x.data_ptr(), _p(x_lo), w.data_ptr(), _p(w_lo), _p(bias), y.data_ptr(), _stream())
     if prof:
         e1.record()
-        conv_profile.append((e0, e1, alg_flops))
+        kind = "single" if nprod == 1 else ("h3" if (nprod == 2 and fmt == _lib.CORR_FP16_ALL) else "tf32")
+        conv_profile.append((e0, e1, alg_flops, kind))
 
 
 def _split(x: Tensor, nprod: int = 3, fmt: int = 0) -> Tuple[Tensor, Tensor]:

@@ -61,6 +61,10 @@ class TrainStep:
         self.model = model
         self.module = model.module if hasattr(model, "module") else model
         tr = config["training"]
+        if tr.get("use_motion_weights", False):
+            # trainer.py:436-440 builds a motion weight mask; the reference's own weighted branch is broken (losses.py:105) and no
+            # shipped config enables it - refuse rather than train silently without the mask
+            raise NotImplementedError("training.use_motion_weights is not supported on the pvg_b200 hot path")
         dev = next(self.module.parameters()).device
         self.vgg = (vgg if vgg is not None else Vgg19()).to(dev)
         self.perceptual_loss = L.ParallelPerceptualLoss(self.vgg)
@@ -93,7 +97,10 @@ class TrainStep:
         self._graph_runs = []
         self._hyper_dev_buf = torch.zeros((16, 7), dtype=torch.float32, device=dev)
         self._hyper_dev = self._hyper_dev_buf
-        self._hyper_host = torch.zeros((16, 7), dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros((16, 7))
+        self._hyper_host = [torch.zeros((16, 7), dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros((16, 7))
+                            for _ in range(4)]
+        self._hyper_events = [None] * len(self._hyper_host)
+        self._hyper_slot = 0
 
     # ----------------------------------------------------------------------------------------------------------
     def current_lr(self) -> float:
@@ -126,9 +133,11 @@ class TrainStep:
         lam_p = lw["perceptual_loss_lambda" + sfx]
         for r, cur in enumerate(pyr):
             p_tot, p_levels = self.perceptual_loss(observations, cur)
+            # Trainer.sum_loss_components (trainer.py:167-186): one weight per VGG level, or a scalar broadcast to all of them
+            lams = list(lam_p) if isinstance(lam_p, (list, tuple)) else [lam_p] * len(p_levels)
             term = p_levels[0] * 0.0
-            for lv in p_levels:
-                term = term + lv * lam_p
+            for lv, lam in zip(p_levels, lams):
+                term = term + lv * lam
             o = self.observations_loss(observations, cur)
             perceptual = perceptual + p_tot
             perceptual_term = perceptual_term + term
@@ -189,10 +198,9 @@ class TrainStep:
             i = j + 1
         return runs
 
-    def _hyper(self, step: int):
+    def _hyper(self, step: int, lr: float):
         b1, b2 = 0.9, 0.999
-        return [self.current_lr() / (1.0 - b1 ** step), math.sqrt(1.0 - b2 ** step), b1, b2, 1e-8, self.weight_decay,
-                1.0 / self.world]
+        return [lr / (1.0 - b1 ** step), math.sqrt(1.0 - b2 ** step), b1, b2, 1e-8, self.weight_decay, 1.0 / self.world]
 
     def optimizer_step(self):
         if self.pg is not None and self.world > 1:
@@ -205,8 +213,10 @@ class TrainStep:
             for k, (i, j, lo, hi) in enumerate(self._graph_runs):
                 ops.adam_step_dev(a.flat[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], self._hyper_dev[k])
             return
-        self.global_step += 1
+        # the reference runs optimizer.step() and THEN lr_scheduler.step() (trainer.py:586-587): step s uses the rate after s - 1
+        # scheduler ticks, i.e. the one current before the counter moves
         lr = self.current_lr()
+        self.global_step += 1
         for i, j, lo, hi in self._adam_runs():
             for k in range(i, j + 1):
                 a.steps[k] += 1
@@ -216,15 +226,27 @@ class TrainStep:
 
     def prepare_replay(self):
         """Host work before a graph replay: advance the step counters and upload the Adam scalars of every run."""
+        lr = self.current_lr()               # rate of THIS step (before the scheduler tick, see optimizer_step)
         self.global_step += 1
         a = self.arena
         rows = []
         for i, j, lo, hi in self._graph_runs:
             for k in range(i, j + 1):
                 a.steps[k] += 1
-            rows.append(self._hyper(a.steps[i]))
-        self._hyper_host[:len(rows)].copy_(torch.tensor(rows, dtype=torch.float32))
-        self._hyper_dev.copy_(self._hyper_host[:len(rows)], non_blocking=True)
+            rows.append(self._hyper(a.steps[i], lr))
+        # pinned staging rows are a ring: the asynchronous upload of step k may still be queued behind a 250 ms replay when the
+        # host prepares step k + 1, so a row is rewritten only after the copy that read it has completed
+        slot = self._hyper_slot
+        self._hyper_slot = (slot + 1) % len(self._hyper_host)
+        if self._hyper_events[slot] is not None:
+            self._hyper_events[slot].synchronize()
+        host = self._hyper_host[slot]
+        host[:len(rows)].copy_(torch.tensor(rows, dtype=torch.float32))
+        self._hyper_dev.copy_(host[:len(rows)], non_blocking=True)
+        if host.is_pinned():
+            ev = torch.cuda.Event()
+            ev.record()
+            self._hyper_events[slot] = ev
 
     # ---- checkpoint interoperability: the reference's latest.pth.tar (training/trainer.py:80-122, ------------------
     #      training/smooth_mi_trainer.py:23-68) = {"model", "optimizer", "lr_scheduler", "step"[, "mi_estimator"]} ----------
@@ -323,6 +345,10 @@ class GraphedTrainStep:
     """The whole optimiser step (forward, losses, backward, all-reduce, Adam) captured once in a CUDA graph and replayed:
     ~5 000 kernel launches per step are submitted by ONE cudaGraphLaunch instead of by the Python interpreter.
 
+    The eager warm-up steps and the capture itself are REAL optimiser steps on ``example_batch`` (parameters, Adam moments and
+    ``global_step`` advance ``warmup`` times; the capture pass records launches only): build the graph with the first batch
+    of the run, or snapshot / restore ``TrainStep.state_dict()`` around the constructor.
+
     Per replay the host only (1) copies the batch into the static input buffers, (2) redraws the step's random numbers
     on the CPU generator in the reference's order and uploads them (NoiseSource.refill), (3) uploads Adam's bias
     corrections / learning rate.  Shapes, ``ground_truth_observations_count`` and the Gumbel temperature are fixed per
@@ -352,6 +378,10 @@ class GraphedTrainStep:
                 self.static_total, self.static_info = step.step(self.static_batch, *self.args)
         finally:
             step._capturing = False
+            # the static buffers are only needed while the launches are recorded; ``refill`` keeps uploading into them.  Outside
+            # a replay the model draws on the CPU generator again (an eager validation forward must not read a training
+            # step's frozen noise)
+            noise.mode = "cpu"
 
     def __call__(self, batch=None):
         if batch is not None:
@@ -360,4 +390,7 @@ class GraphedTrainStep:
         self.step.module.noise.refill()
         self.step.prepare_replay()
         self.graph.replay()
+        # The replay re-packed the weights it USED (W_k) into its own pack buffers and then Adam wrote W_{k+1}: anything that
+        # runs outside the graph afterwards (validation, generate_next, an eager tail step) must re-pack from the arena.
+        ops.invalidate_weight_cache()
         return self.static_total, self.static_info

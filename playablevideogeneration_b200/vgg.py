@@ -16,10 +16,14 @@ TAPS = (0, 5, 10, 19, 28)                                        # relu1_1, relu
 
 
 class Vgg19(nn.Module):
-    """``features_state_dict``: torchvision-style ``features.<idx>.{weight,bias}`` tensors (ImageNet weights when the
-    caller has them; the reference downloads them, vgg.py:16 - there is no network here)."""
+    """``features_state_dict``: torchvision-style ``features.<idx>.{weight,bias}`` tensors.  The reference always loads the
+    ImageNet weights (``models.vgg19(pretrained=True)``, vgg.py:16); without a state dict this class looks for the same
+    checkpoint in the local torch hub cache and RAISES when it is not there - a randomly initialised feature extractor is
+    only built on request (``allow_random_init=True``: benchmarks and parity tests that inject seeded weights afterwards)."""
 
-    def __init__(self, features_state_dict: Optional[Dict[str, torch.Tensor]] = None):
+    HUB_FILES = ("vgg19-dcbb9e9d.pth",)
+
+    def __init__(self, features_state_dict: Optional[Dict[str, torch.Tensor]] = None, allow_random_init: bool = False):
         super().__init__()
         self.convs = nn.ModuleDict()
         cin = 3
@@ -30,10 +34,29 @@ class Vgg19(nn.Module):
             idx = next(it)
             self.convs[str(idx)] = nn.Conv2d(cin, v, 3, padding=1)
             cin = v
+        if features_state_dict is None and not allow_random_init:
+            features_state_dict = self._cached_imagenet_weights()
+            if features_state_dict is None:
+                raise RuntimeError("Vgg19() needs the torchvision ImageNet weights (features.<idx>.weight/bias): pass "
+                                   "features_state_dict, place vgg19-dcbb9e9d.pth in the torch hub cache, or pass "
+                                   "allow_random_init=True for a benchmark / test with injected weights")
         if features_state_dict is not None:
             self.load_features(features_state_dict)
         for p in self.parameters():
             p.requires_grad = False
+
+    @classmethod
+    def _cached_imagenet_weights(cls) -> Optional[Dict[str, torch.Tensor]]:
+        import os
+        try:
+            hub = torch.hub.get_dir()
+        except Exception:
+            return None
+        for name in cls.HUB_FILES:
+            path = os.path.join(hub, "checkpoints", name)
+            if os.path.isfile(path):
+                return torch.load(path, map_location="cpu")
+        return None
 
     def load_features(self, sd: Dict[str, torch.Tensor]) -> None:
         with torch.no_grad():

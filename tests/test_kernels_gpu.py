@@ -79,7 +79,12 @@ CONV_UMMA_SHAPES = [  # N, Cin_logical, Cin_physical, Cout, H, W, k, bias, act
     (2, 64, 64, 64, 26, 20, 3, True, 2), (1, 128, 128, 3, 16, 16, 3, True, 3), (8, 256, 256, 256, 4, 4, 3, False, 0),
     (1, 64, 64, 64, 128, 128, 3, True, 2), (2, 521, 544, 1024, 16, 16, 3, True, 0),
     # channel counts that are not a multiple of 32: the K loop is completed by TMA out-of-bounds zero fill
-    (2, 16, 16, 16, 20, 24, 3, False, 0), (1, 16, 16, 32, 16, 16, 1, True, 0), (2, 40, 40, 48, 12, 12, 3, False, 2)]
+    (2, 16, 16, 16, 20, 24, 3, False, 0), (1, 16, 16, 32, 16, 16, 1, True, 0), (2, 40, 40, 48, 12, 12, 3, False, 2),
+    # the shapes bench.py times: 256x256 maps (61 440-tile VGG conv1_2 family, 64 -> 32 decoder layer), the 13x10 / 6x16 state
+    # maps of full-size Breakout / Tennis, batches of >= 64 frames, the N = 4C ConvLSTM gate conv
+    (2, 64, 64, 64, 256, 256, 3, True, 2), (2, 64, 64, 32, 256, 256, 3, False, 0), (64, 64, 64, 128, 13, 10, 3, False, 0),
+    (64, 128, 128, 128, 6, 16, 3, True, 0), (96, 32, 32, 32, 26, 20, 3, False, 0), (128, 16, 16, 16, 48, 128, 3, False, 0),
+    (8, 265, 288, 512, 32, 32, 3, True, 0), (120, 256, 256, 256, 16, 16, 3, True, 2)]
 
 
 def _conv_ref64(x, wt, b, k):
@@ -167,7 +172,10 @@ def test_conv_umma_forward_tf32(shape):
                                    (2, 3, 3, 16, 37, 45, 3, True, 0), (1, 12, 12, 16, 12, 36, 3, False, 0),
                                    (1, 3, 3, 64, 20, 20, 3, False, 0),
                                    (8, 64, 64, 32, 64, 64, 3, False, 0), (3, 64, 64, 128, 26, 20, 3, True, 0),
-                                   (2, 96, 96, 16, 16, 16, 1, False, 0), (2, 256, 256, 132, 8, 8, 3, False, 0)])
+                                   (2, 96, 96, 16, 16, 16, 1, False, 0), (2, 256, 256, 132, 8, 8, 3, False, 0),
+                                   # timed shapes: 256x256 decoder layer, full-size Breakout / Tennis state maps, N >= 64
+                                   (2, 64, 64, 32, 256, 256, 3, False, 0), (64, 64, 64, 128, 13, 10, 3, False, 0),
+                                   (64, 128, 128, 128, 6, 16, 3, True, 0), (96, 32, 32, 32, 26, 20, 3, False, 0)])
 def test_conv_backward(shape, corr):
     """dx (tensor-core dgrad with flipped packed weights or SIMT), dw (split-K wgrad), db vs torch autograd on CPU."""
     _conv_backward_case(shape, corr)
