@@ -81,7 +81,14 @@ int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo, con
  * y_planes (optional, Cout % 8 == 0): fp16 [2][N*H*W*Cout], the plane pair of y, written by the epilogue so that the next
  * convolution needs no separate split pass (vgg.py:48-52 conv -> relu -> conv chains, residual_block.py:52-57). */
 int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
-                          void* y_planes, void* stream);
+                          void* y_planes, const float* out_scale, void* stream);
+/* out_scale (optional, one float in DEVICE memory): the accumulator is multiplied by it before bias / activation - the 1 / S of
+ * a scaled gradient operand (pvg_split_16_scaled) when the call computes a data gradient (w_planes = the flipped pack). */
+/* Weight gradient from plane pairs only: x_planes = PVG_CORR_FP16_ALL planes of x [N,H,W,d->Cin] (the forward operand, reused),
+ * g_planes = scaled planes of dY [N,H,W,d->Cout] (d->Cout % 8 == 0), out_scale = its 1 / S.  Three kind::f16 MMAs per product,
+ * MN-major operands, split-K; scratch / dw_oihw / accumulate as for pvg_conv2d_wgrad_umma. */
+int pvg_conv2d_wgrad_planes(const pvg_conv_desc* d, int Cin_logical, const void* x_planes, const void* g_planes,
+                            const float* out_scale, float* scratch, float* dw_oihw, int accumulate, void* stream);
 /* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinK] and data-gradient pack [CinRows][R][S][CoutK] with flipped
  * taps (dgrad = pvg_conv2d_fwd(dy, bwd pack)).  CinRows >= Cin: physical channels of the activation (zero-padded concat
  * buffers); CinK >= CinRows, CoutK >= Cout: K-side channel counts of the consumer (tensor-core kernels: rounded up to 32,
@@ -114,6 +121,16 @@ int pvg_act_bwd(const float* dy, const float* y, int act, float slope, float* g,
 /* the same, also emitting the 3xTF32 planes of g in the same pass (hi may be NULL: truncation mode, see pvg_split_tf32) */
 int pvg_act_bwd_split(const float* dy, const float* y, int act, float slope, float* g, float* hi, float* lo, int64_t n,
                       void* stream);
+/* ---- gradients as SCALED fp16 plane pairs (all-fp16 data / weight gradient kernels): fp16 has no range for raw gradients, so
+ *      the tensor is multiplied by a power of two S with max|g| * S in [2^13, 2^14) before the PVG_CORR_FP16_ALL split; the
+ *      consuming kernel multiplies its result by 1 / S (inv_scale, one float in device memory). --------------------------- */
+/* *amax_bits (uint32, zero-initialised by the caller) = max(*amax_bits, bits of max|x|) */
+int pvg_amax(const float* x, int64_t n, uint32_t* amax_bits, void* stream);
+/* planes = PVG_CORR_FP16_ALL planes of x * S, *inv_scale = 1 / S, with S chosen from *amax_bits */
+int pvg_split_16_scaled(const float* x, void* planes, int64_t n, const uint32_t* amax_bits, float* inv_scale, void* stream);
+/* g = dy * act'(y) (g may be NULL) and the scaled planes of g; *amax_bits = max|dy| bounds max|g| (|act'| <= 1) */
+int pvg_act_bwd_split_16_scaled(const float* dy, const float* y, int act, float slope, float* g, void* planes, int64_t n,
+                                const uint32_t* amax_bits, float* inv_scale, void* stream);
 /* g = dy * act'(y) and the 16-bit plane pair of g (pvg_split_16) in one pass */
 int pvg_act_bwd_split_16(const float* dy, const float* y, int act, float slope, float* g, void* planes, int64_t n, int fmt,
                          void* stream);
@@ -144,6 +161,16 @@ int pvg_bn_eval_prepare(const float* running_mean, const float* running_var, int
 int pvg_bn_apply(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
                  const float* weight, const float* bias, const float* residual, int act, float slope,
                  float* y, void* stream);
+/* *_ex: the same pass also writes up to two 16-bit plane pairs of y (planes_a / planes_b: [2][numel(y)], formats fmt_a / fmt_b =
+ * PVG_CORR_*; NULL = none; C % 8 == 0): the operands of the convolution that consumes y (forward: PVG_CORR_FP16_ALL; its
+ * weight gradient: PVG_CORR_BF16), so that no separate pvg_split_16 pass re-reads y. */
+int pvg_bn_apply_ex(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
+                    const float* weight, const float* bias, const float* residual, int act, float slope,
+                    float* y, void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream);
+int pvg_bn_finalize_apply_ex(const float* x, int N, int HW, int C, int groups, const double* sums, int64_t count, float eps,
+                             float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                             const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
+                             void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream);
 /* backward pass 1: with g = dy * act'(y): sums2 (double[groups][2][C], zeroed) += (sum g, sum g * xhat) */
 int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, int HW, int C, int groups,
                       const float* mean, const float* invstd, int act, float slope, double* sums2, void* stream);
@@ -169,9 +196,26 @@ int pvg_upsample2x_fwd(const float* x, int N, int H, int W, int C, float* y, voi
 int pvg_upsample2x_bwd(const float* dy, int N, int H, int W, int C, float* dx, void* stream);   /* H,W = input size */
 int pvg_resize_bilinear(const float* x, int N, int H, int W, int C, float* y, int OH, int OW, void* stream);
 int pvg_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream);
+int pvg_maxpool2_fwd_ex(const float* x, int N, int H, int W, int C, float* y, void* planes_a, int fmt_a, void* stream);
+int pvg_resize_bilinear_ex(const float* x, int N, int H, int W, int C, float* y, int OH, int OW, void* planes_a, int fmt_a,
+                           void* planes_b, int fmt_b, void* stream);
 /* dx = (x is the first arg-max of its 2x2 window) ? dy : 0, times relu'(x) when relu_mask != 0 */
 int pvg_maxpool2_bwd(const float* dy, const float* x, const float* y, int N, int H, int W, int C, int relu_mask,
                      float* dx, void* stream);
+
+/* ---- channel concat feeding the recurrent / non-recurrent blocks of the dynamics network: torch.cat of maps and of (N, C) vectors
+ *      repeated over H x W (conv_dynamics_network.py:64-109, convolutional_lstm_cell.py:88-89), zero-padded to Cpad physical
+ *      channels (a tensor-core-legal K), optionally with the 16-bit plane pairs of the result. ------------------------- */
+#define PVG_CONCAT_MAX_PARTS 6
+typedef struct pvg_concat_desc {
+  int32_t N, H, W, Cpad;
+  int32_t nparts;
+  int32_t c[PVG_CONCAT_MAX_PARTS];        /* channels of each part, in output order */
+  int32_t is_vec[PVG_CONCAT_MAX_PARTS];   /* 0: NHWC map [N][H][W][c]; 1: vector [N][c] broadcast over H x W */
+  int64_t bstride[PVG_CONCAT_MAX_PARTS];  /* elements between consecutive samples of the part (>= H*W*c for maps, >= c for vectors) */
+  const void* src[PVG_CONCAT_MAX_PARTS];
+} pvg_concat_desc;
+int pvg_concat_pad(const pvg_concat_desc* d, float* y, void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream);
 
 /* ---- ConvLSTM cell point-wise part, convolutional_lstm_cell.py:92-101.  gates: [M][4][C] pre-activations in the
  *      order input, forget, output, cell. ------------------------------------------------------------------------ */

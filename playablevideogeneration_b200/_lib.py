@@ -20,11 +20,22 @@ class ConvDesc(Structure):
                 ("algo", c_int32), ("nprod", c_int32), ("corr_fmt", c_int32)]
 
 
+class ConcatDesc(Structure):
+    """struct pvg_concat_desc (include/pvg_b200.h)."""
+    MAX_PARTS = 6
+    _fields_ = [("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cpad", c_int32), ("nparts", c_int32),
+                ("c", c_int32 * 6), ("is_vec", c_int32 * 6), ("bstride", c_int64 * 6), ("src", c_void_p * 6)]
+
+
 P = c_void_p
 # name -> (argtypes); every function returns int (0 = ok) except pvg_last_error / pvg_version / pvg_has_umma
 _SIGNATURES = {
     "pvg_conv2d_fwd": [POINTER(ConvDesc), P, P, P, P, P, P, P],
-    "pvg_conv2d_fwd_planes": [POINTER(ConvDesc), P, P, P, P, P, P],
+    "pvg_conv2d_fwd_planes": [POINTER(ConvDesc), P, P, P, P, P, P, P],
+    "pvg_conv2d_wgrad_planes": [POINTER(ConvDesc), c_int, P, P, P, P, P, c_int, P],
+    "pvg_amax": [P, c_int64, P, P],
+    "pvg_split_16_scaled": [P, P, c_int64, P, P, P],
+    "pvg_act_bwd_split_16_scaled": [P, P, c_int, c_float, P, P, c_int64, P, P, P],
     "pvg_pack_conv_weight": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P],
     "pvg_conv2d_wgrad": [POINTER(ConvDesc), c_int, P, P, P, P],
     "pvg_conv2d_wgrad_umma": [POINTER(ConvDesc), c_int, P, P, P, P, P, P, c_int, P],
@@ -40,6 +51,12 @@ _SIGNATURES = {
     "pvg_bn_finalize": [P, c_int64, c_int, c_int, c_float, c_float, P, P, P, P, P],
     "pvg_bn_eval_prepare": [P, P, c_int, c_float, P, P, P],
     "pvg_bn_apply": [P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_float, P, P],
+    "pvg_bn_apply_ex": [P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_float, P, P, c_int, P, c_int, P],
+    "pvg_bn_finalize_apply_ex": [P, c_int, c_int, c_int, c_int, P, c_int64, c_float, c_float, P, P, P, P, P, P, P, c_int, c_float,
+                                 P, P, c_int, P, c_int, P],
+    "pvg_maxpool2_fwd_ex": [P, c_int, c_int, c_int, c_int, P, P, c_int, P],
+    "pvg_resize_bilinear_ex": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int, P, c_int, P],
+    "pvg_concat_pad": [POINTER(ConcatDesc), P, P, c_int, P, c_int, P],
     "pvg_bn_bwd_reduce": [P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P],
     "pvg_bn_bwd_apply": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P, P, P],
     "pvg_bn_finalize_apply": [P, c_int, c_int, c_int, c_int, P, c_int64, c_float, c_float, P, P, P, P, P, P, P, c_int, c_float,

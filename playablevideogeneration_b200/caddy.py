@@ -102,17 +102,20 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(_conv(in_planes, out_planes, 1, False), nn.AvgPool2d(downsample_factor),
                                             nn.BatchNorm2d(out_planes))
 
-    def forward(self, x):
+    def forward(self, x, out_planes: bool = False):
+        """``out_planes``: the block's output feeds another tensor-core convolution - the last BatchNorm pass writes that
+        convolution's 16-bit operand planes next to the fp32 result (no separate split pass)."""
         pool = self.downsample_factor == 2
+        need = ops.conv_input_planes()
         out = ops.conv2d(x, self.conv1.weight)
-        out = ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE)
+        out = ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE, planes=need)
         out = ops.conv2d(out, self.conv2.weight)
         if self.downsample is not None:
             idn = ops.conv2d(x, self.downsample[0].weight)
             idn = ops.pool_bn_act(idn, self.downsample[2], pool=pool, act=ACT_NONE)
         else:
             idn = x
-        return ops.pool_bn_act(out, self.bn2, residual=idn, act=ACT_LRELU, slope=SLOPE)
+        return ops.pool_bn_act(out, self.bn2, residual=idn, act=ACT_LRELU, slope=SLOPE, planes=need if out_planes else ())
 
 
 class SameBlock(nn.Module):
@@ -138,10 +141,11 @@ class UpBlock(nn.Module):
         self.conv = _conv(in_features, out_features, 3, False)
         self.norm = nn.BatchNorm2d(out_features, affine=True)
 
-    def forward(self, x):
+    def forward(self, x, out_planes: bool = False):
         if not self.late_upscaling:
-            x = ops.upsample2x(x)
-        x = ops.pool_bn_act(ops.conv2d(x, self.conv.weight), self.norm, act=ACT_LRELU, slope=SLOPE)
+            x = ops.upsample2x(x, planes=ops.conv_input_planes())
+        x = ops.pool_bn_act(ops.conv2d(x, self.conv.weight), self.norm, act=ACT_LRELU, slope=SLOPE,
+                            planes=ops.conv_input_planes() if (out_planes and not self.late_upscaling) else ())
         if self.late_upscaling:
             x = ops.upsample2x(x)
         return x
@@ -194,7 +198,7 @@ class ConvLSTM(nn.Module):
             self._c = ops.nhwc(self.initial_hidden_cell_state.unsqueeze(0).expand(batch, -1, -1, -1))
         if self._w is None:
             self._w, self._b = self.cell.fused()
-        z = ops.concat_pad(list(inputs) + [self._h])
+        z = ops.concat_pad(list(inputs) + [self._h], planes=ops.conv_input_planes())
         gates = ops.conv2d(z, self._w, self._b)
         self._h, self._c = ops.lstm_cell(gates, self._c)
         return self._h
@@ -228,12 +232,13 @@ class ConvDynamicsNetwork(nn.Module):
         return ops.pool_bn_act(lstm([x, actions, variations]), bn, act=ACT_NONE)
 
     def forward(self, states, actions, variations, random_noise=None):
+        need = ops.conv_input_planes()
         x = self._recurrent(0, states, actions, variations)
-        x = self.non_recurrent_blocks[0](ops.concat_pad([x, actions, variations]))
+        x = self.non_recurrent_blocks[0](ops.concat_pad([x, actions, variations], planes=need))
         x = self._recurrent(1, x, actions, variations)
-        x = self.non_recurrent_blocks[1](ops.concat_pad([x, actions, variations]))
+        x = self.non_recurrent_blocks[1](ops.concat_pad([x, actions, variations], planes=need))
         x = self._recurrent(2, x, actions, variations)
-        return self.non_recurrent_blocks[2](ops.concat_pad([x, actions, variations]))
+        return self.non_recurrent_blocks[2](ops.concat_pad([x, actions, variations], planes=need))
 
 
 class RepresentationNetwork(nn.Module):
@@ -250,9 +255,10 @@ class RepresentationNetwork(nn.Module):
 
     def forward(self, observations):
         x = ops.conv2d(observations, self.conv1.weight)
-        x = ops.pool_bn_act(x, self.bn1, pool=True, act=ACT_LRELU, slope=SLOPE)
-        for block in self.residuals:
-            x = block(x)
+        x = ops.pool_bn_act(x, self.bn1, pool=True, act=ACT_LRELU, slope=SLOPE, planes=ops.conv_input_planes())
+        last = len(self.residuals) - 1
+        for i, block in enumerate(self.residuals):
+            x = block(x, out_planes=i < last)
         return x[:, :-1], torch.sigmoid(x[:, -1:])
 
 
@@ -279,8 +285,8 @@ class ActionNetwork(nn.Module):
     def forward(self, states, attention):
         b, t = states.shape[:2]
         x = (states * attention).reshape((b * t,) + tuple(states.shape[2:]))
-        for block in self.residuals:
-            x = block(x)
+        x = self.residuals[0](x, out_planes=True)
+        x = self.residuals[1](x)
         x = x.mean(dim=(2, 3))
         mean = F.linear(x, self.mean_fc.weight, self.mean_fc.bias)
         var = torch.abs(F.linear(x, self.variance_fc.weight, self.variance_fc.bias))
@@ -311,9 +317,8 @@ class RenderingNetwork(nn.Module):
         x = hidden_states
         outs = []
         for up, final in zip(self.upsample_blocks, self.final_blocks):
-            if isinstance(up, nn.Sequential):
-                for m in up:
-                    x = m(x)
+            if isinstance(up, nn.Sequential):          # UpBlock -> ResidualBlock: the UpBlock's output feeds the block's convs
+                x = up[1](up[0](x, out_planes=True))
             else:
                 x = up(x)
             outs.append(final(x))

@@ -308,6 +308,7 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int period = taps == 9 ? 9 : C::kDrain;
     const int periods = (k_iters + period - 1) / period;
+    const float out_scale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;      // 1 / S of a scaled gradient operand
     uint32_t pg = 0;
     for (int item = first_item; item < total_items; item += item_stride) {
       const H3Tile t = h3_decode<PAIR>(item, rank, n_tiles, BN, p);
@@ -339,7 +340,7 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[16];
         tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(v[j], 0x1p-12f, acc[c + j]);
+        for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(v[j], 0x1p-12f, acc[c + j]) * out_scale;
       }
       tc_fence_before();
       if (PAIR) mbar_arrive_leader(cfree_bar); else mbar_arrive(cfree_bar);
@@ -388,13 +389,13 @@ static int env_int(const char* name, int dflt) {
 
 template <int BN, bool HALO, bool PAIR>
 static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
-                     void* y_planes, cudaStream_t st) {
+                     void* y_planes, const float* out_scale, cudaStream_t st) {
   using C = H3Cfg<BN, HALO, PAIR>;
   ConvParams p;
   const int CinK = (d->Cin + 31) & ~31;       // the K loop runs over whole 32-channel chunks: TMA zero-fills past the tensor's extent
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = 1;
-  p.y_planes = (uint16_t*)y_planes; p.y_numel = (int64_t)d->N * d->H * d->W * d->Cout;
+  p.y_planes = (uint16_t*)y_planes; p.y_numel = (int64_t)d->N * d->H * d->W * d->Cout; p.out_scale = out_scale;
   static const int dbg = env_int("PVG_H3_DBG", 0);      // timing experiment only (wrong results): haloed tile read without row offsets
   p.dbg = dbg;
   if (HALO) { p.tw = 8; p.th = 16; p.tn = 1; }
@@ -430,23 +431,24 @@ static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w
 }
 
 template <bool HALO, bool PAIR>
-static int dispatch_h3_bn(const pvg_conv_desc* d, const void* xp, const void* wp, const float* bias, float* y, void* yp, cudaStream_t st) {
+static int dispatch_h3_bn(const pvg_conv_desc* d, const void* xp, const void* wp, const float* bias, float* y, void* yp,
+                          const float* os, cudaStream_t st) {
   const int co = d->Cout;
   if constexpr (PAIR) {
-    if (co <= 64) return launch_h3<64, HALO, true>(d, xp, wp, bias, y, yp, st);
-    return launch_h3<128, HALO, true>(d, xp, wp, bias, y, yp, st);
+    if (co <= 64) return launch_h3<64, HALO, true>(d, xp, wp, bias, y, yp, os, st);
+    return launch_h3<128, HALO, true>(d, xp, wp, bias, y, yp, os, st);
   } else {
-    if (co <= 16) return launch_h3<16, HALO, false>(d, xp, wp, bias, y, yp, st);
-    if (co <= 32) return launch_h3<32, HALO, false>(d, xp, wp, bias, y, yp, st);
-    if (co <= 64) return launch_h3<64, HALO, false>(d, xp, wp, bias, y, yp, st);
-    if (co <= 80) return launch_h3<80, HALO, false>(d, xp, wp, bias, y, yp, st);
-    return launch_h3<128, HALO, false>(d, xp, wp, bias, y, yp, st);
+    if (co <= 16) return launch_h3<16, HALO, false>(d, xp, wp, bias, y, yp, os, st);
+    if (co <= 32) return launch_h3<32, HALO, false>(d, xp, wp, bias, y, yp, os, st);
+    if (co <= 64) return launch_h3<64, HALO, false>(d, xp, wp, bias, y, yp, os, st);
+    if (co <= 80) return launch_h3<80, HALO, false>(d, xp, wp, bias, y, yp, os, st);
+    return launch_h3<128, HALO, false>(d, xp, wp, bias, y, yp, os, st);
   }
 }
 
 // all-fp16 forward convolution; called by pvg_conv2d_fwd (nprod == 2, corr_fmt == PVG_CORR_FP16_ALL) and pvg_conv2d_fwd_planes
 int conv2d_fwd_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
-                  void* y_planes, cudaStream_t st) {
+                  void* y_planes, const float* out_scale, cudaStream_t st) {
   static const int force_halo = env_int("PVG_H3_HALO", -1);       // A/B knobs: 0 / 1 force, -1 = heuristic
   static const int force_pair = env_int("PVG_H3_PAIR", -1);
   // halo reuse: 3x3 convs whose maps tile well into 8 x 16 single-image patches
@@ -465,10 +467,10 @@ int conv2d_fwd_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_pl
   const int64_t rounds1 = ceil_div64(m_tiles * n_tiles, kSMs), rounds2 = ceil_div64(ceil_div64(m_tiles, 2) * n_tiles, kSMs / 2);
   bool pair = d->Cout > 32 && rounds2 * 4 <= rounds1 * 5;
   if (force_pair >= 0) pair = force_pair == 1 && d->Cout > 32;
-  if (halo) return pair ? dispatch_h3_bn<true, true>(d, x_planes, w_planes, bias, y, y_planes, st)
-                        : dispatch_h3_bn<true, false>(d, x_planes, w_planes, bias, y, y_planes, st);
-  return pair ? dispatch_h3_bn<false, true>(d, x_planes, w_planes, bias, y, y_planes, st)
-              : dispatch_h3_bn<false, false>(d, x_planes, w_planes, bias, y, y_planes, st);
+  if (halo) return pair ? dispatch_h3_bn<true, true>(d, x_planes, w_planes, bias, y, y_planes, out_scale, st)
+                        : dispatch_h3_bn<true, false>(d, x_planes, w_planes, bias, y, y_planes, out_scale, st);
+  return pair ? dispatch_h3_bn<false, true>(d, x_planes, w_planes, bias, y, y_planes, out_scale, st)
+              : dispatch_h3_bn<false, false>(d, x_planes, w_planes, bias, y, y_planes, out_scale, st);
 }
 
 }  // namespace pvg
@@ -478,12 +480,12 @@ using namespace pvg;
 // y = act(bias + conv(x, w)) with x and w given ONLY as fp16 plane pairs (pvg_split_16 / pvg_pack_16x2 with PVG_CORR_FP16_ALL,
 // or the y_planes of a previous call); y_planes (optional): the plane pair of y for the next convolution.
 extern "C" int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias,
-                                     float* y, void* y_planes, void* stream) {
+                                     float* y, void* y_planes, const float* out_scale, void* stream) {
   PVG_CHECK_ARG(d && x_planes && w_planes && y, "null argument");
   PVG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "empty problem");
   PVG_CHECK_ARG(d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "only odd 'same' kernels are supported");
   PVG_CHECK_ARG(d->Cin % 8 == 0, "16-bit planes need Cin % 8 == 0 (16-byte TMA strides)");
   PVG_CHECK_ARG((((uintptr_t)x_planes | (uintptr_t)w_planes | (uintptr_t)y | (uintptr_t)y_planes) & 15) == 0, "operands must be 16-byte aligned");
   PVG_CHECK_ARG(!y_planes || d->Cout % 8 == 0, "y_planes needs Cout % 8 == 0");
-  return conv2d_fwd_h3(d, x_planes, w_planes, bias, y, y_planes, (cudaStream_t)stream);
+  return conv2d_fwd_h3(d, x_planes, w_planes, bias, y, y_planes, out_scale, (cudaStream_t)stream);
 }

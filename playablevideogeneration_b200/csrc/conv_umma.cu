@@ -34,7 +34,7 @@ namespace pvg {
 
 int conv2d_fwd_simt(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
 int conv2d_fwd_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
-                  void* y_planes, cudaStream_t st);      // conv_h3.cu
+                  void* y_planes, const float* out_scale, cudaStream_t st);      // conv_h3.cu
 
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
@@ -1266,7 +1266,7 @@ extern "C" int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void
     PVG_CHECK_ARG((((uintptr_t)x_lo | (uintptr_t)w_lo) & 15) == 0, "bf16 planes must be 16-byte aligned");
     if (h3) {        // all-fp16 split product: conv_h3.cu (PVG_H3_LEGACY=1: the one-tile-per-CTA kernel of this file, A/B knob)
       static const bool legacy = getenv("PVG_H3_LEGACY") && atoi(getenv("PVG_H3_LEGACY")) == 1;
-      if (!legacy) return conv2d_fwd_h3(d, x_lo, w_lo, bias, y, nullptr, st);
+      if (!legacy) return conv2d_fwd_h3(d, x_lo, w_lo, bias, y, nullptr, nullptr, st);
       return dispatch_bn<4>(d, x, x_lo, w, w_lo, bias, y, st);
     }
     return dispatch_bn<2>(d, x, x_lo, w, w_lo, bias, y, st);

@@ -30,7 +30,10 @@ constexpr int kWSmemBudget = 200 * 1024;
 
 template <int BN, int NPROD>
 struct WCfg {
-  static constexpr int kPlanes = NPROD >= 2 ? 2 : 1;
+  // NPROD == 4: ALL three products as kind::f16 MMAs on fp16 plane pairs (x: PVG_CORR_FP16_ALL planes, the forward operand;
+  // dY: the same format after a power-of-two scaling, pvg_split_16_scaled): no fp32 tiles - a {32 ch x 32 px} box of both
+  // planes has the bytes of one fp32 box, so half of the shared-memory / L2 traffic of the TF32 + corrections evaluation
+  static constexpr int kPlanes = (NPROD == 2 || NPROD == 3) ? 2 : 1;
   static constexpr int kABytes = 4 * kBoxBytes;                 // 4 groups of 32 input channels
   static constexpr int kBBytes = (BN / 32) * kBoxBytes;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
@@ -52,6 +55,7 @@ struct WgradParams {
   int patches_per_split;
   float* dwp;                     // [Cout][R*S][CinP]
   int corr_fp16;                  // NPROD == 2: 16-bit correction planes are fp16 (else bf16)
+  const float* out_scale;         // NPROD == 4 (device, optional): 1 / S of the scaled dY planes
 };
 
 template <int BN, int NPROD>
@@ -110,6 +114,10 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
           const int tap = ok ? gi / p.chunks : 0, cc = ok ? gi - tap * p.chunks : 0;
           const int r = tap / p.S, s = tap - r * p.S;
           const int c0 = ok ? cc * 32 : p.CinP;                  // a group past the end loads an all-out-of-bounds (zero) box
+          if (NPROD == 4) {
+            tma_load_5d(st + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+            continue;
+          }
           tma_load_4d(st + g * kBoxBytes, &tmX, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
           if (NPROD == 3)
             tma_load_4d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
@@ -119,6 +127,10 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
         uint8_t* sb = st + C::kPlanes * C::kABytes;
 #pragma unroll
         for (int g = 0; g < BN / 32; ++g) {
+          if (NPROD == 4) {
+            tma_load_5d(sb + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0, 0);
+            continue;
+          }
           tma_load_4d(sb + g * kBoxBytes, &tmG, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
           if (NPROD == 3) tma_load_4d(sb + C::kBBytes + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0);
           if (NPROD == 2) tma_load_5d(sb + C::kBBytes + g * kBoxBytes, &tmGlo, &full_bar[stage], co0 + 32 * g, w0, h0, n0, 0);
@@ -153,6 +165,21 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
         if (leader) {
           const uint32_t a_hi = stage * kStageU, a_lo = a_hi + kAU;
           const uint32_t b_hi = a_hi + C::kPlanes * kAU, b_lo = b_hi + kBU;
+          if (NPROD == 4) {                            // [f16(lo * 2^12) | f16(v)] tiles per channel group, for both operands
+            const uint32_t pa = a_hi, pb = a_hi + kAU;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              umma_bf16(corr, d16 + (pa + 64 * ks), d16 + (pb + kHalfU + 64 * ks), idesc16, corr_acc);
+              corr_acc = 1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) umma_bf16(corr, d16 + (pa + kHalfU + 64 * ks), d16 + (pb + 64 * ks), idesc16, 1);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              umma_bf16(main_acc, d16 + (pa + kHalfU + 64 * ks), d16 + (pb + kHalfU + 64 * ks), idesc16, main_started);
+              main_started = 1;
+            }
+          }
           if (NPROD == 2) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {           // K = 16 pixels = two 8-row (512 B) atoms: 1024 B = 64 units per step
@@ -171,10 +198,12 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_tf32(corr, d32 + (a_hi + 64 * ks), d32 + (b_lo + 64 * ks), idesc, 1);
           }
+          if (NPROD != 4) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {             // K = 8 pixels = two 4-row (512 B) atoms: 1024 B per step
             umma_tf32(main_acc, d32 + (a_hi + 64 * ks), d32 + (b_hi + 64 * ks), idesc, main_started);
             main_started = 1;
+          }
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -212,7 +241,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
     // Bounds are tested once per 16 channels and the address advances by a constant stride (the per-element form cost ~8
     // instructions per value: with split-K CTAs of a few microseconds the epilogue was a third of the kernel).
     // NPROD == 2: the residual planes carry a 2^12 factor (pvg_split_16), so does the correction accumulator
-    constexpr float kCorrScale = NPROD == 2 ? 0x1p-12f : 1.f;
+    constexpr float kCorrScale = (NPROD == 2 || NPROD == 4) ? 0x1p-12f : 1.f;
+    const float out_scale = (NPROD == 4 && p.out_scale != nullptr) ? __ldg(p.out_scale) : 1.f;
     const int64_t co_stride = (int64_t)p.R * p.S * p.CinP;
     float* out = p.dwp + (int64_t)tap * p.CinP + ci + (int64_t)co0 * co_stride;
 #pragma unroll
@@ -221,7 +251,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
       if (NPROD >= 2) {
         tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], kCorrScale, acc[c + j]);
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], kCorrScale, acc[c + j]) * out_scale;
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = acc[c + j];
@@ -270,11 +300,12 @@ static void choose_patch32(int N, int H, int W, int* tw, int* th, int* tn) {
 
 template <int BN, int NPROD>
 static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_lo, const float* g, const float* g_lo,
-                        float* dwp, cudaStream_t st) {
+                        float* dwp, cudaStream_t st, const float* out_scale = nullptr) {
   using C = WCfg<BN, NPROD>;
   WgradParams p;
+  p.out_scale = out_scale;
   const int CinK = (d->Cin + 31) & ~31;     // K-side channel count padded to whole 32-channel groups (TMA zero-fills the rest)
-  p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp; p.corr_fp16 = d->corr_fmt == PVG_CORR_FP16;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.CinP = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad; p.dwp = dwp; p.corr_fp16 = d->corr_fmt != PVG_CORR_BF16;
   choose_patch32(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   p.chunks = CinK / 32;
@@ -289,9 +320,15 @@ static int launch_wgrad(const pvg_conv_desc* d, const float* x, const float* x_l
   splits = ceil_div(total, p.patches_per_split);
   CUtensorMap tmG, tmGlo, tmX, tmXlo;
   int rc;
-  if ((rc = encode_nhwc_map(&tmG, g, d->N, d->H, d->W, d->Cout, 32, p.tw, p.th, p.tn, true))) return rc;
-  if ((rc = encode_nhwc_map(&tmX, x, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn, true))) return rc;
-  if (NPROD == 3) {
+  if (NPROD != 4) {
+    if ((rc = encode_nhwc_map(&tmG, g, d->N, d->H, d->W, d->Cout, 32, p.tw, p.th, p.tn, true))) return rc;
+    if ((rc = encode_nhwc_map(&tmX, x, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn, true))) return rc;
+  }
+  if (NPROD == 4) {
+    if ((rc = encode_nhwc_16x2_map(&tmGlo, g_lo, d->N, d->H, d->W, d->Cout, p.tw, p.th, p.tn))) return rc;
+    if ((rc = encode_nhwc_16x2_map(&tmXlo, x_lo, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn))) return rc;
+    tmG = tmGlo; tmX = tmXlo;
+  } else if (NPROD == 3) {
     if ((rc = encode_nhwc_map(&tmGlo, g_lo, d->N, d->H, d->W, d->Cout, 32, p.tw, p.th, p.tn, true))) return rc;
     if ((rc = encode_nhwc_map(&tmXlo, x_lo, d->N, d->H, d->W, d->Cin, 32, p.tw, p.th, p.tn, true))) return rc;
   } else if (NPROD == 2) {
@@ -347,6 +384,29 @@ extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, co
     else if (cin <= 96) rc = launch_wgrad<96, 1>(d, x, nullptr, g, nullptr, scratch, st);
     else rc = launch_wgrad<128, 1>(d, x, nullptr, g, nullptr, scratch, st);
   }
+  if (rc) return rc;
+  int64_t total = (int64_t)d->Cout * Cin_logical * d->R * d->S;
+  unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, (d->Cin + 31) & ~31, dw_oihw, accumulate);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+// Weight gradient from plane pairs only (see include/pvg_b200.h): x_planes / g_planes are PVG_CORR_FP16_ALL plane pairs, the
+// latter of dY * S; the result is multiplied by *out_scale = 1 / S.
+extern "C" int pvg_conv2d_wgrad_planes(const pvg_conv_desc* d, int Cin_logical, const void* x_planes, const void* g_planes,
+                                       const float* out_scale, float* scratch, float* dw_oihw, int accumulate, void* stream) {
+  PVG_CHECK_ARG(d && x_planes && g_planes && scratch && dw_oihw, "null argument");
+  PVG_CHECK_ARG(d->Cin % 8 == 0 && d->Cout % 8 == 0, "16-bit planes need Cin % 8 == 0 and Cout % 8 == 0");
+  PVG_CHECK_ARG((((uintptr_t)x_planes | (uintptr_t)g_planes) & 15) == 0, "planes must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* xp = (const float*)x_planes;
+  const float* gp = (const float*)g_planes;
+  int rc;
+  const int co = d->Cout;
+  if (co <= 32) rc = launch_wgrad<32, 4>(d, nullptr, xp, nullptr, gp, scratch, st, out_scale);
+  else if (co <= 64) rc = launch_wgrad<64, 4>(d, nullptr, xp, nullptr, gp, scratch, st, out_scale);
+  else if (co <= 96) rc = launch_wgrad<96, 4>(d, nullptr, xp, nullptr, gp, scratch, st, out_scale);
+  else rc = launch_wgrad<128, 4>(d, nullptr, xp, nullptr, gp, scratch, st, out_scale);
   if (rc) return rc;
   int64_t total = (int64_t)d->Cout * Cin_logical * d->R * d->S;
   unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, (d->Cin + 31) & ~31, dw_oihw, accumulate);

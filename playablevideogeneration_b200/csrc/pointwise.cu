@@ -28,6 +28,72 @@ template <> struct Vec<1> {
   __device__ void store(float* p) const { *p = v[0]; }
 };
 
+// hi != NULL: hi = rna_tf32(x), lo = x - hi (robust to any tensor-core input rounding).
+// hi == NULL: lo = x - trunc_tf32(x); valid when the tensor core truncates raw fp32 operands, x itself is then "hi".
+__device__ __forceinline__ float tf32_part(float v, bool rna) {
+  return rna ? tf32_hi(v) : __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+}
+// 16-bit correction operands of the nprod == 2 product: planes[0][i] = f16((x - trunc_tf32(x)) * 2^12), planes[1][i] = f16(x)
+// with f16 = bf16 (round to nearest) or fp16 (round to nearest, saturating at +-65504).  The 2^12 keeps the residual in
+// fp16's normal range; the tensor-core kernels fold it back (2^-12) when they add the correction accumulator.
+// fp16 carries 11 significant bits: it holds the tf32 "hi" plane of a WEIGHT exactly, so the weight side adds no error
+// that is coherent over the batch (with bf16 weights that error measured 30x the fp32 CPU oracle's on cancellation-heavy
+// gradients); bf16 keeps fp32's exponent range and is what gradients (1e-6..1e-12) need.  kind::f16 cannot mix the two
+// formats in one MMA (illegal instruction on sm_100a), so a conv uses one format for both operands.
+// FMT: PVG_CORR_BF16 (0) | PVG_CORR_FP16 (1) | PVG_CORR_FP16_ALL (2, fp16 planes whose residual is taken w.r.t. f16(x), so
+// that the plane pair alone carries x to 22 bits: ALL three products of the split then run as kind::f16 MMAs on the planes
+// and the fp32 tensor is not read by the convolution at all)
+template <int FMT>
+__device__ __forceinline__ uint32_t f16x2_bits(float a, float b) {
+  if (FMT != PVG_CORR_BF16) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// the part of v that the "hi" operand of the main product carries: trunc_tf32(v) (the tensor core truncates the raw fp32
+// operand) or, in the all-fp16 evaluation, f16(v)
+template <int FMT>
+__device__ __forceinline__ float hi_part(float v) {
+  if (FMT == PVG_CORR_FP16_ALL) return __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+  return tf32_part(v, false);
+}
+template <int FMT>
+__device__ __forceinline__ void store_16_planes(uint16_t* planes, int64_t n, int64_t i4, float4 v) {
+  const float4 h = make_float4(hi_part<FMT>(v.x), hi_part<FMT>(v.y), hi_part<FMT>(v.z), hi_part<FMT>(v.w));
+  constexpr float kS = 4096.f;
+  uint2 lo = make_uint2(f16x2_bits<FMT>((v.x - h.x) * kS, (v.y - h.y) * kS), f16x2_bits<FMT>((v.z - h.z) * kS, (v.w - h.w) * kS));
+  uint2 xb = make_uint2(f16x2_bits<FMT>(v.x, v.y), f16x2_bits<FMT>(v.z, v.w));
+  *reinterpret_cast<uint2*>(planes + 4 * i4) = lo;
+  *reinterpret_cast<uint2*>(planes + n + 4 * i4) = xb;
+}
+
+// Optional 16-bit plane outputs of a producer kernel: up to two plane pairs (e.g. fp16 "all" planes for the next forward conv
+// and bf16 planes for its weight gradient) of the fp32 tensor it writes, so that no separate pvg_split_16 pass re-reads it.
+struct PlaneOut {
+  uint16_t* p[2];
+  int fmt[2];
+  int64_t n;            // elements of the tensor (offset of the second plane of a pair)
+};
+__device__ __forceinline__ void emit_planes4(const PlaneOut& po, int64_t elem, float4 v) {      // elem % 4 == 0
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (po.p[k] == nullptr) continue;
+    if (po.fmt[k] == PVG_CORR_FP16_ALL) store_16_planes<2>(po.p[k], po.n, elem >> 2, v);
+    else if (po.fmt[k] == PVG_CORR_FP16) store_16_planes<1>(po.p[k], po.n, elem >> 2, v);
+    else store_16_planes<0>(po.p[k], po.n, elem >> 2, v);
+  }
+}
+template <int V>
+__device__ __forceinline__ void emit_planes(const PlaneOut& po, int64_t elem, const Vec<V>& o) {
+  if (V == 4) emit_planes4(po, elem, make_float4(o.v[0], o.v[V > 1 ? 1 : 0], o.v[V > 2 ? 2 : 0], o.v[V > 3 ? 3 : 0]));
+}
+static PlaneOut no_planes() { PlaneOut po; po.p[0] = po.p[1] = nullptr; po.fmt[0] = po.fmt[1] = 0; po.n = 0; return po; }
+static PlaneOut make_planes(void* a, int fa, void* b, int fb, int64_t n) {
+  PlaneOut po; po.p[0] = (uint16_t*)a; po.p[1] = (uint16_t*)b; po.fmt[0] = fa; po.fmt[1] = fb; po.n = n; return po;
+}
+
 constexpr int kRedThreads = 256;
 
 // Per-channel reduction of K quantities over the rows of one batch group.  `f(row, unit, acc)` adds the
@@ -141,7 +207,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        int C, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, const float* __restrict__ weight,
                                                        const float* __restrict__ bias, const float* __restrict__ residual,
-                                                       int act, float slope, float* __restrict__ y) {
+                                                       int act, float slope, float* __restrict__ y, const PlaneOut po) {
   const int U = C / V;
   const int64_t total = M * U;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -159,6 +225,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
       o.v[j] = act_fwd(v, act, slope);
     }
     o.store(y + r * C + c);
+    emit_planes<V>(po, r * C + c, o);
   }
 }
 
@@ -195,7 +262,7 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* __r
                                                                 float* running_var, float* __restrict__ mean,
                                                                 float* __restrict__ invstd, const float* __restrict__ weight,
                                                                 const float* __restrict__ bias, const float* __restrict__ residual,
-                                                                int act, float slope, float* __restrict__ y) {
+                                                                int act, float slope, float* __restrict__ y, const PlaneOut po) {
   extern __shared__ float sm_stats[];              // [groups][C] mean, then [groups][C] invstd
   float* s_mean = sm_stats;
   float* s_inv = sm_stats + (size_t)groups * C;
@@ -243,6 +310,7 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* __r
       o.v[j] = act_fwd(v, act, slope);
     }
     o.store(y + r * C + c);
+    emit_planes<V>(po, r * C + c, o);
   }
 }
 
@@ -333,7 +401,8 @@ __device__ __forceinline__ Lerp src_index(int dst, float scale, int in_size) {
 
 template <int V>
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ x, int N, int H, int W, int C,
-                                                              float* __restrict__ y, int OH, int OW, float sh, float sw) {
+                                                              float* __restrict__ y, int OH, int OW, float sh, float sw,
+                                                              const PlaneOut po) {
   const int U = C / V;
   const int64_t total = (int64_t)N * OH * OW * U;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -352,6 +421,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
     for (int j = 0; j < V; ++j)
       o.v[j] = w0y * (w0x * v00.v[j] + w1x * v01.v[j]) + w1y * (w0x * v10.v[j] + w1x * v11.v[j]);
     o.store(y + i * V);
+    emit_planes<V>(po, i * V, o);
   }
 }
 
@@ -395,7 +465,7 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float* __rest
 
 template <int V>
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C,
-                                                           float* __restrict__ y) {
+                                                           float* __restrict__ y, const PlaneOut po) {
   const int U = C / V, OH = H / 2, OW = W / 2;
   const int64_t total = (int64_t)N * OH * OW * U;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -409,6 +479,7 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restri
 #pragma unroll
     for (int j = 0; j < V; ++j) o.v[j] = fmaxf(fmaxf(a.v[j], b.v[j]), fmaxf(cc.v[j], d.v[j]));
     o.store(y + i * V);
+    emit_planes<V>(po, i * V, o);
   }
 }
 
@@ -556,11 +627,6 @@ __global__ void __launch_bounds__(256) absdiff_mean_bwd_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------------------------
 // misc
 // ---------------------------------------------------------------------------------------------------------------
-// hi != NULL: hi = rna_tf32(x), lo = x - hi (robust to any tensor-core input rounding).
-// hi == NULL: lo = x - trunc_tf32(x); valid when the tensor core truncates raw fp32 operands, x itself is then "hi".
-__device__ __forceinline__ float tf32_part(float v, bool rna) {
-  return rna ? tf32_hi(v) : __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-}
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                                          float* __restrict__ lo, int64_t n) {
   const bool rna = hi != nullptr;
@@ -578,41 +644,6 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
-// 16-bit correction operands of the nprod == 2 product: planes[0][i] = f16((x - trunc_tf32(x)) * 2^12), planes[1][i] = f16(x)
-// with f16 = bf16 (round to nearest) or fp16 (round to nearest, saturating at +-65504).  The 2^12 keeps the residual in
-// fp16's normal range; the tensor-core kernels fold it back (2^-12) when they add the correction accumulator.
-// fp16 carries 11 significant bits: it holds the tf32 "hi" plane of a WEIGHT exactly, so the weight side adds no error
-// that is coherent over the batch (with bf16 weights that error measured 30x the fp32 CPU oracle's on cancellation-heavy
-// gradients); bf16 keeps fp32's exponent range and is what gradients (1e-6..1e-12) need.  kind::f16 cannot mix the two
-// formats in one MMA (illegal instruction on sm_100a), so a conv uses one format for both operands.
-// FMT: PVG_CORR_BF16 (0) | PVG_CORR_FP16 (1) | PVG_CORR_FP16_ALL (2, fp16 planes whose residual is taken w.r.t. f16(x), so
-// that the plane pair alone carries x to 22 bits: ALL three products of the split then run as kind::f16 MMAs on the planes
-// and the fp32 tensor is not read by the convolution at all)
-template <int FMT>
-__device__ __forceinline__ uint32_t f16x2_bits(float a, float b) {
-  if (FMT != PVG_CORR_BF16) {
-    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// the part of v that the "hi" operand of the main product carries: trunc_tf32(v) (the tensor core truncates the raw fp32
-// operand) or, in the all-fp16 evaluation, f16(v)
-template <int FMT>
-__device__ __forceinline__ float hi_part(float v) {
-  if (FMT == PVG_CORR_FP16_ALL) return __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
-  return tf32_part(v, false);
-}
-template <int FMT>
-__device__ __forceinline__ void store_16_planes(uint16_t* planes, int64_t n, int64_t i4, float4 v) {
-  const float4 h = make_float4(hi_part<FMT>(v.x), hi_part<FMT>(v.y), hi_part<FMT>(v.z), hi_part<FMT>(v.w));
-  constexpr float kS = 4096.f;
-  uint2 lo = make_uint2(f16x2_bits<FMT>((v.x - h.x) * kS, (v.y - h.y) * kS), f16x2_bits<FMT>((v.z - h.z) * kS, (v.w - h.w) * kS));
-  uint2 xb = make_uint2(f16x2_bits<FMT>(v.x, v.y), f16x2_bits<FMT>(v.z, v.w));
-  *reinterpret_cast<uint2*>(planes + 4 * i4) = lo;
-  *reinterpret_cast<uint2*>(planes + n + 4 * i4) = xb;
-}
 template <int FMT>
 __global__ void __launch_bounds__(256) split_16_kernel(const float* __restrict__ x, uint16_t* __restrict__ planes, int64_t n) {
   const int64_t q = n / 4;                      // n % 8 == 0 (checked by the host wrapper)
@@ -647,6 +678,73 @@ __global__ void __launch_bounds__(256) act_bwd_split_16_kernel(const float* __re
                            d.z * act_bwd_from_out(o.z, act, slope), d.w * act_bwd_from_out(o.w, act, slope));
     stg4(g + 4 * i, v);
     store_16_planes<FMT>(planes, n, i, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradients as fp16 plane pairs: fp16 has no range for raw gradients (1e-6 .. 1e-12), so the tensor is scaled by a power of
+// two S chosen from its largest magnitude, max|g| * S in [2^13, 2^14): the pair {f16((gS - f16(gS)) * 2^12), f16(gS)} then
+// carries every element within 2^26 of the maximum to 22 bits (better than the 19 bits of a TF32 + bf16 pair) and smaller
+// ones with an absolute error below 2^-50 of the maximum.  The consumer (data / weight gradient kernel) multiplies its result
+// by 1 / S, read from device memory.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ amax_bits) {
+  float m = 0.f;
+  const int64_t q = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg4(x + 4 * i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (int64_t i = q * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    if (m == m) atomicMax(amax_bits, __float_as_uint(m));     // non-negative floats order like their bit patterns; NaN is dropped
+  }
+}
+// S = 2^(14 - e) with amax = m * 2^e, m in [0.5, 1); 1 for an all-zero / non-finite tensor
+__device__ __forceinline__ float grad_scale_from_amax(uint32_t amax_bits, float* inv) {
+  const float a = __uint_as_float(amax_bits);
+  if (!(a > 0.f) || !(a < 3.0e38f)) { *inv = 1.f; return 1.f; }
+  int e;
+  frexpf(a, &e);
+  int sh = 14 - e;
+  sh = sh > 120 ? 120 : (sh < -100 ? -100 : sh);
+  *inv = ldexpf(1.f, -sh);
+  return ldexpf(1.f, sh);
+}
+__global__ void __launch_bounds__(256) split_16_scaled_kernel(const float* __restrict__ x, uint16_t* __restrict__ planes, int64_t n,
+                                                              const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale) {
+  float inv;
+  const float S = grad_scale_from_amax(*amax_bits, &inv);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = inv;
+  const int64_t q = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg4(x + 4 * i);
+    store_16_planes<2>(planes, n, i, make_float4(v.x * S, v.y * S, v.z * S, v.w * S));
+  }
+}
+__global__ void __launch_bounds__(256) act_bwd_split_16_scaled_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                                      int act, float slope, float* __restrict__ g,
+                                                                      uint16_t* __restrict__ planes, int64_t n,
+                                                                      const uint32_t* __restrict__ amax_bits,
+                                                                      float* __restrict__ inv_scale) {
+  float inv;
+  const float S = grad_scale_from_amax(*amax_bits, &inv);       // amax of dy: |dy * act'(y)| <= |dy| for every activation on the path
+  if (blockIdx.x == 0 && threadIdx.x == 0) *inv_scale = inv;
+  const int64_t q = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 d = ldg4(dy + 4 * i), o = ldg4(y + 4 * i);
+    float4 v = make_float4(d.x * act_bwd_from_out(o.x, act, slope), d.y * act_bwd_from_out(o.y, act, slope),
+                           d.z * act_bwd_from_out(o.z, act, slope), d.w * act_bwd_from_out(o.w, act, slope));
+    if (g) stg4(g + 4 * i, v);
+    store_16_planes<2>(planes, n, i, make_float4(v.x * S, v.y * S, v.z * S, v.w * S));
   }
 }
 
@@ -725,6 +823,45 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     float* dl = fwd ? fwd_lo : bwd_lo;
     if (dh) dh[o] = h;
     if (dl) dl[o] = v - hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// channel concat of maps and broadcast vectors, zero-padded to a tensor-core-legal channel count, with optional 16-bit planes
+// ---------------------------------------------------------------------------------------------------------------
+struct ConcatParts {
+  const float* src[PVG_CONCAT_MAX_PARTS];
+  int64_t bstride[PVG_CONCAT_MAX_PARTS];      // elements between consecutive samples of the part
+  int off[PVG_CONCAT_MAX_PARTS + 1];          // first output channel of each part; off[nparts] = total real channels
+  int is_vec[PVG_CONCAT_MAX_PARTS];
+  int nparts;
+};
+__global__ void __launch_bounds__(256) concat_pad_kernel(const ConcatParts cp, int64_t rows, int HW, int Cpad, float* __restrict__ y,
+                                                         const PlaneOut po) {
+  const int U = Cpad / 4;
+  const int64_t total = rows * U;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / U;
+    const int c0 = (int)(i % U) * 4;
+    const int64_t n = r / HW, pix = r - n * HW;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      float val = 0.f;
+      for (int k = 0; k < cp.nparts; ++k) {
+        if (c >= cp.off[k] && c < cp.off[k + 1]) {
+          const int ck = cp.off[k + 1] - cp.off[k];
+          const float* sp = cp.src[k] + n * cp.bstride[k] + (cp.is_vec[k] ? 0 : pix * ck) + (c - cp.off[k]);
+          val = __ldg(sp);
+          break;
+        }
+      }
+      v[j] = val;
+    }
+    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    stg4(y + r * Cpad + c0, o);
+    emit_planes4(po, r * Cpad + c0, o);
   }
 }
 
@@ -842,13 +979,43 @@ int pvg_bn_eval_prepare(const float* running_mean, const float* running_var, int
   return 0;
 }
 
+static int planes_ok(const void* a, const void* b, int C) {
+  if ((a || b) && C % 8 != 0) { pvg::set_error("16-bit plane outputs need C % 8 == 0"); return 0; }
+  return 1;
+}
+
+int pvg_bn_apply_ex(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
+                    const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
+                    void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream) {
+  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  if (!planes_ok(planes_a, planes_b, C)) return -1;
+  int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
+  const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, M * C);
+  DISPATCH_V(C, (bn_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+                    x, M, rpg, C, mean, invstd, weight, bias, residual, act, slope, y, po)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
 int pvg_bn_apply(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
                  const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
                  void* stream) {
+  return pvg_bn_apply_ex(x, N, HW, C, groups, mean, invstd, weight, bias, residual, act, slope, y, nullptr, 0, nullptr, 0, stream);
+}
+
+int pvg_bn_finalize_apply_ex(const float* x, int N, int HW, int C, int groups, const double* sums, int64_t count, float eps,
+                             float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                             const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
+                             void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  if (!planes_ok(planes_a, planes_b, C)) return -1;
+  const size_t smem = (size_t)groups * C * 2 * sizeof(float);
+  PVG_CHECK_ARG(smem <= 48 * 1024, "groups * C too large for the fused kernel: call pvg_bn_finalize + pvg_bn_apply");
   int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
-  DISPATCH_V(C, (bn_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
-                    x, M, rpg, C, mean, invstd, weight, bias, residual, act, slope, y)));
+  const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, M * C);
+  DISPATCH_V(C, (bn_finalize_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, smem, (cudaStream_t)stream>>>(
+                    x, M, rpg, C, groups, sums, (double)count, eps, momentum, running_mean, running_var, mean, invstd, weight,
+                    bias, residual, act, slope, y, po)));
   PVG_LAUNCH_OK();
   return 0;
 }
@@ -857,15 +1024,8 @@ int pvg_bn_finalize_apply(const float* x, int N, int HW, int C, int groups, cons
                           float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                           const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
                           void* stream) {
-  PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
-  const size_t smem = (size_t)groups * C * 2 * sizeof(float);
-  PVG_CHECK_ARG(smem <= 48 * 1024, "groups * C too large for the fused kernel: call pvg_bn_finalize + pvg_bn_apply");
-  int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
-  DISPATCH_V(C, (bn_finalize_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, smem, (cudaStream_t)stream>>>(
-                    x, M, rpg, C, groups, sums, (double)count, eps, momentum, running_mean, running_var, mean, invstd, weight,
-                    bias, residual, act, slope, y)));
-  PVG_LAUNCH_OK();
-  return 0;
+  return pvg_bn_finalize_apply_ex(x, N, HW, C, groups, sums, count, eps, momentum, running_mean, running_var, mean, invstd, weight,
+                                  bias, residual, act, slope, y, nullptr, 0, nullptr, 0, stream);
 }
 
 int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, int HW, int C, int groups, const float* mean,
@@ -904,6 +1064,18 @@ int pvg_upsample2x_fwd(const float* x, int N, int H, int W, int C, float* y, voi
   return pvg_resize_bilinear(x, N, H, W, C, y, 2 * H, 2 * W, stream);
 }
 
+int pvg_resize_bilinear_ex(const float* x, int N, int H, int W, int C, float* y, int OH, int OW, void* planes_a, int fmt_a,
+                           void* planes_b, int fmt_b, void* stream) {
+  if (!planes_ok(planes_a, planes_b, C)) return -1;
+  int64_t total = (int64_t)N * OH * OW * C;
+  float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
+  const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, total);
+  DISPATCH_V(C, (resize_bilinear_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y, OH,
+                                                                                                    OW, sh, sw, po)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
 int pvg_upsample2x_bwd(const float* dy, int N, int H, int W, int C, float* dx, void* stream) {
   int64_t total = (int64_t)N * H * W * C;
   DISPATCH_V(C, (upsample2x_bwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(dy, N, H, W, C, dx)));
@@ -915,17 +1087,23 @@ int pvg_resize_bilinear(const float* x, int N, int H, int W, int C, float* y, in
   int64_t total = (int64_t)N * OH * OW * C;
   float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
   DISPATCH_V(C, (resize_bilinear_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y, OH,
-                                                                                                    OW, sh, sw)));
+                                                                                                    OW, sh, sw, no_planes())));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_maxpool2_fwd_ex(const float* x, int N, int H, int W, int C, float* y, void* planes_a, int fmt_a, void* stream) {
+  PVG_CHECK_ARG(H >= 2 && W >= 2, "max_pool2d(2) needs H, W >= 2");     // odd sizes floor, like nn.MaxPool2d
+  if (!planes_ok(planes_a, nullptr, C)) return -1;
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
+  const PlaneOut po = make_planes(planes_a, fmt_a, nullptr, 0, total);
+  DISPATCH_V(C, (maxpool2_fwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y, po)));
   PVG_LAUNCH_OK();
   return 0;
 }
 
 int pvg_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* y, void* stream) {
-  PVG_CHECK_ARG(H >= 2 && W >= 2, "max_pool2d(2) needs H, W >= 2");     // odd sizes floor, like nn.MaxPool2d
-  int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
-  DISPATCH_V(C, (maxpool2_fwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, y)));
-  PVG_LAUNCH_OK();
-  return 0;
+  return pvg_maxpool2_fwd_ex(x, N, H, W, C, y, nullptr, 0, stream);
 }
 
 int pvg_maxpool2_bwd(const float* dy, const float* x, const float* y, int N, int H, int W, int C, int relu_mask, float* dx,
@@ -934,6 +1112,26 @@ int pvg_maxpool2_bwd(const float* dy, const float* x, const float* y, int N, int
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
   DISPATCH_V(C, (maxpool2_bwd_kernel<V><<<ew_grid(total / V, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, y, N, H, W, C,
                                                                                                  relu_mask, dx)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_concat_pad(const pvg_concat_desc* d, float* y, void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream) {
+  PVG_CHECK_ARG(d && y && d->nparts >= 1 && d->nparts <= PVG_CONCAT_MAX_PARTS, "bad part count");
+  PVG_CHECK_ARG(d->Cpad % 4 == 0 && d->N > 0 && d->H > 0 && d->W > 0, "Cpad must be a multiple of 4");
+  if (!planes_ok(planes_a, planes_b, d->Cpad)) return -1;
+  ConcatParts cp;
+  int off = 0;
+  for (int k = 0; k < d->nparts; ++k) {
+    PVG_CHECK_ARG(d->src[k] && d->c[k] > 0, "empty part");
+    cp.src[k] = (const float*)d->src[k]; cp.bstride[k] = d->bstride[k]; cp.is_vec[k] = d->is_vec[k]; cp.off[k] = off;
+    off += d->c[k];
+  }
+  cp.off[d->nparts] = off; cp.nparts = d->nparts;
+  PVG_CHECK_ARG(off <= d->Cpad, "parts wider than Cpad");
+  const int64_t rows = (int64_t)d->N * d->H * d->W;
+  const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, rows * d->Cpad);
+  concat_pad_kernel<<<ew_grid(rows * (d->Cpad / 4), 256), 256, 0, (cudaStream_t)stream>>>(cp, rows, d->H * d->W, d->Cpad, y, po);
   PVG_LAUNCH_OK();
   return 0;
 }
@@ -1013,6 +1211,31 @@ int pvg_act_bwd_split_16(const float* dy, const float* y, int act, float slope, 
     act_bwd_split_16_kernel<1><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
   else
     act_bwd_split_16_kernel<0><<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_amax(const float* x, int64_t n, uint32_t* amax_bits, void* stream) {
+  PVG_CHECK_ARG(x && amax_bits && n > 0 && (((uintptr_t)x) & 15) == 0, "null / misaligned argument");
+  amax_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, n, amax_bits);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_split_16_scaled(const float* x, void* planes, int64_t n, const uint32_t* amax_bits, float* inv_scale, void* stream) {
+  PVG_CHECK_ARG(n % 8 == 0 && (((uintptr_t)x | (uintptr_t)planes) & 15) == 0 && amax_bits && inv_scale,
+                "n % 8 == 0, 16-byte aligned pointers and the amax / scale scalars are required");
+  split_16_scaled_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)planes, n, amax_bits, inv_scale);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_act_bwd_split_16_scaled(const float* dy, const float* y, int act, float slope, float* g, void* planes, int64_t n,
+                                const uint32_t* amax_bits, float* inv_scale, void* stream) {
+  PVG_CHECK_ARG(n % 8 == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)g | (uintptr_t)planes) & 15) == 0 && amax_bits && inv_scale,
+                "n % 8 == 0, 16-byte aligned pointers and the amax / scale scalars are required");
+  act_bwd_split_16_scaled_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n,
+                                                                                        amax_bits, inv_scale);
   PVG_LAUNCH_OK();
   return 0;
 }

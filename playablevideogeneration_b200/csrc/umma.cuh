@@ -291,6 +291,7 @@ struct ConvParams {
   int corr_fp16;                // NPROD == 2: the 16-bit correction planes are fp16 (else bf16)
   uint16_t* y_planes;           // conv_h3.cu, optional: fp16 plane pair [2][N*H*W*Cout] of y (PVG_CORR_FP16_ALL), written by the
   int64_t y_numel;              //   epilogue so that the next convolution needs no separate split pass; y_numel = N*H*W*Cout
+  const float* out_scale;       // conv_h3.cu, optional (device): accumulator scale (1 / S of a scaled gradient operand)
   int dbg;                      // conv_h3.cu timing experiments
 };
 

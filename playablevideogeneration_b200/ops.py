@@ -35,10 +35,12 @@ _precision = os.environ.get("PVG_PRECISION", "tf32x3")
 #   "h3": ALL three products as kind::f16 MMAs on fp16 plane pairs {f16((x - f16(x)) * 2^12), f16(x)} (PVG_CORR_FP16_ALL): the
 #           pair carries 22 bits of x, products are exact, accumulation is fp32 - the same arithmetic as TF32 + fp16
 #           corrections at 3/4 of its tensor time and half of its shared-memory traffic (the conv never reads the fp32 tensor).
-#           Needs operands inside fp16's range: forward activations and weights (default for "fwd"); not gradients.
+#           Needs operands inside fp16's range: forward activations and weights as they are; gradients after a per-tensor
+#           power-of-two scaling chosen from their largest magnitude (pvg_amax + pvg_split_16_scaled), undone by the kernel.
+#           "h3" for the backward roles takes effect when BOTH dgrad and wgrad select it (they share the scaled planes of dY).
 CORR_MODES = ("tf32", "bf16", "fp16", "h3")
-DEFAULT_CORR = {"fwd": os.environ.get("PVG_CORR", "h3"), "dgrad": os.environ.get("PVG_DGRAD_CORR", "bf16"),
-                "wgrad": os.environ.get("PVG_WGRAD_CORR", "bf16")}
+DEFAULT_CORR = {"fwd": os.environ.get("PVG_CORR", "h3"), "dgrad": os.environ.get("PVG_DGRAD_CORR", "h3"),
+                "wgrad": os.environ.get("PVG_WGRAD_CORR", "h3")}
 _corr = dict(DEFAULT_CORR)
 _tf32_truncates: Optional[bool] = None     # does tcgen05 kind::tf32 truncate raw fp32 operands? (probed lazily)
 
@@ -68,8 +70,8 @@ def _mode(role: str) -> Tuple[int, int]:
     if _precision != "tf32x3":
         return 1, 0
     c = _corr[role]
-    if c == "h3" and role == "wgrad":       # the weight-gradient kernel (MN-major operands) has no all-fp16 evaluation
-        c = "bf16"
+    if c == "h3" and role != "fwd" and not (_corr["dgrad"] == "h3" and _corr["wgrad"] == "h3"):
+        c = "bf16"                          # the scaled-gradient planes are shared by both backward kernels
     if c == "tf32" or (c != "h3" and not tf32_truncates()):
         return 3, 0
     return 2, {"fp16": _lib.CORR_FP16, "bf16": _lib.CORR_BF16, "h3": _lib.CORR_FP16_ALL}[c]
@@ -289,6 +291,47 @@ def tf32_truncates() -> bool:
     return _tf32_truncates
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# 16-bit operand planes that travel WITH a tensor: producers (BatchNorm apply, conv epilogue, max-pool, upsample, concat) can
+# write the plane pairs their consumer convolution needs in the same pass (``planes=`` arguments below); they are attached to
+# the returned tensor object as ``_pvg_planes = {format: planes}`` and picked up by ``conv2d``.  Any torch op in between
+# (reshape, slice, stack) simply drops the attribute and the consumer falls back to a pvg_split_16 pass.
+# ---------------------------------------------------------------------------------------------------------------
+def conv_input_planes(weight_grad: bool = True) -> Tuple[int, ...]:
+    """Plane formats a tensor-core convolution consuming a tensor will ask for under the current precision mode: the forward
+    operand format and, when its weight gradient will be taken, the weight-gradient operand format."""
+    if _precision != "tf32x3" or os.environ.get("PVG_NO_PRODUCER_PLANES") == "1":
+        return ()
+    out = []
+    n, f = _mode("fwd")
+    if n == 2:
+        out.append(f)
+    if weight_grad and torch.is_grad_enabled():
+        n, f = _mode("wgrad")
+        if n == 2 and f not in out:
+            out.append(f)
+    return tuple(out)
+
+
+def planes_of(t: Tensor) -> dict:
+    return getattr(t, "_pvg_planes", None) or {}
+
+
+def _attach_planes(t: Tensor, fmts: Sequence[int], planes: Sequence[Optional[Tensor]]) -> Tensor:
+    d = {f: p for f, p in zip(fmts, planes) if p is not None}
+    if d:
+        t._pvg_planes = d
+    return t
+
+
+def _alloc_planes(fmts: Sequence[int], numel: int, channels: int, device) -> List[Optional[Tensor]]:
+    """(up to two) plane-pair buffers for a producer kernel; none when the channel count breaks the 16-byte TMA stride rule."""
+    if channels % 8 != 0:
+        return [None, None]
+    out = [torch.empty((2 * numel,), dtype=_plane_dtype(f), device=device) for f in list(fmts)[:2]]
+    return out + [None] * (2 - len(out))
+
+
 conv_profile = None     # bench.py sets this to a list: (start_event, end_event, algorithmic_flops, kernel family) per tensor-core conv launch
 
 
@@ -345,8 +388,13 @@ class Conv2dFn(torch.autograd.Function):
     count (zero-padded concat buffers)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, slope):
+    def forward(ctx, x, weight, bias, act, slope, x_planes, out_planes):
+        """``x_planes``: {format: planes} that came with x (may be empty); ``out_planes``: also return the forward-operand
+        plane pair of y (all-fp16 forward kernel only)."""
+        x_in = x
         x = nhwc(x)
+        if x is not x_in:
+            x_planes = {}
         _check_cuda(weight)
         cout, cin_log, r, s = weight.shape
         cin_p = x.shape[1]
@@ -356,13 +404,41 @@ class Conv2dFn(torch.autograd.Function):
         packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
         b = bias.detach().contiguous() if bias is not None else None
         flops = 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * cout * r * s * cin_log
-        y = _conv_forward(x, packs, 0, cout, r, b, act, slope, algo, nprod, fmt, flops)
+        y_planes = None
+        xp_used = None
+        if algo == ALGO_UMMA and nprod == 2 and fmt == _lib.CORR_FP16_ALL:
+            # all-fp16 forward conv straight from plane pairs (and, on request, to the plane pair of y)
+            xp = xp_used = x_planes[fmt] if fmt in x_planes else _split(x, nprod, fmt)[1]
+            n, _, h, w = x.shape
+            y = empty_nhwc((n, cout, h, w), x.device)
+            if out_planes and cout % 8 == 0:
+                y_planes = torch.empty((2 * y.numel(),), dtype=torch.float16, device=x.device)
+            d = ConvDesc(n, h, w, cin_p, cout, r, r, (r - 1) // 2, act, float(slope), ALGO_UMMA, 2, fmt)
+            prof = conv_profile is not None
+            if prof:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            call("pvg_conv2d_fwd_planes", d, xp.data_ptr(), packs.lo(0, 2, fmt).data_ptr(), _p(b), y.data_ptr(), _p(y_planes), None,
+                 _stream())
+            if prof:
+                e1.record()
+                conv_profile.append((e0, e1, flops, "h3"))
+        else:
+            split = (x, x_planes[fmt]) if (algo == ALGO_UMMA and nprod == 2 and fmt in x_planes) else None
+            y = _conv_forward(x, packs, 0, cout, r, b, act, slope, algo, nprod, fmt, flops, split=split)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.meta = (act, slope, bias is not None, cin_log)
-        return y
+        wm = _mode("wgrad")
+        ctx.x_wplanes = x_planes.get(wm[1]) if wm[0] == 2 else None      # weight-gradient operand planes that came with x
+        if ctx.x_wplanes is None and wm == (2, _lib.CORR_FP16_ALL) and xp_used is not None and weight.requires_grad:
+            ctx.x_wplanes = xp_used          # the forward operand planes double as the weight-gradient operand
+        ctx.x_wfmt = wm[1]
+        if y_planes is not None:
+            ctx.mark_non_differentiable(y_planes)
+        return y, y_planes
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dy_planes=None):
         x, weight, y = ctx.saved_tensors
         act, slope, has_bias, cin_log = ctx.meta
         cout, _, r, s = weight.shape
@@ -370,6 +446,16 @@ class Conv2dFn(torch.autograd.Function):
         dy = nhwc(dy)
         dmode = _mode("dgrad")            # (nprod, fmt) of the data-gradient kernel (conv_umma.cu)
         wmode = _mode("wgrad")            # ... of the weight-gradient kernel (conv_wgrad_umma.cu)
+        H3 = (2, _lib.CORR_FP16_ALL)
+        if dmode == H3 or wmode == H3:
+            if (dmode == H3 and wmode == H3 and cin_p % _TC_CIN_MULTIPLE == 0 and cout % 8 == 0 and _precision == "tf32x3"
+                    and not (cin_p <= 4 and r <= 7) and not (r == 7 and cout <= 3)):
+                return Conv2dFn._backward_h3(ctx, dy, x, weight, y)
+            # shapes the all-fp16 kernels do not take (image-facing layers, channel counts that are not a multiple of 8):
+            # TF32 main product + bf16 corrections
+            BF = (2, _lib.CORR_BF16)
+            dmode = BF if dmode == H3 else dmode
+            wmode = BF if wmode == H3 else wmode
         want_dx = ctx.needs_input_grad[0] and cout % _TC_CIN_MULTIPLE == 0 and dmode[0] >= 2
         want_dw = ctx.needs_input_grad[1] and cin_p % _TC_CIN_MULTIPLE == 0 and cout % 4 == 0 and wmode[0] >= 2
         g_splits = {}                     # (nprod, fmt) -> (hi, lo) of g
@@ -400,6 +486,8 @@ class Conv2dFn(torch.autograd.Function):
 
         if ctx.needs_input_grad[0]:
             algo, np_, fmt_ = _conv_algo(cout, cin_p, r, "dgrad")
+            if algo == ALGO_UMMA and (np_, fmt_) == H3:
+                np_, fmt_ = dmode
             packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
             # data gradient = "same" convolution of g with the tap-flipped, transposed pack [CinP][R][S][Cout]
             dx = _conv_forward(g, packs, 2, cin_p, r, None, ACT_NONE, 0.0, algo, np_, fmt_,
@@ -429,7 +517,10 @@ class Conv2dFn(torch.autograd.Function):
                     g4, dw4 = g, dw
                     g_pair = split_g(wmode) if nprod >= 2 else (g, None)
                 scratch = zero_pool.zeros((cout4 * r * s * _pad32(cin_p),), torch.float32, dy.device)
-                x_hi, x_lo = _split(x, nprod, wfmt) if nprod >= 2 else (x, None)
+                if nprod == 2 and ctx.x_wplanes is not None and ctx.x_wfmt == wfmt:
+                    x_hi, x_lo = x, ctx.x_wplanes                  # written by x's producer in the forward pass
+                else:
+                    x_hi, x_lo = _split(x, nprod, wfmt) if nprod >= 2 else (x, None)
                 g_hi, g_lo = g_pair
                 prof = wgrad_profile is not None
                 if prof:
@@ -448,11 +539,76 @@ class Conv2dFn(torch.autograd.Function):
             db = torch.empty((cout,), dtype=torch.float32, device=dy.device)
             scratch = torch.empty((cout,), dtype=torch.float64, device=dy.device)
             call("pvg_channel_sum", g.data_ptr(), n * h * w, cout, scratch.data_ptr(), db.data_ptr(), _stream())
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0) -> Tensor:
-    return Conv2dFn.apply(x, weight, bias, act, slope)
+def _backward_h3(ctx, dy, x, weight, y):
+    """Data and weight gradient as all-fp16 split products (conv_h3.cu with the flipped pack; conv_wgrad_umma.cu NPROD = 4):
+    dY is scaled by a power of two chosen from max|dY| so that its fp16 plane pair is exact to 22 bits, both kernels undo the
+    scale; x is consumed through the very planes the forward convolution read."""
+    act, slope, has_bias, cin_log = ctx.meta
+    cout, _, r, s = weight.shape
+    n, cin_p, h, w = x.shape
+    dev = dy.device
+    st = _stream()
+    amax = zero_pool.zeros((1,), torch.int32, dev)
+    inv = torch.empty((1,), dtype=torch.float32, device=dev)
+    planes = torch.empty((2 * dy.numel(),), dtype=torch.float16, device=dev)
+    call("pvg_amax", dy.data_ptr(), dy.numel(), amax.data_ptr(), st)
+    need_g = has_bias and ctx.needs_input_grad[2]
+    if act != ACT_NONE:
+        g = torch.empty_like(dy) if need_g else None
+        call("pvg_act_bwd_split_16_scaled", dy.data_ptr(), y.data_ptr(), act, float(slope), _p(g), planes.data_ptr(), dy.numel(),
+             amax.data_ptr(), inv.data_ptr(), st)
+    else:
+        g = dy
+        call("pvg_split_16_scaled", dy.data_ptr(), planes.data_ptr(), dy.numel(), amax.data_ptr(), inv.data_ptr(), st)
+    dx = dw = db = None
+    packs = _get_packs(weight, cin_p, True)
+    if ctx.needs_input_grad[0]:
+        dx = empty_nhwc((n, cin_p, h, w), dev)
+        d = ConvDesc(n, h, w, cout, cin_p, r, r, (r - 1) // 2, ACT_NONE, 0.0, ALGO_UMMA, 2, _lib.CORR_FP16_ALL)
+        prof = conv_profile is not None
+        if prof:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        call("pvg_conv2d_fwd_planes", d, planes.data_ptr(), packs.lo(2, 2, _lib.CORR_FP16_ALL).data_ptr(), None, dx.data_ptr(), None,
+             inv.data_ptr(), st)
+        if prof:
+            e1.record()
+            conv_profile.append((e0, e1, 2.0 * n * h * w * cout * r * s * cin_log, "h3"))
+    if ctx.needs_input_grad[1]:
+        xp = ctx.x_wplanes if ctx.x_wplanes is not None else _split(x, 2, _lib.CORR_FP16_ALL)[1]
+        dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        scratch = zero_pool.zeros((cout * r * s * _pad32(cin_p),), torch.float32, dev)
+        d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_UMMA, 2, _lib.CORR_FP16_ALL)
+        prof = wgrad_profile is not None
+        if prof:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        call("pvg_conv2d_wgrad_planes", d, cin_log, xp.data_ptr(), planes.data_ptr(), inv.data_ptr(), scratch.data_ptr(),
+             dw.data_ptr(), 0, st)
+        if prof:
+            e1.record()
+            wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout * r * s * cin_log))
+    if need_g:
+        db = torch.empty((cout,), dtype=torch.float32, device=dev)
+        scr = torch.empty((cout,), dtype=torch.float64, device=dev)
+        call("pvg_channel_sum", g.data_ptr(), n * h * w, cout, scr.data_ptr(), db.data_ptr(), st)
+    return dx, dw, db, None, None, None, None
+
+
+Conv2dFn._backward_h3 = staticmethod(_backward_h3)
+
+
+def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0,
+           out_planes: bool = False) -> Tensor:
+    """``out_planes``: the consumer of the result is another tensor-core convolution - have the epilogue write its operand planes."""
+    want = bool(out_planes) and _lib.CORR_FP16_ALL in conv_input_planes(False)
+    y, yp = Conv2dFn.apply(x, weight, bias, act, slope, planes_of(x), want)
+    if yp is not None:
+        y._pvg_planes = {_lib.CORR_FP16_ALL: yp}
+    return y
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -461,7 +617,7 @@ def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = 
 class PoolBNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, pool, act, slope, eps, momentum,
-                groups):
+                groups, plane_fmts=()):
         x = nhwc(x)
         n, c, h, w = x.shape
         dev = x.device
@@ -480,12 +636,15 @@ class PoolBNActFn(torch.autograd.Function):
             if training:
                 call("pvg_bn_stats", x.data_ptr(), n, h * w, c, groups, sums.data_ptr(), st)
         y = empty_nhwc((n, c, oh, ow), dev)
+        pa, pb = _alloc_planes(plane_fmts, y.numel(), c, dev)
+        fa = plane_fmts[0] if len(plane_fmts) > 0 else 0
+        fb = plane_fmts[1] if len(plane_fmts) > 1 else 0
         wd = weight.detach() if weight is not None else None
         bd = bias.detach() if bias is not None else None
         if training and groups * c * 8 <= 48 * 1024:      # statistics finalisation fused into the apply pass
-            call("pvg_bn_finalize_apply", xp.data_ptr(), n, oh * ow, c, groups, sums.data_ptr(), (n // groups) * oh * ow,
+            call("pvg_bn_finalize_apply_ex", xp.data_ptr(), n, oh * ow, c, groups, sums.data_ptr(), (n // groups) * oh * ow,
                  float(eps), float(momentum), _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), _p(wd),
-                 _p(bd), _p(residual), act, float(slope), y.data_ptr(), st)
+                 _p(bd), _p(residual), act, float(slope), y.data_ptr(), _p(pa), fa, _p(pb), fb, st)
         else:
             if training:
                 call("pvg_bn_finalize", sums.data_ptr(), (n // groups) * oh * ow, groups, c, float(eps), float(momentum),
@@ -495,14 +654,17 @@ class PoolBNActFn(torch.autograd.Function):
                     raise _lib.PvgError("grouped statistics only exist in training mode")
                 call("pvg_bn_eval_prepare", running_mean.data_ptr(), running_var.data_ptr(), c, float(eps), mean.data_ptr(),
                      invstd.data_ptr(), st)
-            call("pvg_bn_apply", xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(), invstd.data_ptr(), _p(wd), _p(bd),
-                 _p(residual), act, float(slope), y.data_ptr(), st)
+            call("pvg_bn_apply_ex", xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(), invstd.data_ptr(), _p(wd), _p(bd),
+                 _p(residual), act, float(slope), y.data_ptr(), _p(pa), fa, _p(pb), fb, st)
         ctx.save_for_backward(xp, weight, mean, invstd, y if act != ACT_NONE else None)
         ctx.meta = (training, pool, act, slope, groups, residual is not None, (n, c, h, w))
-        return y
+        for t in (pa, pb):
+            if t is not None:
+                ctx.mark_non_differentiable(t)
+        return y, pa, pb
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dpa=None, _dpb=None):
         xp, weight, mean, invstd, y = ctx.saved_tensors
         training, pool, act, slope, groups, has_res, (n, c, h, w) = ctx.meta
         dy = nhwc(dy)
@@ -531,16 +693,19 @@ class PoolBNActFn(torch.autograd.Function):
                  st)                  # dweight / dbias: the parameter gradients ride along in the same launch
         elif need_params:
             call("pvg_bn_bwd_params", sums2.data_ptr(), groups, c, dweight.data_ptr(), dbias.data_ptr(), st)
-        return (dx, dweight, dbias, g_out) + (None,) * 9
+        return (dx, dweight, dbias, g_out) + (None,) * 10
 
 
-def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, groups=1):
-    """``bn`` is an nn.BatchNorm2d used purely as the parameter/buffer container (reference state_dict names)."""
+def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, groups=1, planes: Sequence[int] = ()):
+    """``bn`` is an nn.BatchNorm2d used purely as the parameter/buffer container (reference state_dict names).
+    ``planes``: plane formats (``conv_input_planes()``) the apply pass writes next to y for the convolution that consumes it."""
     training = bn.training
     if training and bn.num_batches_tracked is not None:
         defer_count(bn.num_batches_tracked, groups)         # applied by flush_deferred() at the end of Model.forward
-    return PoolBNActFn.apply(x, bn.weight, bias_or_none(bn), residual, bn.running_mean, bn.running_var, training, pool, act,
-                             slope, bn.eps, bn.momentum if bn.momentum is not None else 0.1, groups)
+    planes = tuple(planes)[:2]
+    y, pa, pb = PoolBNActFn.apply(x, bn.weight, bias_or_none(bn), residual, bn.running_mean, bn.running_var, training, pool, act,
+                                  slope, bn.eps, bn.momentum if bn.momentum is not None else 0.1, groups, planes)
+    return _attach_planes(y, planes, (pa, pb))
 
 
 def bias_or_none(m):
@@ -554,25 +719,32 @@ class Upsample2xFn(torch.autograd.Function):
     """F.interpolate(scale_factor=2, mode='bilinear', align_corners=False), model/layers/up_block.py:35,43."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, plane_fmts=()):
         x = nhwc(x)
         n, c, h, w = x.shape
         y = empty_nhwc((n, c, 2 * h, 2 * w), x.device)
-        call("pvg_upsample2x_fwd", x.data_ptr(), n, h, w, c, y.data_ptr(), _stream())
+        pa, pb = _alloc_planes(plane_fmts, y.numel(), c, x.device)
+        call("pvg_resize_bilinear_ex", x.data_ptr(), n, h, w, c, y.data_ptr(), 2 * h, 2 * w, _p(pa),
+             plane_fmts[0] if len(plane_fmts) > 0 else 0, _p(pb), plane_fmts[1] if len(plane_fmts) > 1 else 0, _stream())
         ctx.shape = (n, c, h, w)
-        return y
+        for t in (pa, pb):
+            if t is not None:
+                ctx.mark_non_differentiable(t)
+        return y, pa, pb
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dpa=None, _dpb=None):
         n, c, h, w = ctx.shape
         dy = nhwc(dy)
         dx = empty_nhwc((n, c, h, w), dy.device)
         call("pvg_upsample2x_bwd", dy.data_ptr(), n, h, w, c, dx.data_ptr(), _stream())
-        return dx
+        return dx, None
 
 
-def upsample2x(x: Tensor) -> Tensor:
-    return Upsample2xFn.apply(x)
+def upsample2x(x: Tensor, planes: Sequence[int] = ()) -> Tensor:
+    planes = tuple(planes)[:2]
+    y, pa, pb = Upsample2xFn.apply(x, planes)
+    return _attach_planes(y, planes, (pa, pb))
 
 
 def resize_bilinear(x: Tensor, size: Tuple[int, int]) -> Tensor:
@@ -588,16 +760,20 @@ class MaxPool2Fn(torch.autograd.Function):
     """nn.MaxPool2d(2, 2) of torchvision VGG19 (model/layers/vgg.py:16)."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, plane_fmts=()):
         x = nhwc(x)
         n, c, h, w = x.shape
         y = empty_nhwc((n, c, h // 2, w // 2), x.device)
-        call("pvg_maxpool2_fwd", x.data_ptr(), n, h, w, c, y.data_ptr(), _stream())
+        pa, _ = _alloc_planes(plane_fmts[:1], y.numel(), c, x.device)
+        call("pvg_maxpool2_fwd_ex", x.data_ptr(), n, h, w, c, y.data_ptr(), _p(pa), plane_fmts[0] if len(plane_fmts) > 0 else 0,
+             _stream())
         ctx.save_for_backward(x, y)
-        return y
+        if pa is not None:
+            ctx.mark_non_differentiable(pa)
+        return y, pa
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dpa=None):
         x, y = ctx.saved_tensors
         n, c, h, w = x.shape
         dy = nhwc(dy)
@@ -605,11 +781,13 @@ class MaxPool2Fn(torch.autograd.Function):
         if (h % 2) or (w % 2):
             dx.zero_()
         call("pvg_maxpool2_bwd", dy.data_ptr(), x.data_ptr(), y.data_ptr(), n, h, w, c, 0, dx.data_ptr(), _stream())
-        return dx
+        return dx, None
 
 
-def maxpool2(x: Tensor) -> Tensor:
-    return MaxPool2Fn.apply(x)
+def maxpool2(x: Tensor, planes: Sequence[int] = ()) -> Tensor:
+    planes = tuple(planes)[:1]
+    y, pa = MaxPool2Fn.apply(x, planes)
+    return _attach_planes(y, planes, (pa,))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -649,44 +827,59 @@ class ConcatPadFn(torch.autograd.Function):
     tensor-core A operand (K chunks of 32 channels)."""
 
     @staticmethod
-    def forward(ctx, c_pad, *parts):
+    def forward(ctx, c_pad, plane_fmts, *parts):
         ref = next(p for p in parts if p.dim() == 4)
         n, _, h, w = ref.shape
         out = empty_nhwc((n, c_pad, h, w), ref.device)
-        off = 0
-        spans = []
-        for p in parts:
+        if len(parts) > _lib.ConcatDesc.MAX_PARTS:
+            raise _lib.PvgError("too many parts for one concat")
+        d = _lib.ConcatDesc()
+        d.N, d.H, d.W, d.Cpad, d.nparts = n, h, w, c_pad, len(parts)
+        keep, spans, off = [], [], 0
+        for k, p in enumerate(parts):
+            _check_cuda(p)
             c = p.shape[1]
+            q = p.detach()
             if p.dim() == 4:
-                out[:, off:off + c].copy_(p)
-            else:
-                out[:, off:off + c].copy_(p.detach()[:, :, None, None].expand(n, c, h, w))
+                # a map is consumed in place when every sample is NHWC-dense (the batch stride is free: time slices of (B, T, ...))
+                if not (c == 1 or q.stride()[1] == 1) or q.stride()[2] != w * c or q.stride()[3] != c:
+                    q = nhwc(q)
+            elif q.stride(1) != 1:
+                q = q.contiguous()
+            keep.append(q)
+            d.c[k], d.is_vec[k], d.bstride[k], d.src[k] = c, 0 if p.dim() == 4 else 1, q.stride(0), q.data_ptr()
             spans.append((off, c, p.dim()))
             off += c
         if off > c_pad:
             raise _lib.PvgError("concat wider than its padded size")
-        if off < c_pad:
-            out[:, off:].zero_()
+        pa, pb = _alloc_planes(plane_fmts, out.numel(), c_pad, ref.device)
+        call("pvg_concat_pad", d, out.data_ptr(), _p(pa), plane_fmts[0] if len(plane_fmts) > 0 else 0, _p(pb),
+             plane_fmts[1] if len(plane_fmts) > 1 else 0, _stream())
         ctx.spans = spans
-        return out
+        for t in (pa, pb):
+            if t is not None:
+                ctx.mark_non_differentiable(t)
+        return out, pa, pb
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dpa=None, _dpb=None):
         grads = []
         for i, (off, c, dim) in enumerate(ctx.spans):
-            if not ctx.needs_input_grad[i + 1]:
+            if not ctx.needs_input_grad[i + 2]:
                 grads.append(None)
             elif dim == 4:
                 grads.append(dout[:, off:off + c])
             else:
                 grads.append(dout[:, off:off + c].sum(dim=(2, 3)))
-        return (None,) + tuple(grads)
+        return (None, None) + tuple(grads)
 
 
-def concat_pad(parts: Sequence[Tensor], multiple: int = 32) -> Tensor:
+def concat_pad(parts: Sequence[Tensor], multiple: int = 32, planes: Sequence[int] = ()) -> Tensor:
     total = sum(p.shape[1] for p in parts)
     c_pad = (total + multiple - 1) // multiple * multiple
-    return ConcatPadFn.apply(c_pad, *parts)
+    planes = tuple(planes)[:2]
+    y, pa, pb = ConcatPadFn.apply(c_pad, planes, *parts)
+    return _attach_planes(y, planes, (pa, pb))
 
 
 # ---------------------------------------------------------------------------------------------------------------

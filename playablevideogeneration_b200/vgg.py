@@ -66,14 +66,18 @@ class Vgg19(nn.Module):
 
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
         feats = []
+        convs = [v for v in CFG if v != "M"]
+        fwd_planes = ops.conv_input_planes(weight_grad=False)      # frozen weights: only the forward operand format
         it = iter(CONV_IDX)
-        for v in CFG:
+        for pos, v in enumerate(CFG):
             if v == "M":
-                x = ops.maxpool2(x)
+                x = ops.maxpool2(x, planes=fwd_planes)              # every pool of VGG19 is followed by a convolution
                 continue
             idx = next(it)
             conv = self.convs[str(idx)]
-            x = ops.conv2d(x, conv.weight, conv.bias, act=ACT_RELU)
+            next_is_conv = pos + 1 < len(CFG) and CFG[pos + 1] != "M"
+            # conv -> ReLU -> conv chains: the epilogue writes the next convolution's fp16 operand planes itself
+            x = ops.conv2d(x, conv.weight, conv.bias, act=ACT_RELU, out_planes=next_is_conv)
             if idx in TAPS:
                 feats.append(x)
         return feats

@@ -20,12 +20,12 @@ def _act(x, act, slope):
     return x
 
 
-def conv2d(x, weight, bias=None, act=ACT_NONE, slope=0.0):
+def conv2d(x, weight, bias=None, act=ACT_NONE, slope=0.0, out_planes=False):
     cin = weight.shape[1]
     return _act(F.conv2d(x[:, :cin], weight, bias, padding=weight.shape[2] // 2), act, slope)
 
 
-def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, groups=1):
+def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, groups=1, planes=()):
     assert groups == 1
     if pool:
         x = F.avg_pool2d(x, 2)
@@ -35,7 +35,7 @@ def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, group
     return _act(y, act, slope)
 
 
-def upsample2x(x):
+def upsample2x(x, planes=()):
     return F.interpolate(x, scale_factor=2, mode="bilinear")
 
 
@@ -43,7 +43,7 @@ def resize_bilinear(x, size):
     return F.interpolate(x.detach(), size, mode="bilinear")
 
 
-def maxpool2(x):
+def maxpool2(x, planes=()):
     return F.max_pool2d(x, 2)
 
 
@@ -53,7 +53,7 @@ def lstm_cell(gates, c_prev):
     return torch.sigmoid(o) * torch.tanh(c), c
 
 
-def concat_pad(parts, multiple=32):
+def concat_pad(parts, multiple=32, planes=()):
     ref = next(p for p in parts if p.dim() == 4)
     h, w = ref.shape[2:]
     exp = [p if p.dim() == 4 else p[:, :, None, None].expand(-1, -1, h, w) for p in parts]
@@ -83,4 +83,5 @@ def install(monkeypatch):
                  "absdiff_mean", "adam_step"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "nhwc", lambda x: x)
+    monkeypatch.setattr(ops, "conv_input_planes", lambda weight_grad=True: ())
     monkeypatch.setattr(losses, "_global_l1", lambda gt, rec: F.l1_loss(rec, gt))

@@ -336,6 +336,51 @@ def test_concat_pad():
     _close("concat_da", ag.grad, a.grad, 0.0, 0.0)
 
 
+def test_producer_planes_equal_a_split_pass():
+    """Producers that write the 16-bit operand planes of their result next to it (BatchNorm apply, conv epilogue, max-pool,
+    bilinear upsample, channel concat) must write exactly what a separate pvg_split_16 pass over the result would."""
+    ops = _ops()
+    from playablevideogeneration_b200 import _lib
+    fmts = (_lib.CORR_FP16_ALL, _lib.CORR_BF16)
+
+    def check(name, y):
+        got = ops.planes_of(y)
+        assert got, name
+        for f, pl in got.items():
+            ref = ops._split(y.detach(), 2, f)[1]
+            assert torch.equal(pl.view(torch.int16), ref.view(torch.int16)), (name, f)
+
+    x = _rand(4, 64, 12, 20, seed=1).to(DEV)
+    bn = torch.nn.BatchNorm2d(64).to(DEV).train()
+    check("bn_train", ops.pool_bn_act(x, bn, pool=True, act=ops.ACT_LRELU, planes=fmts))
+    res = _rand(4, 64, 12, 20, seed=2).to(DEV)
+    check("bn_eval_res", ops.pool_bn_act(x, bn.eval(), residual=res, act=ops.ACT_LRELU, planes=fmts))
+    check("upsample", ops.upsample2x(x, planes=fmts))
+    check("maxpool", ops.maxpool2(x, planes=fmts[:1]))
+    a, v, hdd = _rand(2, 64, 4, 6, seed=1).to(DEV), _rand(2, 9, seed=2).to(DEV), _rand(2, 128, 4, 6, seed=3).to(DEV)
+    check("concat", ops.concat_pad([a, v, hdd], planes=fmts))
+    wt = _rand(72, 64, 3, 3, seed=4, scale=0.05).to(DEV)
+    y = ops.conv2d(ops.nhwc(x), wt, act=ops.ACT_RELU, out_planes=True)
+    assert list(ops.planes_of(y)) == [_lib.CORR_FP16_ALL]
+    check("conv_epilogue", y)
+    # and a consumer fed by producer planes gives the result of the split path, bit for bit
+    wt2 = _rand(32, 72, 3, 3, seed=5, scale=0.05).to(DEV)
+    z_planes = ops.conv2d(y, wt2)
+    z_split = ops.conv2d(y.detach().clone(), wt2)
+    assert torch.equal(z_planes, z_split)
+
+
+def test_concat_pad_strided_time_slices():
+    """Maps handed to the concat as time slices of a (B, T, C, H, W) tensor (batch-strided, NHWC-dense per sample) are read in
+    place."""
+    ops = _ops()
+    seq = ops.empty_nhwc((3 * 5, 64, 4, 6), DEV).normal_().reshape(3, 5, 64, 4, 6)
+    v = _rand(3, 9, seed=2).to(DEV)
+    got = ops.concat_pad([seq[:, 2], v])
+    ref = torch.cat([seq[:, 2], v[:, :, None, None].expand(-1, -1, 4, 6)], dim=1)
+    assert got.shape == (3, 96, 4, 6) and torch.equal(got[:, :73], ref) and float(got[:, 73:].abs().max()) == 0.0
+
+
 def test_absdiff_mean():
     ops = _ops()
     a, b = _rand(5, 64, 9, 7, seed=1), _rand(5, 64, 9, 7, seed=2).requires_grad_(True)

@@ -4,7 +4,7 @@ import os, sys, json, random, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from oracle.cases import build_config
+from playablevideogeneration_b200.configs import build_config
 from playablevideogeneration_b200 import _lib, ops
 from playablevideogeneration_b200.caddy import Model
 from playablevideogeneration_b200.training.step import TrainStep
@@ -17,7 +17,7 @@ dev = torch.device("cuda")
 cfg = build_config(dict(config=w["config"], H=w["H"], W=w["W"], S=w["S"]))
 torch.manual_seed(0); random.seed(0)
 model = Model(cfg).to(dev)
-vgg = Vgg19()
+vgg = Vgg19(allow_random_init=True)
 step = TrainStep(cfg, model, vgg)
 batch = tuple(t.to(dev) for t in bench.synthetic_batch(w))
 for _ in range(2):
