@@ -97,32 +97,42 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
 
   if (warp == 0) {
     const uint32_t leader = elect_one();      // see umma.cuh: single-lane issue without per-instruction election loops
+    // Everything that does not change from stage to stage is decoded ONCE: the (tap, chunk) of this CTA's four row groups and
+    // the patch coordinates, which then advance incrementally.  (ncu, round 2: with the integer divisions inside the loop -
+    // ~11 per stage, each a MUFU.RCP sequence - the producer warp needed ~2000 clk per stage and the MMA warp spent 55 % of
+    // its time waiting for data: tensor pipe 5 % active on the 64->32 @256^2 layer.)
+    int gc0[4], gdw[4], gdh[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int gi = g0 + g;
+      const bool ok = gi < p.groups;
+      const int tap = ok ? gi / p.chunks : 0, cc = ok ? gi - tap * p.chunks : 0;
+      const int r = tap / p.S, sx = tap - r * p.S;
+      gc0[g] = ok ? cc * 32 : p.CinP;                  // a group past the end loads an all-out-of-bounds (zero) box
+      gdw[g] = sx - p.pad; gdh[g] = r - p.pad;
+    }
+    int t0 = p_begin;
+    int pw = t0 % p.tiles_w; t0 /= p.tiles_w;
+    int ph = t0 % p.tiles_h;
+    int pn = t0 / p.tiles_h;
     int stage = 0; uint32_t phase = 0;
     for (int it = 0; it < iters; ++it) {
-      int t = p_begin + it;
-      const int pw = t % p.tiles_w; t /= p.tiles_w;
-      const int ph = t % p.tiles_h; t /= p.tiles_h;
-      const int w0 = pw * p.tw, h0 = ph * p.th, n0 = t * p.tn;
+      const int w0 = pw * p.tw, h0 = ph * p.th, n0 = pn * p.tn;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (leader) {
         uint8_t* st = smem + stage * C::kStageBytes;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int gi = g0 + g;
-          const bool ok = gi < p.groups;
-          const int tap = ok ? gi / p.chunks : 0, cc = ok ? gi - tap * p.chunks : 0;
-          const int r = tap / p.S, s = tap - r * p.S;
-          const int c0 = ok ? cc * 32 : p.CinP;                  // a group past the end loads an all-out-of-bounds (zero) box
           if (NPROD == 4) {
-            tma_load_5d(st + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+            tma_load_5d(st + g * kBoxBytes, &tmXlo, &full_bar[stage], gc0[g], w0 + gdw[g], h0 + gdh[g], n0, 0);
             continue;
           }
-          tma_load_4d(st + g * kBoxBytes, &tmX, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
+          tma_load_4d(st + g * kBoxBytes, &tmX, &full_bar[stage], gc0[g], w0 + gdw[g], h0 + gdh[g], n0);
           if (NPROD == 3)
-            tma_load_4d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0);
+            tma_load_4d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], gc0[g], w0 + gdw[g], h0 + gdh[g], n0);
           if (NPROD == 2)     // [f16(lo * 2^12) 32 px x 64 B | f16(x) 32 px x 64 B] of this channel group
-            tma_load_5d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], c0, w0 + s - p.pad, h0 + r - p.pad, n0, 0);
+            tma_load_5d(st + C::kABytes + g * kBoxBytes, &tmXlo, &full_bar[stage], gc0[g], w0 + gdw[g], h0 + gdh[g], n0, 0);
         }
         uint8_t* sb = st + C::kPlanes * C::kABytes;
 #pragma unroll
@@ -138,6 +148,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
       }
       __syncwarp();
       if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      if (++pw == p.tiles_w) { pw = 0; if (++ph == p.tiles_h) { ph = 0; ++pn; } }
     }
   } else if (warp == 1) {
     const uint32_t leader = elect_one();

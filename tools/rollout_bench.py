@@ -4,7 +4,7 @@ metric: generated frames/s).  usage: python tools/rollout_bench.py [batch] [step
 import os, sys, json, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle.cases import build_config
+from playablevideogeneration_b200.configs import build_config
 from playablevideogeneration_b200 import ops
 from playablevideogeneration_b200.caddy import Model
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64

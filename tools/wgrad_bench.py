@@ -26,7 +26,7 @@ for name, n, cin, cout, h, w, k in SHAPES:
         y = ops.conv2d(x, wt)
         y.backward(g)
     torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b, _ in ops.wgrad_profile)
+    ms = sorted(a.elapsed_time(b) for a, b, _ in ops.wgrad_profile) or [float("nan")]
     ops.wgrad_profile = None
     flops = 2.0 * n * h * w * cout * k * k * cin
     print(f"{name:28s} wgrad {ms[len(ms)//2]:8.3f} ms  {flops / ms[len(ms)//2] / 1e9:7.1f} TFLOP/s (algorithmic) [{prec}]", flush=True)
