@@ -96,6 +96,10 @@ int pvg_conv2d_wgrad_planes(const pvg_conv_desc* d, int Cin_logical, const void*
  * consumers) else w (SIMT consumers); any output pointer may be NULL. */
 int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinRows, int CinK, int CoutK, int round_hi,
                          float* fwd_hi, float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream);
+/* the same with CoutRows >= Cout rows in the forward pack (zero rows): the convolution then writes an output physically padded
+ * to CoutRows channels */
+int pvg_pack_conv_weight_ex(const float* w_oihw, int Cout, int Cin, int R, int S, int CinRows, int CinK, int CoutK, int CoutRows,
+                            int round_hi, float* fwd_hi, float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream);
 /* weight gradient (cudnnConvolutionBackwardFilter): dw_oihw[co][ci][r][s] += sum_pixels dy * x ; x has CinP
  * physical channels of which the first Cin are real.  dw must be zero-initialised by the caller. */
 int pvg_conv2d_wgrad(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* dy, float* dw_oihw,
@@ -166,11 +170,14 @@ int pvg_bn_apply(const float* x, int N, int HW, int C, int groups, const float* 
  * weight gradient: PVG_CORR_BF16), so that no separate pvg_split_16 pass re-reads y. */
 int pvg_bn_apply_ex(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
                     const float* weight, const float* bias, const float* residual, int act, float slope,
-                    float* y, void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream);
+                    float* y, void* planes_a, int fmt_a, void* planes_b, int fmt_b, int Cparams, void* stream);
+/* Cparams (0 = C): number of channels that HAVE parameters / running statistics - a 65-channel BatchNorm
+ * (representation_network.py:28) applied to a tensor physically padded to 72 channels so that the convolutions around it run on
+ * the tensor cores; padding channels are zero in, zero out, and are skipped by the running-statistics update. */
 int pvg_bn_finalize_apply_ex(const float* x, int N, int HW, int C, int groups, const double* sums, int64_t count, float eps,
                              float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                              const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
-                             void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream);
+                             void* planes_a, int fmt_a, void* planes_b, int fmt_b, int Cparams, void* stream);
 /* backward pass 1: with g = dy * act'(y): sums2 (double[groups][2][C], zeroed) += (sum g, sum g * xhat) */
 int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, int HW, int C, int groups,
                       const float* mean, const float* invstd, int act, float slope, double* sums2, void* stream);
@@ -181,6 +188,10 @@ int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int
                      const float* mean, const float* invstd, const float* weight, int act, float slope,
                      const double* sums2, int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias,
                      void* stream);   /* dweight / dbias (optional): pvg_bn_bwd_params folded into the same launch */
+int pvg_bn_bwd_apply_ex(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
+                        const float* mean, const float* invstd, const float* weight, int act, float slope,
+                        const double* sums2, int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias,
+                        int Cparams, void* stream);   /* Cparams: see pvg_bn_apply_ex */
 /* dweight[c] = sum_groups sum_gx ; dbias[c] = sum_groups sum_g */
 int pvg_bn_bwd_params(const double* sums2, int groups, int C, float* dweight, float* dbias, void* stream);
 

@@ -51,14 +51,16 @@ _SIGNATURES = {
     "pvg_bn_finalize": [P, c_int64, c_int, c_int, c_float, c_float, P, P, P, P, P],
     "pvg_bn_eval_prepare": [P, P, c_int, c_float, P, P, P],
     "pvg_bn_apply": [P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_float, P, P],
-    "pvg_bn_apply_ex": [P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_float, P, P, c_int, P, c_int, P],
+    "pvg_bn_apply_ex": [P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_float, P, P, c_int, P, c_int, c_int, P],
     "pvg_bn_finalize_apply_ex": [P, c_int, c_int, c_int, c_int, P, c_int64, c_float, c_float, P, P, P, P, P, P, P, c_int, c_float,
-                                 P, P, c_int, P, c_int, P],
+                                 P, P, c_int, P, c_int, c_int, P],
     "pvg_maxpool2_fwd_ex": [P, c_int, c_int, c_int, c_int, P, P, c_int, P],
     "pvg_resize_bilinear_ex": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int, P, c_int, P],
     "pvg_concat_pad": [POINTER(ConcatDesc), P, P, c_int, P, c_int, P],
     "pvg_bn_bwd_reduce": [P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P],
     "pvg_bn_bwd_apply": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P, P, P],
+    "pvg_bn_bwd_apply_ex": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P, P, c_int, P],
+    "pvg_pack_conv_weight_ex": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P],
     "pvg_bn_finalize_apply": [P, c_int, c_int, c_int, c_int, P, c_int64, c_float, c_float, P, P, P, P, P, P, P, c_int, c_float,
                               P, P],
     "pvg_bn_bwd_params": [P, c_int, c_int, P, P, P],

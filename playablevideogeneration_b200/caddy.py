@@ -104,14 +104,19 @@ class ResidualBlock(nn.Module):
 
     def forward(self, x, out_planes: bool = False):
         """``out_planes``: the block's output feeds another tensor-core convolution - the last BatchNorm pass writes that
-        convolution's 16-bit operand planes next to the fp32 result (no separate split pass)."""
+        convolution's 16-bit operand planes next to the fp32 result (no separate split pass).
+        A block whose channel count is not a multiple of 8 (the encoder's 65-channel tail, representation_network.py:28)
+        computes on tensors physically padded with zero channels to the next multiple of 8: its three convolutions and their
+        gradients then run on the tensor cores instead of the fp32 CUDA-core kernels.  The result keeps the padding."""
         pool = self.downsample_factor == 2
         need = ops.conv_input_planes()
-        out = ops.conv2d(x, self.conv1.weight)
+        cout = self.conv1.out_channels
+        cphys = (cout + 7) // 8 * 8 if (cout % 8 and x.shape[1] % 8 == 0 and ops.supports_padded_cout()) else None
+        out = ops.conv2d(x, self.conv1.weight, cout_phys=cphys)
         out = ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE, planes=need)
-        out = ops.conv2d(out, self.conv2.weight)
+        out = ops.conv2d(out, self.conv2.weight, cout_phys=cphys)
         if self.downsample is not None:
-            idn = ops.conv2d(x, self.downsample[0].weight)
+            idn = ops.conv2d(x, self.downsample[0].weight, cout_phys=cphys)
             idn = ops.pool_bn_act(idn, self.downsample[2], pool=pool, act=ACT_NONE)
         else:
             idn = x
@@ -259,7 +264,8 @@ class RepresentationNetwork(nn.Module):
         last = len(self.residuals) - 1
         for i, block in enumerate(self.residuals):
             x = block(x, out_planes=i < last)
-        return x[:, :-1], torch.sigmoid(x[:, -1:])
+        sf = self.residuals[last].conv1.out_channels - 1          # x may carry zero padding channels beyond sf + 1
+        return x[:, :sf], torch.sigmoid(x[:, sf:sf + 1])
 
 
 class ActionNetwork(nn.Module):

@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        int C, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, const float* __restrict__ weight,
                                                        const float* __restrict__ bias, const float* __restrict__ residual,
-                                                       int act, float slope, float* __restrict__ y, const PlaneOut po) {
+                                                       int act, float slope, float* __restrict__ y, const PlaneOut po,
+                                                       const int Cp) {
+  // Cp <= C: channels that HAVE parameters (a 65-channel BatchNorm on a tensor physically padded to 72 channels so that its
+  // convolutions run on the tensor cores); the padding channels are zero in, zero out
   const int U = C / V;
   const int64_t total = M * U;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -219,7 +222,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     if (residual) res = Vec<V>::load(residual + r * C + c);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float w = weight ? __ldg(weight + c + j) : 1.f, b = bias ? __ldg(bias + c + j) : 0.f;
+      const bool real = c + j < Cp;
+      float w = real ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f, b = (real && bias) ? __ldg(bias + c + j) : 0.f;
       float v = (t.v[j] - __ldg(mean + (size_t)g * C + c + j)) * __ldg(invstd + (size_t)g * C + c + j) * w + b;
       if (residual) v += res.v[j];
       o.v[j] = act_fwd(v, act, slope);
@@ -262,7 +266,8 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* __r
                                                                 float* running_var, float* __restrict__ mean,
                                                                 float* __restrict__ invstd, const float* __restrict__ weight,
                                                                 const float* __restrict__ bias, const float* __restrict__ residual,
-                                                                int act, float slope, float* __restrict__ y, const PlaneOut po) {
+                                                                int act, float slope, float* __restrict__ y, const PlaneOut po,
+                                                                const int Cp) {
   extern __shared__ float sm_stats[];              // [groups][C] mean, then [groups][C] invstd
   float* s_mean = sm_stats;
   float* s_inv = sm_stats + (size_t)groups * C;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* __r
     if (blockIdx.x == 0) { mean[i] = mf; invstd[i] = isf; }
   }
   if (blockIdx.x == 0 && (running_mean || running_var)) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
       float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
       for (int g = 0; g < groups; ++g) {
         const double s = sums[((size_t)g * 2 + 0) * C + c], ss = sums[((size_t)g * 2 + 1) * C + c];
@@ -304,7 +309,8 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* __r
     if (residual) res = Vec<V>::load(residual + r * C + c);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float w = weight ? __ldg(weight + c + j) : 1.f, b = bias ? __ldg(bias + c + j) : 0.f;
+      const bool real = c + j < Cp;
+      float w = real ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f, b = (real && bias) ? __ldg(bias + c + j) : 0.f;
       float v = (t.v[j] - s_mean[(size_t)g * C + c + j]) * s_inv[(size_t)g * C + c + j] * w + b;
       if (residual) v += res.v[j];
       o.v[j] = act_fwd(v, act, slope);
@@ -321,9 +327,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ invstd, const float* __restrict__ weight,
                                                            int act, float slope, const double* __restrict__ sums2, int eval,
                                                            int unpool, float* __restrict__ dx, float* __restrict__ g_out,
-                                                           int groups, float* __restrict__ dweight, float* __restrict__ dbias) {
+                                                           int groups, float* __restrict__ dweight, float* __restrict__ dbias,
+                                                           const int Cp) {
   if (blockIdx.x == 0 && (dweight || dbias)) {       // bn_bwd_params folded in: one launch less per BatchNorm backward
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
       double sg = 0.0, sgx = 0.0;
       for (int g = 0; g < groups; ++g) { sg += sums2[((size_t)g * 2 + 0) * C + c]; sgx += sums2[((size_t)g * 2 + 1) * C + c]; }
       if (dweight) dweight[c] = (float)sgx;
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       float gg = d.v[j] * (act != PVG_ACT_NONE ? act_bwd_from_out(yv.v[j], act, slope) : 1.f);
       go.v[j] = gg;
       float is = __ldg(invstd + (size_t)g * C + c + j);
-      float w = weight ? __ldg(weight + c + j) : 1.f;
+      float w = (c + j < Cp) ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f;
       float val;
       if (eval) {
         val = w * is * gg;
@@ -797,8 +804,8 @@ __global__ void cast_d2f_kernel(const double* in, float* out, int n) {
 // physical channel count of the activation the data gradient is taken with respect to
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int R, int S,
                                                           int CinRows, int CinK, int CoutK, int round_hi, float* fwd_hi,
-                                                          float* fwd_lo, float* bwd_hi, float* bwd_lo) {
-  const int64_t total_f = (int64_t)Cout * R * S * CinK;
+                                                          float* fwd_lo, float* bwd_hi, float* bwd_lo, int CoutRows) {
+  const int64_t total_f = (int64_t)CoutRows * R * S * CinK;      // CoutRows >= Cout: zero rows for physically padded outputs
   const int64_t total_b = (int64_t)CinRows * R * S * CoutK;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_f + total_b; i += (int64_t)gridDim.x * blockDim.x) {
     const bool fwd = i < total_f;
@@ -986,13 +993,14 @@ static int planes_ok(const void* a, const void* b, int C) {
 
 int pvg_bn_apply_ex(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
                     const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
-                    void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream) {
+                    void* planes_a, int fmt_a, void* planes_b, int fmt_b, int Cparams, void* stream) {
+  const int Cp = (Cparams > 0 && Cparams < C) ? Cparams : C;
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
   if (!planes_ok(planes_a, planes_b, C)) return -1;
   int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
   const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, M * C);
   DISPATCH_V(C, (bn_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
-                    x, M, rpg, C, mean, invstd, weight, bias, residual, act, slope, y, po)));
+                    x, M, rpg, C, mean, invstd, weight, bias, residual, act, slope, y, po, Cp)));
   PVG_LAUNCH_OK();
   return 0;
 }
@@ -1000,22 +1008,23 @@ int pvg_bn_apply_ex(const float* x, int N, int HW, int C, int groups, const floa
 int pvg_bn_apply(const float* x, int N, int HW, int C, int groups, const float* mean, const float* invstd,
                  const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
                  void* stream) {
-  return pvg_bn_apply_ex(x, N, HW, C, groups, mean, invstd, weight, bias, residual, act, slope, y, nullptr, 0, nullptr, 0, stream);
+  return pvg_bn_apply_ex(x, N, HW, C, groups, mean, invstd, weight, bias, residual, act, slope, y, nullptr, 0, nullptr, 0, 0, stream);
 }
 
 int pvg_bn_finalize_apply_ex(const float* x, int N, int HW, int C, int groups, const double* sums, int64_t count, float eps,
                              float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                              const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
-                             void* planes_a, int fmt_a, void* planes_b, int fmt_b, void* stream) {
+                             void* planes_a, int fmt_a, void* planes_b, int fmt_b, int Cparams, void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
   if (!planes_ok(planes_a, planes_b, C)) return -1;
+  const int Cp = (Cparams > 0 && Cparams < C) ? Cparams : C;
   const size_t smem = (size_t)groups * C * 2 * sizeof(float);
   PVG_CHECK_ARG(smem <= 48 * 1024, "groups * C too large for the fused kernel: call pvg_bn_finalize + pvg_bn_apply");
   int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
   const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, M * C);
   DISPATCH_V(C, (bn_finalize_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, smem, (cudaStream_t)stream>>>(
                     x, M, rpg, C, groups, sums, (double)count, eps, momentum, running_mean, running_var, mean, invstd, weight,
-                    bias, residual, act, slope, y, po)));
+                    bias, residual, act, slope, y, po, Cp)));
   PVG_LAUNCH_OK();
   return 0;
 }
@@ -1025,7 +1034,7 @@ int pvg_bn_finalize_apply(const float* x, int N, int HW, int C, int groups, cons
                           const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
                           void* stream) {
   return pvg_bn_finalize_apply_ex(x, N, HW, C, groups, sums, count, eps, momentum, running_mean, running_var, mean, invstd, weight,
-                                  bias, residual, act, slope, y, nullptr, 0, nullptr, 0, stream);
+                                  bias, residual, act, slope, y, nullptr, 0, nullptr, 0, 0, stream);
 }
 
 int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, int HW, int C, int groups, const float* mean,
@@ -1044,12 +1053,20 @@ int pvg_bn_bwd_reduce(const float* dy, const float* y, const float* x, int N, in
 int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
                      const float* mean, const float* invstd, const float* weight, int act, float slope, const double* sums2,
                      int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias, void* stream) {
+  return pvg_bn_bwd_apply_ex(dy, y, x, N, H, W, C, groups, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out, dweight,
+                             dbias, 0, stream);
+}
+
+int pvg_bn_bwd_apply_ex(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
+                        const float* mean, const float* invstd, const float* weight, int act, float slope, const double* sums2,
+                        int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias, int Cparams, void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  const int Cp = (Cparams > 0 && Cparams < C) ? Cparams : C;
   int OH = unpool ? H / 2 : H, OW = unpool ? W / 2 : W;
   int64_t M = (int64_t)N * OH * OW, rpg = (int64_t)(N / groups) * OH * OW;
   DISPATCH_V(C, (bn_bwd_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
                     dy, y, x, M, rpg, OH, OW, C, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out, groups, dweight,
-                    dbias)));
+                    dbias, Cp)));
   PVG_LAUNCH_OK();
   return 0;
 }
@@ -1268,10 +1285,15 @@ int pvg_channel_sum(const float* x, int64_t M, int C, double* scratch, float* ou
 
 int pvg_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int R, int S, int CinRows, int CinK, int CoutK, int round_hi,
                          float* fwd_hi, float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream) {
-  PVG_CHECK_ARG(CinRows >= Cin && CinK >= CinRows && CoutK >= Cout, "padded channel counts smaller than the real ones");
-  int64_t total = (int64_t)Cout * R * S * CinK + (int64_t)CinRows * R * S * CoutK;
+  return pvg_pack_conv_weight_ex(w_oihw, Cout, Cin, R, S, CinRows, CinK, CoutK, Cout, round_hi, fwd_hi, fwd_lo, bwd_hi, bwd_lo, stream);
+}
+
+int pvg_pack_conv_weight_ex(const float* w_oihw, int Cout, int Cin, int R, int S, int CinRows, int CinK, int CoutK, int CoutRows,
+                            int round_hi, float* fwd_hi, float* fwd_lo, float* bwd_hi, float* bwd_lo, void* stream) {
+  PVG_CHECK_ARG(CinRows >= Cin && CinK >= CinRows && CoutK >= Cout && CoutRows >= Cout, "padded channel counts smaller than the real ones");
+  int64_t total = (int64_t)CoutRows * R * S * CinK + (int64_t)CinRows * R * S * CoutK;
   pack_weight_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, R, S, CinRows, CinK, CoutK,
-                                                                          round_hi, fwd_hi, fwd_lo, bwd_hi, bwd_lo);
+                                                                          round_hi, fwd_hi, fwd_lo, bwd_hi, bwd_lo, CoutRows);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -221,7 +221,7 @@ class _Packs:
         return None
 
 
-def _get_packs(weight: Tensor, cin_rows: int, tensor_core: bool) -> _Packs:
+def _get_packs(weight: Tensor, cin_rows: int, tensor_core: bool, cout_rows: Optional[int] = None) -> _Packs:
     """Packed (+tf32-split) copies of a conv weight for an activation with ``cin_rows`` physical channels, cached ON the
     tensor object (so a recycled allocation can never alias a stale pack) and rebuilt when the tensor's autograd version or
     the global weights epoch moves.  Tensor-core consumers get tf32-rounded hi planes and K-side channel counts rounded up
@@ -233,17 +233,18 @@ def _get_packs(weight: Tensor, cin_rows: int, tensor_core: bool) -> _Packs:
             weight._pvg_packs = cache
         except Exception:
             pass
-    key = (cin_rows, tensor_core)
+    cout, cin, r, s = weight.shape
+    cout_rows = cout if cout_rows is None else cout_rows        # physical output channels (zero rows beyond the real ones)
+    key = (cin_rows, tensor_core, cout_rows)
     hit = cache.get(key)
     ver = (weight._version, weights_epoch)
     if hit is not None and hit[0] == ver:
         return hit[1]
-    cout, cin, r, s = weight.shape
-    cin_k, cout_k = (_pad32(cin_rows), _pad32(cout)) if tensor_core else (cin_rows, cout)
+    cin_k, cout_k = (_pad32(cin_rows), _pad32(cout_rows)) if tensor_core else (cin_rows, cout_rows)
     w = weight.detach().contiguous()
-    fwd = torch.empty((2, cout * r * s * cin_k), dtype=torch.float32, device=weight.device)
+    fwd = torch.empty((2, cout_rows * r * s * cin_k), dtype=torch.float32, device=weight.device)
     bwd = torch.empty((2, cin_rows * r * s * cout_k), dtype=torch.float32, device=weight.device)
-    call("pvg_pack_conv_weight", w.data_ptr(), cout, cin, r, s, cin_rows, cin_k, cout_k, 1 if tensor_core else 0,
+    call("pvg_pack_conv_weight_ex", w.data_ptr(), cout, cin, r, s, cin_rows, cin_k, cout_k, cout_rows, 1 if tensor_core else 0,
          fwd[0].data_ptr(), fwd[1].data_ptr(), bwd[0].data_ptr(), bwd[1].data_ptr(), _stream())
     packs = _Packs(fwd, bwd)
     cache[key] = (ver, packs)
@@ -388,7 +389,7 @@ class Conv2dFn(torch.autograd.Function):
     count (zero-padded concat buffers)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, slope, x_planes, out_planes):
+    def forward(ctx, x, weight, bias, act, slope, x_planes, out_planes, cout_phys=None):
         """``x_planes``: {format: planes} that came with x (may be empty); ``out_planes``: also return the forward-operand
         plane pair of y (all-fp16 forward kernel only)."""
         x_in = x
@@ -401,7 +402,10 @@ class Conv2dFn(torch.autograd.Function):
         if cin_log > cin_p or r != s:
             raise _lib.PvgError(f"conv weight {tuple(weight.shape)} does not fit input with {cin_p} channels")
         algo, nprod, fmt = _conv_algo(cin_p, cout, r, "fwd")
-        packs = _get_packs(weight, cin_p, algo == ALGO_UMMA)
+        cphys = cout if cout_phys is None else int(cout_phys)
+        if cphys != cout and not (algo == ALGO_UMMA and nprod == 2 and fmt == _lib.CORR_FP16_ALL and bias is None and cphys % 8 == 0):
+            raise _lib.PvgError("physically padded outputs exist on the all-fp16 tensor-core path only (see supports_padded_cout)")
+        packs = _get_packs(weight, cin_p, algo == ALGO_UMMA, cphys)
         b = bias.detach().contiguous() if bias is not None else None
         flops = 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * cout * r * s * cin_log
         y_planes = None
@@ -410,10 +414,10 @@ class Conv2dFn(torch.autograd.Function):
             # all-fp16 forward conv straight from plane pairs (and, on request, to the plane pair of y)
             xp = xp_used = x_planes[fmt] if fmt in x_planes else _split(x, nprod, fmt)[1]
             n, _, h, w = x.shape
-            y = empty_nhwc((n, cout, h, w), x.device)
-            if out_planes and cout % 8 == 0:
+            y = empty_nhwc((n, cphys, h, w), x.device)
+            if out_planes and cphys % 8 == 0:
                 y_planes = torch.empty((2 * y.numel(),), dtype=torch.float16, device=x.device)
-            d = ConvDesc(n, h, w, cin_p, cout, r, r, (r - 1) // 2, act, float(slope), ALGO_UMMA, 2, fmt)
+            d = ConvDesc(n, h, w, cin_p, cphys, r, r, (r - 1) // 2, act, float(slope), ALGO_UMMA, 2, fmt)
             prof = conv_profile is not None
             if prof:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -428,6 +432,7 @@ class Conv2dFn(torch.autograd.Function):
             y = _conv_forward(x, packs, 0, cout, r, b, act, slope, algo, nprod, fmt, flops, split=split)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.meta = (act, slope, bias is not None, cin_log)
+        ctx.cphys = cphys
         wm = _mode("wgrad")
         ctx.x_wplanes = x_planes.get(wm[1]) if wm[0] == 2 else None      # weight-gradient operand planes that came with x
         if ctx.x_wplanes is None and wm == (2, _lib.CORR_FP16_ALL) and xp_used is not None and weight.requires_grad:
@@ -447,8 +452,10 @@ class Conv2dFn(torch.autograd.Function):
         dmode = _mode("dgrad")            # (nprod, fmt) of the data-gradient kernel (conv_umma.cu)
         wmode = _mode("wgrad")            # ... of the weight-gradient kernel (conv_wgrad_umma.cu)
         H3 = (2, _lib.CORR_FP16_ALL)
+        if ctx.cphys != cout and not (dmode == H3 and wmode == H3 and _precision == "tf32x3"):
+            raise _lib.PvgError("physically padded outputs need the all-fp16 backward kernels")
         if dmode == H3 or wmode == H3:
-            if (dmode == H3 and wmode == H3 and cin_p % _TC_CIN_MULTIPLE == 0 and cout % 8 == 0 and _precision == "tf32x3"
+            if (dmode == H3 and wmode == H3 and cin_p % _TC_CIN_MULTIPLE == 0 and ctx.cphys % 8 == 0 and _precision == "tf32x3"
                     and not (cin_p <= 4 and r <= 7) and not (r == 7 and cout <= 3)):
                 return Conv2dFn._backward_h3(ctx, dy, x, weight, y)
             # shapes the all-fp16 kernels do not take (image-facing layers, channel counts that are not a multiple of 8):
@@ -539,7 +546,7 @@ class Conv2dFn(torch.autograd.Function):
             db = torch.empty((cout,), dtype=torch.float32, device=dy.device)
             scratch = torch.empty((cout,), dtype=torch.float64, device=dy.device)
             call("pvg_channel_sum", g.data_ptr(), n * h * w, cout, scratch.data_ptr(), db.data_ptr(), _stream())
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def _backward_h3(ctx, dy, x, weight, y):
@@ -547,7 +554,8 @@ def _backward_h3(ctx, dy, x, weight, y):
     dY is scaled by a power of two chosen from max|dY| so that its fp16 plane pair is exact to 22 bits, both kernels undo the
     scale; x is consumed through the very planes the forward convolution read."""
     act, slope, has_bias, cin_log = ctx.meta
-    cout, _, r, s = weight.shape
+    cout_log, _, r, s = weight.shape
+    cout = ctx.cphys                    # physical channels of dY (>= the weight's: zero rows in the packs)
     n, cin_p, h, w = x.shape
     dev = dy.device
     st = _stream()
@@ -564,7 +572,7 @@ def _backward_h3(ctx, dy, x, weight, y):
         g = dy
         call("pvg_split_16_scaled", dy.data_ptr(), planes.data_ptr(), dy.numel(), amax.data_ptr(), inv.data_ptr(), st)
     dx = dw = db = None
-    packs = _get_packs(weight, cin_p, True)
+    packs = _get_packs(weight, cin_p, True, cout)
     if ctx.needs_input_grad[0]:
         dx = empty_nhwc((n, cin_p, h, w), dev)
         d = ConvDesc(n, h, w, cout, cin_p, r, r, (r - 1) // 2, ACT_NONE, 0.0, ALGO_UMMA, 2, _lib.CORR_FP16_ALL)
@@ -576,10 +584,10 @@ def _backward_h3(ctx, dy, x, weight, y):
              inv.data_ptr(), st)
         if prof:
             e1.record()
-            conv_profile.append((e0, e1, 2.0 * n * h * w * cout * r * s * cin_log, "h3"))
+            conv_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log, "h3"))
     if ctx.needs_input_grad[1]:
         xp = ctx.x_wplanes if ctx.x_wplanes is not None else _split(x, 2, _lib.CORR_FP16_ALL)[1]
-        dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        dw = torch.empty((cout, cin_log, r, s), dtype=torch.float32, device=dev)
         scratch = zero_pool.zeros((cout * r * s * _pad32(cin_p),), torch.float32, dev)
         d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_UMMA, 2, _lib.CORR_FP16_ALL)
         prof = wgrad_profile is not None
@@ -590,22 +598,34 @@ def _backward_h3(ctx, dy, x, weight, y):
              dw.data_ptr(), 0, st)
         if prof:
             e1.record()
-            wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout * r * s * cin_log))
+            wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log))
+        if cout != cout_log:
+            dw = dw[:cout_log]
     if need_g:
         db = torch.empty((cout,), dtype=torch.float32, device=dev)
         scr = torch.empty((cout,), dtype=torch.float64, device=dev)
         call("pvg_channel_sum", g.data_ptr(), n * h * w, cout, scr.data_ptr(), db.data_ptr(), st)
-    return dx, dw, db, None, None, None, None
+    return dx, dw, db, None, None, None, None, None
 
 
 Conv2dFn._backward_h3 = staticmethod(_backward_h3)
 
 
+def supports_padded_cout() -> bool:
+    """True when conv2d(..., cout_phys=) is available: every conv role on the all-fp16 tensor-core kernels."""
+    H3 = (2, _lib.CORR_FP16_ALL)
+    return (_precision == "tf32x3" and os.environ.get("PVG_NO_COUT_PAD") != "1" and _mode("fwd") == H3 and _mode("dgrad") == H3
+            and _mode("wgrad") == H3)
+
+
 def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0,
-           out_planes: bool = False) -> Tensor:
-    """``out_planes``: the consumer of the result is another tensor-core convolution - have the epilogue write its operand planes."""
+           out_planes: bool = False, cout_phys: Optional[int] = None) -> Tensor:
+    """``out_planes``: the consumer of the result is another tensor-core convolution - have the epilogue write its operand planes.
+    ``cout_phys``: write the result physically padded (zero channels) to this many channels - a multiple of 8 - so that a layer
+    with an odd channel count (the 65-channel encoder tail, representation_network.py:28) and its consumers stay on the
+    tensor cores."""
     want = bool(out_planes) and _lib.CORR_FP16_ALL in conv_input_planes(False)
-    y, yp = Conv2dFn.apply(x, weight, bias, act, slope, planes_of(x), want)
+    y, yp = Conv2dFn.apply(x, weight, bias, act, slope, planes_of(x), want, cout_phys)
     if yp is not None:
         y._pvg_planes = {_lib.CORR_FP16_ALL: yp}
     return y
@@ -625,8 +645,12 @@ class PoolBNActFn(torch.autograd.Function):
         if residual is not None:
             residual = nhwc(residual)
         oh, ow = (h // 2, w // 2) if pool else (h, w)
-        mean = torch.empty((groups, c), dtype=torch.float32, device=dev)
-        invstd = torch.empty((groups, c), dtype=torch.float32, device=dev)
+        cp = c if running_mean is None else int(running_mean.shape[0])     # channels that have parameters (<= c: zero padding)
+        if weight is not None:
+            cp = int(weight.shape[0])
+        padded = cp != c
+        mean = (torch.zeros if padded else torch.empty)((groups, c), dtype=torch.float32, device=dev)
+        invstd = (torch.zeros if padded else torch.empty)((groups, c), dtype=torch.float32, device=dev)
         sums = zero_pool.zeros((groups, 2, c), torch.float64, dev) if (training or pool) else None
         if pool:
             xp = empty_nhwc((n, c, oh, ow), dev)
@@ -644,20 +668,23 @@ class PoolBNActFn(torch.autograd.Function):
         if training and groups * c * 8 <= 48 * 1024:      # statistics finalisation fused into the apply pass
             call("pvg_bn_finalize_apply_ex", xp.data_ptr(), n, oh * ow, c, groups, sums.data_ptr(), (n // groups) * oh * ow,
                  float(eps), float(momentum), _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), _p(wd),
-                 _p(bd), _p(residual), act, float(slope), y.data_ptr(), _p(pa), fa, _p(pb), fb, st)
+                 _p(bd), _p(residual), act, float(slope), y.data_ptr(), _p(pa), fa, _p(pb), fb, cp, st)
         else:
+            if padded and training:
+                raise _lib.PvgError("channel-padded BatchNorm needs the fused finalize + apply kernel")
             if training:
                 call("pvg_bn_finalize", sums.data_ptr(), (n // groups) * oh * ow, groups, c, float(eps), float(momentum),
                      _p(running_mean), _p(running_var), mean.data_ptr(), invstd.data_ptr(), st)
             else:
                 if groups != 1:
                     raise _lib.PvgError("grouped statistics only exist in training mode")
-                call("pvg_bn_eval_prepare", running_mean.data_ptr(), running_var.data_ptr(), c, float(eps), mean.data_ptr(),
+                call("pvg_bn_eval_prepare", running_mean.data_ptr(), running_var.data_ptr(), cp, float(eps), mean.data_ptr(),
                      invstd.data_ptr(), st)
             call("pvg_bn_apply_ex", xp.data_ptr(), n, oh * ow, c, groups, mean.data_ptr(), invstd.data_ptr(), _p(wd), _p(bd),
-                 _p(residual), act, float(slope), y.data_ptr(), _p(pa), fa, _p(pb), fb, st)
+                 _p(residual), act, float(slope), y.data_ptr(), _p(pa), fa, _p(pb), fb, cp, st)
         ctx.save_for_backward(xp, weight, mean, invstd, y if act != ACT_NONE else None)
         ctx.meta = (training, pool, act, slope, groups, residual is not None, (n, c, h, w))
+        ctx.cp = cp
         for t in (pa, pb):
             if t is not None:
                 ctx.mark_non_differentiable(t)
@@ -680,18 +707,20 @@ class PoolBNActFn(torch.autograd.Function):
         g_out = empty_nhwc((n, c, oh, ow), dev) if (has_res and ctx.needs_input_grad[3]) else None
         dweight = dbias = None
         if need_params:
-            dweight = torch.empty((c,), dtype=torch.float32, device=dev)
-            dbias = torch.empty((c,), dtype=torch.float32, device=dev)
+            dweight = torch.empty((ctx.cp,), dtype=torch.float32, device=dev)
+            dbias = torch.empty((ctx.cp,), dtype=torch.float32, device=dev)
         if dx is not None or g_out is not None:
             if dx is None:        # only the residual gradient is wanted
                 dx_buf = empty_nhwc((n, c, h, w), dev)
             else:
                 dx_buf = dx
-            call("pvg_bn_bwd_apply", dy.data_ptr(), _p(y), xp.data_ptr(), n, h, w, c, groups, mean.data_ptr(),
+            call("pvg_bn_bwd_apply_ex", dy.data_ptr(), _p(y), xp.data_ptr(), n, h, w, c, groups, mean.data_ptr(),
                  invstd.data_ptr(), _p(weight.detach() if weight is not None else None), act, float(slope),
                  sums2.data_ptr(), 0 if training else 1, 1 if pool else 0, dx_buf.data_ptr(), _p(g_out), _p(dweight), _p(dbias),
-                 st)                  # dweight / dbias: the parameter gradients ride along in the same launch
+                 ctx.cp, st)          # dweight / dbias: the parameter gradients ride along in the same launch
         elif need_params:
+            if ctx.cp != c:
+                raise _lib.PvgError("channel-padded BatchNorm backward needs the input gradient path")
             call("pvg_bn_bwd_params", sums2.data_ptr(), groups, c, dweight.data_ptr(), dbias.data_ptr(), st)
         return (dx, dweight, dbias, g_out) + (None,) * 10
 

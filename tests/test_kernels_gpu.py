@@ -381,6 +381,53 @@ def test_concat_pad_strided_time_slices():
     assert got.shape == (3, 96, 4, 6) and torch.equal(got[:, :73], ref) and float(got[:, 73:].abs().max()) == 0.0
 
 
+def test_padded_65_channel_block_runs_on_tensor_cores_and_matches_fp64():
+    """The encoder tail ResidualBlock(64 -> 65) (representation_network.py:28) on tensors physically padded to 72 channels:
+    forward, input gradient and every parameter gradient against a float64 torch reference; padding channels stay zero; the
+    BatchNorm running statistics (65 entries) are updated as by nn.BatchNorm2d."""
+    import copy
+    ops = _ops()
+    from playablevideogeneration_b200 import _lib
+    from playablevideogeneration_b200.caddy import ResidualBlock
+    torch.manual_seed(3)
+    blk = ResidualBlock(64, 65, 1)
+    ref = copy.deepcopy(blk).double()
+    blk = blk.to(DEV).train()
+    x = _rand(4, 64, 16, 16, seed=5)
+    xr = x.double().requires_grad_(True)
+    out = ref.bn1(F.conv2d(xr, ref.conv1.weight, padding=1))
+    out = F.leaky_relu(out, 0.2)
+    out = ref.bn2(F.conv2d(out, ref.conv2.weight, padding=1))
+    idn = ref.downsample[2](F.conv2d(xr, ref.downsample[0].weight))
+    yr = F.leaky_relu(out + idn, 0.2)
+    gy = _rand(4, 65, 16, 16, seed=6)
+    yr.backward(gy.double())
+    assert ops.supports_padded_cout()
+    calls = []
+    orig = _lib.call
+    def spy(name, *a):
+        calls.append((name, a[0].algo if a and isinstance(a[0], _lib.ConvDesc) else None))
+        return orig(name, *a)
+    ops.call = spy
+    try:
+        xg = x.to(DEV).requires_grad_(True)
+        y = blk(xg)
+        assert y.shape[1] == 72 and float(y[:, 65:].abs().max()) == 0.0
+        gpad = torch.zeros_like(y)
+        gpad[:, :65] = gy.to(DEV)
+        y.backward(gpad)
+    finally:
+        ops.call = orig
+    assert not any(n in ("pvg_conv2d_fwd", "pvg_conv2d_wgrad") and algo == _lib.ALGO_SIMT for n, algo in calls), \
+        "a 65-channel convolution fell back to the CUDA-core kernels"
+    _close("pad65_fwd", y[:, :65], yr, 2e-5, 2e-6)
+    _close("pad65_dx", xg.grad, xr.grad, 2e-5, 1e-6)
+    for (k, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        _close("pad65_d" + k, p.grad, q.grad, 5e-5, 1e-6)
+    _close("pad65_running_mean", blk.bn2.running_mean, ref.bn2.running_mean, 1e-5, 1e-6)
+    _close("pad65_running_var", blk.bn1.running_var, ref.bn1.running_var, 1e-5, 1e-6)
+
+
 def test_absdiff_mean():
     ops = _ops()
     a, b = _rand(5, 64, 9, 7, seed=1), _rand(5, 64, 9, 7, seed=2).requires_grad_(True)
