@@ -65,16 +65,41 @@ class NoiseSource:
             self.plan = []
 
     def freeze(self):
-        self.bufs = [torch.empty(shape, dtype=torch.float32, device=dev) if dev is not None else None
-                     for _, shape, dev in self.plan]
+        """All recorded draws become views of ONE device buffer, mirrored by ONE pinned host buffer: a refill is the CPU draws
+        (in the recorded order - the reference's RNG stream) plus a single asynchronous upload.  (One pageable copy per draw -
+        about 60 per training step - blocked the host behind the running replay and left the GPU idle for ~1 ms per step.)"""
+        sizes = [int(torch.Size(shape).numel()) if dev is not None else 0 for _, shape, dev in self.plan]
+        devs = [dev for _, _, dev in self.plan if dev is not None]
+        total = sum(sizes)
+        self._flat = torch.empty((max(total, 1),), dtype=torch.float32, device=devs[0]) if devs else None
+        self._host = torch.empty((max(total, 1),), dtype=torch.float32)
+        if self._flat is not None and self._flat.is_cuda:
+            self._host = self._host.pin_memory()
+        self._host_event = None
+        self.bufs, self._spans, off = [], [], 0
+        for (kind, shape, dev), n in zip(self.plan, sizes):
+            if dev is None:
+                self.bufs.append(None)
+                self._spans.append(None)
+            else:
+                self.bufs.append(self._flat[off:off + n].view(shape))
+                self._spans.append((off, n))
+                off += n
         self.mode = "static"
         self.refill()
 
     def refill(self):
-        for (kind, shape, dev), buf in zip(self.plan, self.bufs):
-            t = self._draw(kind, shape)
-            if buf is not None:
-                buf.copy_(t)
+        if self._host_event is not None:
+            self._host_event.synchronize()              # the previous upload has read the pinned buffer
+        for (kind, shape, dev), span in zip(self.plan, self._spans):
+            t = self._draw(kind, shape)                 # drawn even when unused: keeps the CPU RNG stream of the reference
+            if span is not None:
+                self._host[span[0]:span[0] + span[1]].copy_(t.reshape(-1))
+        if self._flat is not None:
+            self._flat.copy_(self._host, non_blocking=True)
+            if self._flat.is_cuda:
+                self._host_event = torch.cuda.Event()
+                self._host_event.record()
         self.cursor = 0
 
 
@@ -102,8 +127,9 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(_conv(in_planes, out_planes, 1, False), nn.AvgPool2d(downsample_factor),
                                             nn.BatchNorm2d(out_planes))
 
-    def forward(self, x, out_planes: bool = False):
-        """``out_planes``: the block's output feeds another tensor-core convolution - the last BatchNorm pass writes that
+    def forward(self, x, out_planes: bool = False, groups: int = 1):
+        """``groups``: the batch holds that many independent reference calls (time steps) - BatchNorm statistics per chunk.
+        ``out_planes``: the block's output feeds another tensor-core convolution - the last BatchNorm pass writes that
         convolution's 16-bit operand planes next to the fp32 result (no separate split pass).
         A block whose channel count is not a multiple of 8 (the encoder's 65-channel tail, representation_network.py:28)
         computes on tensors physically padded with zero channels to the next multiple of 8: its three convolutions and their
@@ -113,14 +139,15 @@ class ResidualBlock(nn.Module):
         cout = self.conv1.out_channels
         cphys = (cout + 7) // 8 * 8 if (cout % 8 and x.shape[1] % 8 == 0 and ops.supports_padded_cout()) else None
         out = ops.conv2d(x, self.conv1.weight, cout_phys=cphys)
-        out = ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE, planes=need)
+        out = ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE, planes=need, groups=groups)
         out = ops.conv2d(out, self.conv2.weight, cout_phys=cphys)
         if self.downsample is not None:
             idn = ops.conv2d(x, self.downsample[0].weight, cout_phys=cphys)
-            idn = ops.pool_bn_act(idn, self.downsample[2], pool=pool, act=ACT_NONE)
+            idn = ops.pool_bn_act(idn, self.downsample[2], pool=pool, act=ACT_NONE, groups=groups)
         else:
             idn = x
-        return ops.pool_bn_act(out, self.bn2, residual=idn, act=ACT_LRELU, slope=SLOPE, planes=need if out_planes else ())
+        return ops.pool_bn_act(out, self.bn2, residual=idn, act=ACT_LRELU, slope=SLOPE, planes=need if out_planes else (),
+                               groups=groups)
 
 
 class SameBlock(nn.Module):
@@ -146,10 +173,10 @@ class UpBlock(nn.Module):
         self.conv = _conv(in_features, out_features, 3, False)
         self.norm = nn.BatchNorm2d(out_features, affine=True)
 
-    def forward(self, x, out_planes: bool = False):
+    def forward(self, x, out_planes: bool = False, groups: int = 1):
         if not self.late_upscaling:
             x = ops.upsample2x(x, planes=ops.conv_input_planes())
-        x = ops.pool_bn_act(ops.conv2d(x, self.conv.weight), self.norm, act=ACT_LRELU, slope=SLOPE,
+        x = ops.pool_bn_act(ops.conv2d(x, self.conv.weight), self.norm, act=ACT_LRELU, slope=SLOPE, groups=groups,
                             planes=ops.conv_input_planes() if (out_planes and not self.late_upscaling) else ())
         if self.late_upscaling:
             x = ops.upsample2x(x)
@@ -319,14 +346,17 @@ class RenderingNetwork(nn.Module):
                                               nn.Sequential(UpBlock(c1, c2), ResidualBlock(c2, c2)), UpBlock(c2, c3)])
         self.final_blocks = nn.ModuleList([FinalBlock(c1, 3, 3), FinalBlock(c2, 3, 3), FinalBlock(c3, 3, 7)])
 
-    def forward(self, hidden_states):
+    def forward(self, hidden_states, groups: int = 1):
+        """``groups`` > 1: ``hidden_states`` stacks that many decoder calls of the reference along the batch axis (the
+        teacher-forced steps of forward_full_model, whose frames nothing downstream waits for); every BatchNorm keeps the
+        per-call batch statistics and replays the running-statistics updates in call order."""
         x = hidden_states
         outs = []
         for up, final in zip(self.upsample_blocks, self.final_blocks):
             if isinstance(up, nn.Sequential):          # UpBlock -> ResidualBlock: the UpBlock's output feeds the block's convs
-                x = up[1](up[0](x, out_planes=True))
+                x = up[1](up[0](x, out_planes=True, groups=groups), groups=groups)
             else:
-                x = up(x)
+                x = up(x, groups=groups)
             outs.append(final(x))
         outs = list(reversed(outs))
         return outs[0], outs
@@ -480,6 +510,7 @@ class Model(nn.Module):
         self.centroid_estimator = CentroidEstimator(self.actions_count, m["action_network"]["action_space_dimension"],
                                                     m["centroid_estimator"]["alpha"])
         self.train_forward_counts = 0
+        self.batch_teacher_forced_decoder = True     # decode the teacher-forced steps of forward_full_model in one batch
         self.noise = NoiseSource()
         self._graph_inference = False
         self._graphed_rollout: Optional[GraphedRollout] = None
@@ -547,23 +578,42 @@ class Model(nn.Module):
         self.dynamics_network.reinit_memory(b)
         rec_states, rec_att, hidden_all, recs = [states[:, 0]], [attention[:, 0]], [], []
         pyramid: Optional[List[List[torch.Tensor]]] = None
+        pending: List[torch.Tensor] = []            # hidden states of teacher-forced steps whose frames nobody waits for
+
+        def render(hiddens):
+            """model.py:241-243 for one step, or for several teacher-forced steps in ONE decoder launch sequence."""
+            nonlocal pyramid
+            k = len(hiddens)
+            rec, multi = self.rendering_network(hiddens[0] if k == 1 else torch.cat(hiddens, dim=0), groups=k)
+            if pyramid is None:
+                pyramid = [[] for _ in multi]
+            for j in range(k):
+                recs.append(rec if k == 1 else rec[j * b:(j + 1) * b])
+                for i, m in enumerate(multi):
+                    pyramid[i].append(m if k == 1 else m[j * b:(j + 1) * b])
+
         for idx in range(t - 1):
             self.generate_noise(b)          # reference draws (and never uses) the noise: keeps the RNG stream aligned
             hidden = self.dynamics_network(rec_states[-1], samples[:, idx], variations[:, idx])
-            rec, multi = self.rendering_network(hidden)
             hidden_all.append(hidden)
-            recs.append(rec)
-            if pyramid is None:
-                pyramid = [[] for _ in multi]
-            for i, m in enumerate(multi):
-                pyramid[i].append(m)
+            pending.append(hidden)
             if idx + 1 < ground_truth_observations_init:
+                # teacher forcing: the next state comes from the ground truth, so this step's frame is not needed yet - the
+                # decoder runs later, batched with the other teacher-forced steps (per-step BatchNorm statistics kept)
                 s, a = states[:, idx + 1], attention[:, idx + 1]
+                if self.batch_teacher_forced_decoder and idx + 2 <= t - 1:
+                    rec_states.append(s)
+                    rec_att.append(a)
+                    continue
+                render(pending); pending = []
             else:
+                render(pending); pending = []
                 obs = self.compute_current_observation(idx + 1, ground_truth_observations_init, observations, recs)
                 s, a = self.representation_network(obs)
             rec_states.append(s)
             rec_att.append(a)
+        if pending:
+            render(pending)
         f_rec_states = torch.stack(rec_states, dim=1)
         f_rec_att = torch.stack(rec_att[1:], dim=1)
         f_hidden = torch.stack(hidden_all, dim=1)

@@ -729,6 +729,8 @@ def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, group
     """``bn`` is an nn.BatchNorm2d used purely as the parameter/buffer container (reference state_dict names).
     ``planes``: plane formats (``conv_input_planes()``) the apply pass writes next to y for the convolution that consumes it."""
     training = bn.training
+    if not training:
+        groups = 1                                          # running statistics: the chunks of a stacked batch are not told apart
     if training and bn.num_batches_tracked is not None:
         defer_count(bn.num_batches_tracked, groups)         # applied by flush_deferred() at the end of Model.forward
     planes = tuple(planes)[:2]

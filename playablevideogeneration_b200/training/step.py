@@ -357,6 +357,7 @@ class GraphedTrainStep:
     def __init__(self, step: TrainStep, example_batch, ground_truth_observations_count: int, gumbel_temperature: float,
                  pretraining: bool = False, warmup: int = 2):
         self.step = step
+        self._staging = self._staged = self._copy_stream = self._copy_done = None
         self.args = (ground_truth_observations_count, gumbel_temperature, pretraining)
         self.static_batch = tuple(t.clone() for t in example_batch)
         noise = step.module.noise
@@ -383,10 +384,31 @@ class GraphedTrainStep:
             # step's frozen noise)
             noise.mode = "cpu"
 
+    def prefetch(self, batch) -> None:
+        """Starts the host->device copy of the NEXT step's batch on a side stream, into a staging buffer: it overlaps the replay
+        that is running (the graph reads ``static_batch``, which is not touched).  ``__call__(batch)`` with the same batch object
+        then only waits for that copy and moves the data device-to-device (100 MB: ~0.05 ms) in front of the replay."""
+        if self._staging is None:
+            self._staging = tuple(torch.empty_like(t) for t in self.static_batch)
+            self._copy_stream = torch.cuda.Stream()
+            self._copy_done = torch.cuda.Event()
+        self._copy_stream.wait_stream(torch.cuda.current_stream())      # the previous D2D out of the staging buffer has been queued
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._staging, batch):
+                dst.copy_(src, non_blocking=True)
+            self._copy_done.record(self._copy_stream)
+        self._staged = batch
+
     def __call__(self, batch=None):
         if batch is not None:
-            for dst, src in zip(self.static_batch, batch):
-                dst.copy_(src, non_blocking=True)
+            if self._staged is batch:                    # uploaded by prefetch() while the previous step ran
+                torch.cuda.current_stream().wait_event(self._copy_done)
+                for dst, src in zip(self.static_batch, self._staging):
+                    dst.copy_(src, non_blocking=True)
+                self._staged = None
+            else:
+                for dst, src in zip(self.static_batch, batch):
+                    dst.copy_(src, non_blocking=True)
         self.step.module.noise.refill()
         self.step.prepare_replay()
         self.graph.replay()

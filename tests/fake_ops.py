@@ -26,10 +26,10 @@ def conv2d(x, weight, bias=None, act=ACT_NONE, slope=0.0, out_planes=False, cout
 
 
 def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, groups=1, planes=()):
-    assert groups == 1
     if pool:
         x = F.avg_pool2d(x, 2)
-    y = bn(x)
+    n = x.shape[0] // groups                       # reference semantics: one BatchNorm call per group, in order
+    y = bn(x) if groups == 1 else torch.cat([bn(x[g * n:(g + 1) * n]) for g in range(groups)], dim=0)
     if residual is not None:
         y = y + residual
     return _act(y, act, slope)
