@@ -35,6 +35,7 @@ extern "C" {
 #define PVG_ACT_RELU    2   /* torchvision VGG19 features, model/layers/vgg.py:16 */
 #define PVG_ACT_TANH    3   /* model/layers/final_block.py:27 */
 #define PVG_ACT_SIGMOID 4   /* model/main_model/representation_network.py:55 */
+#define PVG_ACT_LSTM    5   /* internal: the fused ConvLSTM cell epilogue of pvg_convlstm_step */
 
 #define PVG_CORR_BF16 0
 #define PVG_CORR_FP16 1
@@ -231,6 +232,18 @@ int pvg_concat_pad(const pvg_concat_desc* d, float* y, void* planes_a, int fmt_a
 /* ---- ConvLSTM cell point-wise part, convolutional_lstm_cell.py:92-101.  gates: [M][4][C] pre-activations in the
  *      order input, forget, output, cell. ------------------------------------------------------------------------ */
 int pvg_lstm_fwd(const float* gates, const float* c_prev, int64_t M, int C, float* c_new, float* h_new, void* stream);
+/* One ConvLSTM cell step with the point-wise part FUSED into the gate convolution (convolutional_lstm_cell.py:88-101): the four
+ * gate convolutions are one implicit GEMM whose output columns are interleaved (column 4c + {0,1,2,3} = input, forget, output,
+ * cell gate of hidden channel c: pack the weight rows and the bias in that order), and the epilogue applies bias, sigmoid / tanh,
+ * c' = f*c + i*g, h' = o*tanh(c') in registers.  z_planes: PVG_CORR_FP16_ALL planes of the padded channel concat
+ * [inputs..., h] [N,H,W,d->Cin]; w_planes: planes of the packed weight (pvg_pack_conv_weight + pvg_pack_16x2), d->Cout = 4C;
+ * gates_act (NULL for inference): [N,H,W,4C] ACTIVATED gates, interleaved - what pvg_lstm_bwd_act needs. */
+int pvg_convlstm_step(const pvg_conv_desc* d, const void* z_planes, const void* w_planes, const float* bias,
+                      const float* c_prev, float* c_new, float* h_new, float* gates_act, void* stream);
+/* backward of the point-wise part from the ACTIVATED, interleaved gates: dgates (pre-activation gradients, interleaved) and
+ * dc_prev; dh / dc_new may be NULL */
+int pvg_lstm_bwd_act(const float* gates_act, const float* c_prev, const float* c_new, const float* dh, const float* dc_new,
+                     int64_t M, int C, float* dgates, float* dc_prev, void* stream);
 int pvg_lstm_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc_new,
                  int64_t M, int C, float* dgates, float* dc_prev, void* stream);
 

@@ -8,7 +8,7 @@ from ctypes import c_double, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpvg_b200.so")
 
-ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_LSTM = 0, 1, 2, 3, 4, 5
 ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PERSISTENT = 0, 1, 2, 3
 CORR_BF16, CORR_FP16, CORR_FP16_ALL = 0, 1, 2
 
@@ -70,6 +70,8 @@ _SIGNATURES = {
     "pvg_maxpool2_fwd": [P, c_int, c_int, c_int, c_int, P, P],
     "pvg_maxpool2_bwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P],
     "pvg_lstm_fwd": [P, P, c_int64, c_int, P, P, P],
+    "pvg_convlstm_step": [POINTER(ConvDesc), P, P, P, P, P, P, P, P],
+    "pvg_lstm_bwd_act": [P, P, P, P, P, c_int64, c_int, P, P, P],
     "pvg_lstm_bwd": [P, P, P, P, P, c_int64, c_int, P, P, P],
     "pvg_absdiff_mean_fwd": [P, P, c_int, c_int64, P, P],
     "pvg_absdiff_mean_bwd": [P, P, P, c_int, c_int64, P, P],

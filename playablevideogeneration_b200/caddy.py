@@ -204,8 +204,13 @@ class ConvLSTMCell(nn.Module):
         self.output_gate = _conv(in_planes + out_planes, out_planes, 3, True)
         self.cell_gate = _conv(in_planes + out_planes, out_planes, 3, True)
 
-    def fused(self):
+    def fused(self, interleaved: bool = False):
+        """The four gate convolutions as one weight / bias: stacked [i; f; o; g] (N = 4C), or with the output channels
+        INTERLEAVED (row 4c + gate) - the layout whose conv epilogue holds all four gates of a channel in one thread."""
         gates = (self.input_gate, self.forget_gate, self.output_gate, self.cell_gate)
+        if interleaved:
+            w = torch.stack([g.weight for g in gates], dim=1)
+            return w.reshape((-1,) + tuple(w.shape[2:])), torch.stack([g.bias for g in gates], dim=1).reshape(-1)
         return torch.cat([g.weight for g in gates], 0), torch.cat([g.bias for g in gates], 0)
 
 
@@ -228,11 +233,15 @@ class ConvLSTM(nn.Module):
         if self._h is None:
             self._h = ops.nhwc(self.initial_hidden_state.unsqueeze(0).expand(batch, -1, -1, -1))
             self._c = ops.nhwc(self.initial_hidden_cell_state.unsqueeze(0).expand(batch, -1, -1, -1))
+        fused_cell = ops.supports_fused_lstm() and self.cell.input_gate.out_channels % 4 == 0
         if self._w is None:
-            self._w, self._b = self.cell.fused()
+            self._w, self._b = self.cell.fused(interleaved=fused_cell)
         z = ops.concat_pad(list(inputs) + [self._h], planes=ops.conv_input_planes())
-        gates = ops.conv2d(z, self._w, self._b)
-        self._h, self._c = ops.lstm_cell(gates, self._c)
+        if fused_cell:          # gate convolution with sigmoid / tanh / c-update / h-output fused into its epilogue: one launch
+            self._h, self._c = ops.convlstm_step(z, self._w, self._b, self._c)
+        else:
+            gates = ops.conv2d(z, self._w, self._b)
+            self._h, self._c = ops.lstm_cell(gates, self._c)
         return self._h
 
 
@@ -446,7 +455,7 @@ class GraphedRollout:
             self.c = [ops.nhwc(l.initial_hidden_cell_state.detach().unsqueeze(0).expand(b, -1, -1, -1)).clone() for l in self.lstms]
             rng = torch.get_rng_state()          # warm-up and capture run the host-side noise draw: not part of the rollout
             for l in self.lstms:
-                l._w, l._b = l.cell.fused()
+                l._w, l._b = l.cell.fused(interleaved=ops.supports_fused_lstm() and l.cell.input_gate.out_channels % 4 == 0)
             for _ in range(2):                    # eager warm-up: weight packs, kernel attributes, the tf32 probe
                 self._bind()
                 model._rollout_step(self.obs, self.onehot, self.var)

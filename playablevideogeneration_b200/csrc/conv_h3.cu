@@ -109,6 +109,36 @@ __device__ __forceinline__ void store_planes16(const float (&v)[16], uint16_t* _
   pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
 }
 
+// ConvLSTM cell point-wise part fused into the gate convolution's epilogue (convolutional_lstm_cell.py:92-101).  The four gate
+// convolutions are ONE GEMM whose output channels are interleaved: column 4 * c + {0, 1, 2, 3} = input / forget / output / cell
+// gate of hidden channel c, so a thread that holds 16 consecutive accumulator columns of its pixel holds all four gates of 4
+// hidden channels: bias, sigmoid / tanh, c' = f * c + i * g and h' = o * tanh(c') happen in registers.  The ACTIVATED gates are
+// stored (training: the backward pass needs them; pass gates == NULL for inference).
+__device__ __forceinline__ void lstm_finish16(const float (&v)[16], const float* __restrict__ bias, int co, int Cout, bool valid,
+                                              const float* __restrict__ c_prev, float* __restrict__ c_new, float* __restrict__ h_new,
+                                              float* __restrict__ gates, int64_t pix) {
+  if (!valid || co >= Cout) return;
+  const int C = Cout >> 2, ch0 = co >> 2;
+  float4 cp = ldg4(c_prev + pix * C + ch0);
+  const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+  float cn[4], hn[4], ga[16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 b = bias != nullptr ? ldg4(bias + co + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float gi = 1.f / (1.f + expf(-(v[4 * k] + b.x))), gf = 1.f / (1.f + expf(-(v[4 * k + 1] + b.y)));
+    const float go = 1.f / (1.f + expf(-(v[4 * k + 2] + b.z))), gc = tanhf(v[4 * k + 3] + b.w);
+    cn[k] = gf * cpv[k] + gi * gc;
+    hn[k] = go * tanhf(cn[k]);
+    ga[4 * k] = gi; ga[4 * k + 1] = gf; ga[4 * k + 2] = go; ga[4 * k + 3] = gc;
+  }
+  stg4(c_new + pix * C + ch0, make_float4(cn[0], cn[1], cn[2], cn[3]));
+  stg4(h_new + pix * C + ch0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+  if (gates != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) stg4(gates + pix * Cout + co + 4 * k, make_float4(ga[4 * k], ga[4 * k + 1], ga[4 * k + 2], ga[4 * k + 3]));
+  }
+}
+
 template <int BN, bool HALO, bool PAIR>
 __global__ void __launch_bounds__(kH3Threads, 1)
 conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
@@ -349,6 +379,10 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = acc[c + j];
+        if (p.act == PVG_ACT_LSTM) {          // fused ConvLSTM cell: p.y = activated gates (optional), Cout = 4 * hidden channels
+          lstm_finish16(v, p.bias, t.co0 + c, p.Cout, valid, p.lstm_c_prev, p.lstm_c_new, p.lstm_h_new, p.y, pix);
+          continue;
+        }
         finish16(v, p.bias, t.co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);
         if (p.y_planes != nullptr && valid && t.co0 + c < p.Cout) {
           uint16_t* lo_row = p.y_planes + pix * p.Cout;          // Cout % 8 == 0 (checked by the host): 16-byte aligned rows
@@ -382,6 +416,10 @@ static int encode_halo_map(CUtensorMap* m, const void* planes, int N, int H, int
   return 0;
 }
 
+// operands of the fused ConvLSTM epilogue (PVG_ACT_LSTM), set by pvg_convlstm_step around its call of conv2d_fwd_h3
+struct LstmIO { const float* c_prev; float* c_new; float* h_new; };
+static thread_local LstmIO g_lstm = {nullptr, nullptr, nullptr};
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -396,6 +434,7 @@ static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = CinK; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.pad = d->pad;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = 1;
   p.y_planes = (uint16_t*)y_planes; p.y_numel = (int64_t)d->N * d->H * d->W * d->Cout; p.out_scale = out_scale;
+  p.lstm_c_prev = g_lstm.c_prev; p.lstm_c_new = g_lstm.c_new; p.lstm_h_new = g_lstm.h_new;
   static const int dbg = env_int("PVG_H3_DBG", 0);      // timing experiment only (wrong results): haloed tile read without row offsets
   p.dbg = dbg;
   if (HALO) { p.tw = 8; p.th = 16; p.tn = 1; }
@@ -488,4 +527,22 @@ extern "C" int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_plane
   PVG_CHECK_ARG((((uintptr_t)x_planes | (uintptr_t)w_planes | (uintptr_t)y | (uintptr_t)y_planes) & 15) == 0, "operands must be 16-byte aligned");
   PVG_CHECK_ARG(!y_planes || d->Cout % 8 == 0, "y_planes needs Cout % 8 == 0");
   return conv2d_fwd_h3(d, x_planes, w_planes, bias, y, y_planes, out_scale, (cudaStream_t)stream);
+}
+
+// One ConvLSTM cell step: gates = conv3x3([inputs..., h]) as ONE implicit GEMM over interleaved gate columns, with the cell update
+// fused into its epilogue (see lstm_finish16).  z_planes: PVG_CORR_FP16_ALL planes of the (zero-padded) channel concat
+// [N,H,W,d->Cin]; w_planes: planes of the interleaved gate weight pack (d->Cout = 4 * hidden channels, a multiple of 16);
+// bias: interleaved [4C]; c_prev / c_new / h_new: [N,H,W,C]; gates_act (NULL for inference): [N,H,W,4C] activated gates.
+extern "C" int pvg_convlstm_step(const pvg_conv_desc* d, const void* z_planes, const void* w_planes, const float* bias,
+                                 const float* c_prev, float* c_new, float* h_new, float* gates_act, void* stream) {
+  PVG_CHECK_ARG(d && z_planes && w_planes && c_prev && c_new && h_new, "null argument");
+  PVG_CHECK_ARG(d->Cout % 16 == 0 && d->Cin % 8 == 0 && d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "unsupported cell shape");
+  PVG_CHECK_ARG((((uintptr_t)z_planes | (uintptr_t)w_planes | (uintptr_t)bias | (uintptr_t)c_prev | (uintptr_t)c_new | (uintptr_t)h_new |
+                  (uintptr_t)gates_act) & 15) == 0, "operands must be 16-byte aligned");
+  pvg_conv_desc dd = *d;
+  dd.act = PVG_ACT_LSTM;
+  g_lstm.c_prev = c_prev; g_lstm.c_new = c_new; g_lstm.h_new = h_new;
+  const int rc = conv2d_fwd_h3(&dd, z_planes, w_planes, bias, gates_act, nullptr, nullptr, (cudaStream_t)stream);
+  g_lstm.c_prev = nullptr; g_lstm.c_new = nullptr; g_lstm.h_new = nullptr;
+  return rc;
 }

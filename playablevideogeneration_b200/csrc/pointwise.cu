@@ -586,6 +586,23 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const float* __restrict__
   }
 }
 
+// backward of the fused ConvLSTM epilogue (conv_h3.cu): activated gates in interleaved order [M][C][4] = (i, f, o, g)
+__global__ void __launch_bounds__(256) lstm_bwd_act_kernel(const float* __restrict__ ga, const float* __restrict__ c_prev,
+                                                           const float* __restrict__ c_new, const float* __restrict__ dh,
+                                                           const float* __restrict__ dc_new, int64_t total,
+                                                           float* __restrict__ dgates, float* __restrict__ dc_prev) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = ldg4(ga + 4 * i);
+    const float ii = g.x, ff = g.y, oo = g.z, cc = g.w;
+    const float tc = tanhf(__ldg(c_new + i));
+    const float dhj = dh ? __ldg(dh + i) : 0.f;
+    const float dc = (dc_new ? __ldg(dc_new + i) : 0.f) + dhj * oo * (1.f - tc * tc);
+    stg4(dgates + 4 * i, make_float4(dc * cc * ii * (1.f - ii), dc * __ldg(c_prev + i) * ff * (1.f - ff), dhj * tc * oo * (1.f - oo),
+                                     dc * ii * (1.f - cc * cc)));
+    dc_prev[i] = dc * ff;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // L1-type reductions
 // ---------------------------------------------------------------------------------------------------------------
@@ -1164,6 +1181,16 @@ int pvg_lstm_bwd(const float* gates, const float* c_prev, const float* c_new, co
                  int C, float* dgates, float* dc_prev, void* stream) {
   DISPATCH_V(C, (lstm_bwd_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, dh,
                                                                                                dc_new, M, C, dgates, dc_prev)));
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_lstm_bwd_act(const float* gates_act, const float* c_prev, const float* c_new, const float* dh, const float* dc_new, int64_t M,
+                     int C, float* dgates, float* dc_prev, void* stream) {
+  PVG_CHECK_ARG(gates_act && c_prev && c_new && dgates && dc_prev, "null argument");
+  PVG_CHECK_ARG((((uintptr_t)gates_act | (uintptr_t)dgates) & 15) == 0, "gate tensors must be 16-byte aligned");
+  const int64_t total = M * C;
+  lstm_bwd_act_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(gates_act, c_prev, c_new, dh, dc_new, total, dgates, dc_prev);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -292,6 +292,9 @@ struct ConvParams {
   uint16_t* y_planes;           // conv_h3.cu, optional: fp16 plane pair [2][N*H*W*Cout] of y (PVG_CORR_FP16_ALL), written by the
   int64_t y_numel;              //   epilogue so that the next convolution needs no separate split pass; y_numel = N*H*W*Cout
   const float* out_scale;       // conv_h3.cu, optional (device): accumulator scale (1 / S of a scaled gradient operand)
+  const float* lstm_c_prev;     // conv_h3.cu, act == PVG_ACT_LSTM: fused ConvLSTM cell operands [N][H][W][Cout / 4]
+  float* lstm_c_new;
+  float* lstm_h_new;
   int dbg;                      // conv_h3.cu timing experiments
 };
 

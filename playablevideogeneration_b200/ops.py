@@ -852,6 +852,70 @@ def lstm_cell(gates: Tensor, c_prev: Tensor) -> Tuple[Tensor, Tensor]:
     return LSTMCellFn.apply(gates, c_prev)
 
 
+class _CtxShim:
+    """The fields ``_backward_h3`` reads from a Conv2dFn context."""
+
+    def __init__(self, meta, cphys, x_wplanes, needs_input_grad):
+        self.meta, self.cphys, self.x_wplanes, self.needs_input_grad = meta, cphys, x_wplanes, needs_input_grad
+
+
+class ConvLSTMStepFn(torch.autograd.Function):
+    """convolutional_lstm_cell.py:88-101 as ONE launch: the gate convolution over the padded concat z = [inputs..., h] with the
+    cell update fused into its epilogue (pvg_convlstm_step).  ``w_il`` / ``b_il``: the four gate weights / biases INTERLEAVED
+    along the output channels (row 4c + gate).  Backward: pvg_lstm_bwd_act, then the all-fp16 data / weight gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, z, w_il, b_il, c_prev, z_planes):
+        z_in = z
+        z, c_prev = nhwc(z), nhwc(c_prev)
+        if z is not z_in:
+            z_planes = {}
+        fmt = _lib.CORR_FP16_ALL
+        n, cin_p, h, w = z.shape
+        cout, cin_log, r, _ = w_il.shape
+        c = cout // 4
+        packs = _get_packs(w_il, cin_p, True)
+        zp = z_planes[fmt] if fmt in z_planes else _split(z, 2, fmt)[1]
+        need_grad = any(ctx.needs_input_grad[:4])
+        gates = empty_nhwc((n, cout, h, w), z.device) if need_grad else None
+        c_new, h_new = empty_nhwc((n, c, h, w), z.device), empty_nhwc((n, c, h, w), z.device)
+        d = ConvDesc(n, h, w, cin_p, cout, r, r, (r - 1) // 2, ACT_NONE, 0.0, ALGO_UMMA, 2, fmt)
+        prof = conv_profile is not None
+        if prof:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        call("pvg_convlstm_step", d, zp.data_ptr(), packs.lo(0, 2, fmt).data_ptr(), b_il.detach().contiguous().data_ptr(),
+             c_prev.data_ptr(), c_new.data_ptr(), h_new.data_ptr(), _p(gates), _stream())
+        if prof:
+            e1.record()
+            conv_profile.append((e0, e1, 2.0 * n * h * w * cout * r * r * cin_log, "h3"))
+        ctx.save_for_backward(z, w_il, gates, c_prev, c_new)
+        ctx.zp = zp if w_il.requires_grad else None
+        return h_new, c_new
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        z, w_il, gates, c_prev, c_new = ctx.saved_tensors
+        n, c, h, w = c_prev.shape
+        dh = nhwc(dh) if dh is not None else None
+        dc = nhwc(dc) if dc is not None else None
+        dgates, dc_prev = torch.empty_like(gates), torch.empty_like(c_prev)
+        call("pvg_lstm_bwd_act", gates.data_ptr(), c_prev.data_ptr(), c_new.data_ptr(), _p(dh), _p(dc), n * h * w, c,
+             dgates.data_ptr(), dc_prev.data_ptr(), _stream())
+        shim = _CtxShim((ACT_NONE, 0.0, True, w_il.shape[1]), w_il.shape[0], ctx.zp, tuple(ctx.needs_input_grad[:3]))
+        dz, dw, db = _backward_h3(shim, dgates, z, w_il, None)[:3]
+        return dz, dw, db, dc_prev, None
+
+
+def supports_fused_lstm() -> bool:
+    return supports_padded_cout() and os.environ.get("PVG_NO_FUSED_LSTM") != "1"
+
+
+def convlstm_step(z: Tensor, w_il: Tensor, b_il: Tensor, c_prev: Tensor) -> Tuple[Tensor, Tensor]:
+    """(h_new, c_new) of one ConvLSTM cell step; z = padded concat [inputs..., h] (its planes are picked up when attached)."""
+    return ConvLSTMStepFn.apply(z, w_il, b_il, c_prev, planes_of(z))
+
+
 class ConcatPadFn(torch.autograd.Function):
     """Channel concat of 4-D maps and 2-D (N, C) vectors broadcast over H x W (conv_dynamics_network.py:64-109,
     convolutional_lstm_cell.py:35-75), zero-padded to ``c_pad`` physical channels so the result is a legal

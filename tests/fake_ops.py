@@ -85,4 +85,5 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "nhwc", lambda x: x)
     monkeypatch.setattr(ops, "conv_input_planes", lambda weight_grad=True: ())
     monkeypatch.setattr(ops, "supports_padded_cout", lambda: False)
+    monkeypatch.setattr(ops, "supports_fused_lstm", lambda: False)
     monkeypatch.setattr(losses, "_global_l1", lambda gt, rec: F.l1_loss(rec, gt))

@@ -321,6 +321,46 @@ def test_lstm_cell():
     _close("lstm_dc", cg.grad, cprev.grad, 1e-5, 1e-6)
 
 
+@pytest.mark.parametrize("shape", [(2, 201, 224, 128, 32, 32), (3, 137, 160, 64, 13, 10), (8, 521, 544, 256, 16, 16)])
+def test_fused_convlstm_step_matches_fp64(shape):
+    """pvg_convlstm_step (gate convolution + cell update in one launch, interleaved gate columns) and its backward against the
+    reference cell (convolutional_lstm_cell.py:88-101) in float64: four separate gate convolutions, sigmoid / tanh, c', h'."""
+    ops = _ops()
+    n, cin, cin_p, c, h, w = shape
+    z = _rand(n, cin_p, h, w, seed=1)
+    z[:, cin:] = 0
+    ws = [_rand(c, cin, 3, 3, seed=10 + k, scale=(cin * 9) ** -0.5) for k in range(4)]
+    bs = [_rand(c, seed=20 + k, scale=0.1) for k in range(4)]
+    cp = _rand(n, c, h, w, seed=3)
+    zr = z[:, :cin].double().requires_grad_(True)
+    wr = [t.double().requires_grad_(True) for t in ws]
+    br = [t.double().requires_grad_(True) for t in bs]
+    cr = cp.double().requires_grad_(True)
+    gi, gf, go = (torch.sigmoid(F.conv2d(zr, wr[k], br[k], padding=1)) for k in range(3))
+    gc = torch.tanh(F.conv2d(zr, wr[3], br[3], padding=1))
+    cn = gf * cr + gi * gc
+    hn = go * torch.tanh(cn)
+    gh, gcn = _rand(n, c, h, w, seed=4), _rand(n, c, h, w, seed=5)
+    (hn * gh.double() + cn * gcn.double()).sum().backward()
+    zg = z.to(DEV).requires_grad_(True)
+    wg = [t.to(DEV).requires_grad_(True) for t in ws]
+    bg = [t.to(DEV).requires_grad_(True) for t in bs]
+    cg = cp.to(DEV).requires_grad_(True)
+    w_il = torch.stack(wg, dim=1).reshape(4 * c, cin, 3, 3)
+    b_il = torch.stack(bg, dim=1).reshape(-1)
+    assert ops.supports_fused_lstm()
+    h2, c2 = ops.convlstm_step(zg, w_il, b_il, cg)
+    (h2 * gh.to(DEV) + c2 * gcn.to(DEV)).sum().backward()
+    tag = str(shape)
+    _close("fused_lstm_h" + tag, h2, hn, 1e-5, 2e-6)
+    _close("fused_lstm_c" + tag, c2, cn, 1e-5, 2e-6)
+    _close("fused_lstm_dz" + tag, zg.grad[:, :cin], zr.grad, 2e-5, 1e-6)
+    _close("fused_lstm_dc" + tag, cg.grad, cr.grad, 1e-5, 1e-6)
+    for k in range(4):
+        _close(f"fused_lstm_dw{k}" + tag, wg[k].grad, wr[k].grad, 3e-5, 1e-6)
+        _close(f"fused_lstm_db{k}" + tag, bg[k].grad, br[k].grad, 2e-5, 1e-5)
+
+
 def test_concat_pad():
     ops = _ops()
     a, v, hdd = _rand(2, 64, 4, 6, seed=1).requires_grad_(True), _rand(2, 9, seed=2).requires_grad_(True), _rand(2, 128, 4, 6, seed=3).requires_grad_(True)
