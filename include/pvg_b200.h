@@ -254,6 +254,15 @@ int pvg_absdiff_mean_fwd(const float* a, const float* b, int N, int64_t count, d
 int pvg_absdiff_mean_bwd(const float* a, const float* b, const float* gout, int N, int64_t count, float* db,
                          void* stream);
 
+/* ---- evaluator: per-frame squared-error reductions of evaluation/metrics/{mse,psnr,motion_masked_mse}.py and the
+ *      uint8 frame conversion of evaluation/evaluation_dataset_builder.py:66-68,142-154 --------------------------------- */
+/* out[n] (double, zeroed by the caller) = mean over (C, P) of (a - b)^2, n = b * T + t; use_mask: each pixel weighted by
+ * sum_c |a_t - a_(t-1)| / C of the reference frames a (0 for t = 0).  channels_last: element (c, p) at c + p * C, else c * P + p. */
+int pvg_sqdiff_mean(const float* a, const float* b, int N, int T, int C, int64_t P, int channels_last, int use_mask, double* out,
+                    void* stream);
+/* out[i] = (uint8)(v * 255), v = x in [0, 1], or (x + 1) / 2 when any element of x is negative; min_scratch: one int */
+int pvg_frames_to_u8(const float* x, int64_t n, int* min_scratch, uint8_t* out, void* stream);
+
 /* ---- optimiser: torch.optim.Adam(lr, weight_decay) as configured at training/trainer.py:36 -------------------- */
 int pvg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, void* stream);

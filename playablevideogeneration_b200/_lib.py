@@ -76,6 +76,8 @@ _SIGNATURES = {
     "pvg_absdiff_mean_fwd": [P, P, c_int, c_int64, P, P],
     "pvg_absdiff_mean_bwd": [P, P, P, c_int, c_int64, P, P],
     "pvg_frames_u8_to_nhwc": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, P, P],
+    "pvg_sqdiff_mean": [P, P, c_int, c_int, c_int, c_int64, c_int, c_int, P, P],
+    "pvg_frames_to_u8": [P, c_int64, P, P, P],
     "pvg_adam_step": [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P],
     "pvg_adam_step_dev": [P, P, P, P, c_int64, P, P],
 }

@@ -889,6 +889,64 @@ __global__ void __launch_bounds__(256) concat_pad_kernel(const ConcatParts cp, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// evaluator-side reductions and the frame conversion of the evaluation-dataset builder
+// ---------------------------------------------------------------------------------------------------------------
+// out[n] = mean over (c, p) of (a - b)^2 [* motion mask], n = b * T + t.  Element (c, p) of sample n lives at n * C * P + c * sc + p * sp
+// (channels-last: sc = 1, sp = C; planar: sc = P, sp = 1).  With use_mask the weight of pixel p is sum_c |a_t - a_{t-1}| / C of the
+// REFERENCE frames (0 for t = 0): evaluation/metrics/motion_mask.py:13-34, motion_masked_mse.py:23-26.
+__global__ void __launch_bounds__(256) sqdiff_mean_kernel(const float* __restrict__ a, const float* __restrict__ b, int T, int C, int64_t P,
+                                                          int64_t sc, int64_t sp, int use_mask, double* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int t = n % T;
+  const float* pa = a + (int64_t)n * C * P;
+  const float* pb = b + (int64_t)n * C * P;
+  const float* pprev = pa - (int64_t)C * P;          // previous frame of the same sequence (only read when t > 0)
+  double acc = 0.0;
+  if (!(use_mask && t == 0)) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+      float d2 = 0.f, m = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const int64_t o = c * sc + p * sp;
+        const float ra = __ldg(pa + o), d = ra - __ldg(pb + o);
+        d2 += d * d;
+        if (use_mask) m += fabsf(ra - __ldg(pprev + o));
+      }
+      acc += use_mask ? (double)d2 * (double)(m / (float)C) : (double)d2;
+    }
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out + n, red[0] / ((double)C * (double)P));
+}
+
+// smallest element of x as ordered-int bits (atomicMin on the transformed pattern); *min_bits initialised to INT_MAX by the caller
+__device__ __forceinline__ int float_to_ordered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__global__ void __launch_bounds__(256) min_kernel(const float* __restrict__ x, int64_t n, int* __restrict__ min_bits) {
+  float m = 3.0e38f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fminf(m, __ldg(x + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(min_bits, float_to_ordered(m));
+}
+// uint8 frames of the evaluation-dataset builder: x in [-1, 1] (some value negative: (x + 1) / 2 first) or [0, 1] -> (uint8)(x * 255),
+// truncating like numpy's astype (evaluation_dataset_builder.py:66-68,142-154); element order unchanged (channels-last in, HWC out)
+__global__ void __launch_bounds__(256) frames_to_u8_kernel(const float* __restrict__ x, int64_t n, const int* __restrict__ min_bits,
+                                                           uint8_t* __restrict__ out) {
+  const bool shift = *min_bits < 0;                    // ordered-int pattern of a negative float is negative
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = __ldg(x + i);
+    if (shift) v = (v + 1.f) / 2.f;
+    v = v * 255.f;
+    out[i] = (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
+  }
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                                                    float wd, float bc1, float bc2_sqrt, float grad_scale) {
@@ -1332,6 +1390,31 @@ int pvg_frames_u8_to_nhwc(const uint8_t* src, int N, int Hs, int Ws, int left, i
   PVG_CHECK_ARG(stdv != 0.f, "std must not be zero");
   const int64_t total = (int64_t)N * H * W;
   frames_u8_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, total, Hs, Ws, left, top, H, W, mean, stdv, dst);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_sqdiff_mean(const float* a, const float* b, int N, int T, int C, int64_t P, int channels_last, int use_mask, double* out,
+                    void* stream) {
+  PVG_CHECK_ARG(a && b && out && N > 0 && T > 0 && N % T == 0 && C > 0 && P > 0, "bad argument");
+  int gx = (int)ceil_div64(P, 256 * 8);
+  int cap = kSMs * 8 / N;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  sqdiff_mean_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(a, b, T, C, P, channels_last ? 1 : P, channels_last ? C : 1, use_mask, out);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_frames_to_u8(const float* x, int64_t n, int* min_scratch, uint8_t* out, void* stream) {
+  PVG_CHECK_ARG(x && out && min_scratch && n > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int init = 0x7fffffff;
+  PVG_CUDA_OK(cudaMemcpyAsync(min_scratch, &init, sizeof(int), cudaMemcpyHostToDevice, st));
+  min_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, n, min_scratch);
+  PVG_LAUNCH_OK();
+  frames_to_u8_kernel<<<ew_grid(n, 256), 256, 0, st>>>(x, n, min_scratch, out);
   PVG_LAUNCH_OK();
   return 0;
 }

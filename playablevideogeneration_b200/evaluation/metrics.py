@@ -11,6 +11,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ..vgg import Vgg19
 
 
@@ -18,14 +19,17 @@ class MSE(nn.Module):
     """evaluation/metrics/mse.py:12-21."""
 
     def forward(self, reference_observations: torch.Tensor, generated_observations: torch.Tensor) -> torch.Tensor:
-        return torch.mean((reference_observations - generated_observations).pow(2), dim=[2, 3, 4])
+        return ops.sqdiff_mean(reference_observations, generated_observations)          # one fused reduction kernel
 
 
 class PSNR(nn.Module):
     """evaluation/metrics/psnr.py:10-28: -10 log10(mse + 1e-8) of the observations divided by ``range``."""
 
     def forward(self, reference_observations: torch.Tensor, generated_observations: torch.Tensor, range=1.0) -> torch.Tensor:
-        mse = torch.mean((reference_observations / range - generated_observations / range) ** 2, dim=[2, 3, 4])
+        if range == 1.0:
+            mse = ops.sqdiff_mean(reference_observations, generated_observations)
+        else:
+            mse = ops.sqdiff_mean(reference_observations / range, generated_observations / range)
         return -10 * torch.log10(mse + 1e-8)
 
 
@@ -41,8 +45,9 @@ class MotionMaskedMSE(nn.Module):
     """evaluation/metrics/motion_masked_mse.py:14-27: squared error weighted by the reference's frame-difference mask."""
 
     def forward(self, reference_observations: torch.Tensor, generated_observations: torch.Tensor) -> torch.Tensor:
-        mask = frame_difference_motion_mask(reference_observations)
-        return torch.mean((reference_observations - generated_observations).pow(2) * mask, dim=[2, 3, 4])
+        if reference_observations.size(2) != 3:
+            raise AssertionError("the motion mask is defined on RGB frames (evaluation/metrics/motion_mask.py:22)")
+        return ops.sqdiff_mean(reference_observations, generated_observations, motion_mask=True)     # mask computed in the same pass
 
 
 class VGGCosineSimilarity(nn.Module):

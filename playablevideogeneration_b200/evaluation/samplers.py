@@ -51,5 +51,14 @@ def frames_to_uint8_hwc(observations: torch.Tensor) -> torch.Tensor:
     """(..., C, H, W) float frames -> (..., H, W, C) uint8 on the device, the conversion the reference does on the host
     (np.moveaxis + (x * 255).astype(np.uint8), evaluation_dataset_builder.py:66-68 / utils/tensor_displayer.py:25-27):
     a quarter of the bytes cross PCIe."""
+    from .. import ops
+    x = observations
+    if x.is_cuda and x.dtype == torch.float32 and x.dim() >= 4:
+        lead = x.shape[:-3]
+        flat = x.reshape((-1,) + tuple(x.shape[-3:]))
+        if flat.stride()[1:] != (1, flat.shape[3] * flat.shape[1], flat.shape[1]) and flat.shape[1] != 1:
+            flat = flat.contiguous(memory_format=torch.channels_last)          # frames from the model already are channels-last
+        u8 = ops.frames_to_uint8(flat)                                          # one min pass + one conversion pass on the device
+        return u8.permute(0, 2, 3, 1).reshape(tuple(lead) + (flat.shape[2], flat.shape[3], flat.shape[1]))
     x = normalize_range(observations)
     return (x * 255).clamp(0, 255).to(torch.uint8).movedim(-3, -1).contiguous()

@@ -1034,6 +1034,49 @@ def absdiff_mean(a: Tensor, b: Tensor) -> Tensor:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# evaluator-side reductions / frame conversion (no gradients)
+# ---------------------------------------------------------------------------------------------------------------
+def _frame_layout(t: Tensor) -> Optional[bool]:
+    """True: every (b, t) frame of a (bs, T, C, H, W) tensor is channels-last dense; False: planar dense; None: neither."""
+    bs, T, c, h, w = t.shape
+    st = t.stride()
+    if st[0] == T * c * h * w and st[1] == c * h * w:
+        if st[2:] == (h * w, w, 1):
+            return False
+        if (c == 1 or st[2] == 1) and st[3] == w * c and st[4] == c:
+            return True
+    return None
+
+
+def sqdiff_mean(reference: Tensor, generated: Tensor, motion_mask: bool = False) -> Tensor:
+    """(bs, T) mean over (C, H, W) of (reference - generated)^2, optionally weighted per pixel by the reference's frame-difference
+    motion mask (evaluation/metrics/mse.py:21, motion_masked_mse.py:23-26) - one fused reduction."""
+    _check_cuda(reference); _check_cuda(generated)
+    if reference.shape != generated.shape or reference.dim() != 5:
+        raise _lib.PvgError("sqdiff_mean takes two (bs, T, C, H, W) tensors of the same shape")
+    la, lb = _frame_layout(reference), _frame_layout(generated)
+    if la is None or la != lb:
+        reference, generated = reference.contiguous(), generated.contiguous()
+        la = False
+    bs, T, c, h, w = reference.shape
+    out = torch.zeros((bs * T,), dtype=torch.float64, device=reference.device)
+    call("pvg_sqdiff_mean", reference.data_ptr(), generated.data_ptr(), bs * T, T, c, h * w, 1 if la else 0, 1 if motion_mask else 0,
+         out.data_ptr(), _stream())
+    return out.float().reshape(bs, T)
+
+
+def frames_to_uint8(x: Tensor) -> Tensor:
+    """uint8 copy of x in its own element order: (x * 255) truncated, after (x + 1) / 2 when any element is negative."""
+    _check_cuda(x)
+    if not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)):
+        x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device).as_strided(x.shape, x.stride())
+    scratch = torch.empty((1,), dtype=torch.int32, device=x.device)
+    call("pvg_frames_to_u8", x.data_ptr(), x.numel(), scratch.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # optimiser
 # ---------------------------------------------------------------------------------------------------------------
 def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, beta1: float = 0.9, beta2: float = 0.999,

@@ -64,6 +64,14 @@ def concat_pad(parts, multiple=32, planes=()):
     return out
 
 
+def sqdiff_mean(reference, generated, motion_mask=False):
+    d = (reference - generated).pow(2)
+    if motion_mask:
+        m = torch.abs(reference[:, 1:] - reference[:, :-1]).sum(dim=2, keepdim=True) / reference.shape[2]
+        d = d * torch.cat([torch.zeros_like(m[:, 0:1]), m], dim=1)
+    return d.mean(dim=[2, 3, 4])
+
+
 def absdiff_mean(a, b):
     return (a.detach() - b).abs().reshape(a.shape[0], -1).mean(dim=1)
 
@@ -80,7 +88,7 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_dec
 def install(monkeypatch):
     from playablevideogeneration_b200.training import losses
     for name in ("conv2d", "pool_bn_act", "upsample2x", "resize_bilinear", "maxpool2", "lstm_cell", "concat_pad",
-                 "absdiff_mean", "adam_step"):
+                 "absdiff_mean", "sqdiff_mean", "adam_step"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "nhwc", lambda x: x)
     monkeypatch.setattr(ops, "conv_input_planes", lambda weight_grad=True: ())

@@ -481,6 +481,34 @@ def test_absdiff_mean():
     _close("absdiff_bwd", bg.grad, b.grad, 1e-6, 1e-9)
 
 
+def test_evaluator_reductions_and_uint8_frames():
+    """pvg_sqdiff_mean (MSE / PSNR / motion-masked MSE of evaluation/metrics/*.py in one pass, both frame layouts) and
+    pvg_frames_to_u8 (the builder's uint8 conversion) against their plain torch expressions."""
+    ops = _ops()
+    from playablevideogeneration_b200.evaluation.samplers import frames_to_uint8_hwc
+    ref = torch.rand((2, 5, 3, 20, 28), generator=torch.Generator().manual_seed(1))
+    gen = (ref + 0.1 * _rand(2, 5, 3, 20, 28, seed=2)).clamp(0, 1)
+    want = (ref - gen).pow(2).mean(dim=[2, 3, 4])
+    mask = torch.abs(ref[:, 1:] - ref[:, :-1]).sum(dim=2, keepdim=True) / 3
+    mask = torch.cat([torch.zeros_like(mask[:, 0:1]), mask], dim=1)
+    want_m = ((ref - gen).pow(2) * mask).mean(dim=[2, 3, 4])
+    for layout in ("planar", "channels_last"):
+        a, b = ref.to(DEV), gen.to(DEV)
+        if layout == "channels_last":
+            a = a.reshape(10, 3, 20, 28).contiguous(memory_format=torch.channels_last).reshape(2, 5, 3, 20, 28)
+            b = b.reshape(10, 3, 20, 28).contiguous(memory_format=torch.channels_last).reshape(2, 5, 3, 20, 28)
+        _close("sqdiff_" + layout, ops.sqdiff_mean(a, b), want, 2e-6, 1e-9)
+        _close("sqdiff_mask_" + layout, ops.sqdiff_mean(a, b, motion_mask=True), want_m, 2e-6, 1e-10)
+    for rng in ("signed", "unit"):
+        x = _rand(3, 3, 16, 24, seed=3).clamp(-1, 1) if rng == "signed" else torch.rand((3, 3, 16, 24), generator=torch.Generator().manual_seed(4))
+        xn = (x + 1) / 2 if float(x.min()) < 0 else x
+        want_u8 = (xn * 255).clamp(0, 255).to(torch.uint8).movedim(-3, -1).contiguous()
+        for fmt in (torch.contiguous_format, torch.channels_last):
+            got = frames_to_uint8_hwc(x.to(DEV).contiguous(memory_format=fmt))
+            assert got.dtype == torch.uint8 and tuple(got.shape) == (3, 16, 24, 3)
+            assert torch.equal(got.cpu(), want_u8), (rng, fmt, int((got.cpu() != want_u8).sum()))
+
+
 def test_adam_matches_torch():
     ops = _ops()
     p0, steps = _rand(1000, seed=1), 3
