@@ -90,6 +90,10 @@ int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const vo
  * MN-major operands, split-K; scratch / dw_oihw / accumulate as for pvg_conv2d_wgrad_umma. */
 int pvg_conv2d_wgrad_planes(const pvg_conv_desc* d, int Cin_logical, const void* x_planes, const void* g_planes,
                             const float* out_scale, float* scratch, float* dw_oihw, int accumulate, void* stream);
+/* dw_oihw == NULL defers the unpack: a weight that is used at every time step (autograd sums over its uses,
+ * training/trainer.py:584-587) lets all its uses accumulate their split-K partials in ONE scratch and unpacks once: */
+int pvg_unpack_dw(const float* scratch, int Cout, int Cin_logical, int R, int S, int CinPhys, float* dw_oihw, int accumulate,
+                  void* stream);
 /* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinK] and data-gradient pack [CinRows][R][S][CoutK] with flipped
  * taps (dgrad = pvg_conv2d_fwd(dy, bwd pack)).  CinRows >= Cin: physical channels of the activation (zero-padded concat
  * buffers); CinK >= CinRows, CoutK >= Cout: K-side channel counts of the consumer (tensor-core kernels: rounded up to 32,

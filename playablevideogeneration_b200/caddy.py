@@ -75,7 +75,8 @@ class NoiseSource:
         self._host = torch.empty((max(total, 1),), dtype=torch.float32)
         if self._flat is not None and self._flat.is_cuda:
             self._host = self._host.pin_memory()
-        self._host_event = None
+        self._host_event = self._commit_event = self._stage_buf = None
+        self._staged = False
         self.bufs, self._spans, off = [], [], 0
         for (kind, shape, dev), n in zip(self.plan, sizes):
             if dev is None:
@@ -89,17 +90,50 @@ class NoiseSource:
         self.refill()
 
     def refill(self):
+        """Draw the next step's numbers and put them where the (captured) step reads them."""
+        self.stage()
+        self.commit()
+
+    def stage(self, stream=None):
+        """First half of a refill: the CPU draws (recorded order = the reference's RNG stream) and their upload into a STAGING
+        device buffer, optionally on a side stream - safe while a replay that reads the live buffer is still running."""
         if self._host_event is not None:
             self._host_event.synchronize()              # the previous upload has read the pinned buffer
         for (kind, shape, dev), span in zip(self.plan, self._spans):
             t = self._draw(kind, shape)                 # drawn even when unused: keeps the CPU RNG stream of the reference
             if span is not None:
                 self._host[span[0]:span[0] + span[1]].copy_(t.reshape(-1))
+        if self._flat is None:
+            return
+        if not self._flat.is_cuda:
+            self._stage_buf = self._host
+            self._staged = True
+            return
+        if self._stage_buf is None:
+            self._stage_buf = torch.empty_like(self._flat)
+        cur = torch.cuda.current_stream()
+        st = stream if stream is not None else cur
+        if self._commit_event is not None:
+            st.wait_event(self._commit_event)           # the last commit has read the staging buffer
+        with torch.cuda.stream(st):
+            self._stage_buf.copy_(self._host, non_blocking=True)
+            self._host_event = torch.cuda.Event()
+            self._host_event.record(st)
+        self._staged = True
+
+    def commit(self):
+        """Second half: staging -> live buffer, device to device on the current stream (in front of the replay)."""
         if self._flat is not None:
-            self._flat.copy_(self._host, non_blocking=True)
+            if not self._staged:
+                self.stage()
             if self._flat.is_cuda:
-                self._host_event = torch.cuda.Event()
-                self._host_event.record()
+                torch.cuda.current_stream().wait_event(self._host_event)
+                self._flat.copy_(self._stage_buf, non_blocking=True)
+                self._commit_event = torch.cuda.Event()
+                self._commit_event.record()
+            else:
+                self._flat.copy_(self._stage_buf)
+        self._staged = False
         self.cursor = 0
 
 

@@ -406,7 +406,7 @@ extern "C" int pvg_conv2d_wgrad_umma(const pvg_conv_desc* d, int Cin_logical, co
 // latter of dY * S; the result is multiplied by *out_scale = 1 / S.
 extern "C" int pvg_conv2d_wgrad_planes(const pvg_conv_desc* d, int Cin_logical, const void* x_planes, const void* g_planes,
                                        const float* out_scale, float* scratch, float* dw_oihw, int accumulate, void* stream) {
-  PVG_CHECK_ARG(d && x_planes && g_planes && scratch && dw_oihw, "null argument");
+  PVG_CHECK_ARG(d && x_planes && g_planes && scratch, "null argument");
   PVG_CHECK_ARG(d->Cin % 8 == 0 && d->Cout % 8 == 0, "16-bit planes need Cin % 8 == 0 and Cout % 8 == 0");
   PVG_CHECK_ARG((((uintptr_t)x_planes | (uintptr_t)g_planes) & 15) == 0, "planes must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -419,8 +419,20 @@ extern "C" int pvg_conv2d_wgrad_planes(const pvg_conv_desc* d, int Cin_logical, 
   else if (co <= 96) rc = launch_wgrad<96, 4>(d, nullptr, xp, nullptr, gp, scratch, st, out_scale);
   else rc = launch_wgrad<128, 4>(d, nullptr, xp, nullptr, gp, scratch, st, out_scale);
   if (rc) return rc;
+  if (dw_oihw == nullptr) return 0;       // deferred: the split-K partials of further uses keep meeting in `scratch` (pvg_unpack_dw)
   int64_t total = (int64_t)d->Cout * Cin_logical * d->R * d->S;
   unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, st>>>(scratch, d->Cout, Cin_logical, d->R, d->S, (d->Cin + 31) & ~31, dw_oihw, accumulate);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+// packed [Cout][R*S][roundup(CinPhys, 32)] weight-gradient scratch -> OIHW (the second half of the weight-gradient entry points,
+// for callers that let several uses of one weight accumulate in the same scratch and unpack once)
+extern "C" int pvg_unpack_dw(const float* scratch, int Cout, int Cin_logical, int R, int S, int CinPhys, float* dw_oihw, int accumulate,
+                             void* stream) {
+  PVG_CHECK_ARG(scratch && dw_oihw && Cout > 0 && Cin_logical > 0 && CinPhys >= Cin_logical, "bad argument");
+  int64_t total = (int64_t)Cout * Cin_logical * R * S;
+  unpack_dw_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(scratch, Cout, Cin_logical, R, S, (CinPhys + 31) & ~31, dw_oihw, accumulate);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -587,19 +587,23 @@ def _backward_h3(ctx, dy, x, weight, y):
             conv_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log, "h3"))
     if ctx.needs_input_grad[1]:
         xp = ctx.x_wplanes if ctx.x_wplanes is not None else _split(x, 2, _lib.CORR_FP16_ALL)[1]
-        dw = torch.empty((cout, cin_log, r, s), dtype=torch.float32, device=dev)
-        scratch = zero_pool.zeros((cout * r * s * _pad32(cin_p),), torch.float32, dev)
+        deferred = wgrad_defer.active
+        if deferred:
+            dw, scratch = None, wgrad_defer.scratch_for(weight, cin_p, cout, r, s, dev)
+        else:
+            dw = torch.empty((cout, cin_log, r, s), dtype=torch.float32, device=dev)
+            scratch = zero_pool.zeros((cout * r * s * _pad32(cin_p),), torch.float32, dev)
         d = ConvDesc(n, h, w, cin_p, cout, r, s, (r - 1) // 2, ACT_NONE, 0.0, ALGO_UMMA, 2, _lib.CORR_FP16_ALL)
         prof = wgrad_profile is not None
         if prof:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         call("pvg_conv2d_wgrad_planes", d, cin_log, xp.data_ptr(), planes.data_ptr(), inv.data_ptr(), scratch.data_ptr(),
-             dw.data_ptr(), 0, st)
+             _p(dw), 0, st)
         if prof:
             e1.record()
             wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log))
-        if cout != cout_log:
+        if dw is not None and cout != cout_log:
             dw = dw[:cout_log]
     if need_g:
         db = torch.empty((cout,), dtype=torch.float32, device=dev)
@@ -850,6 +854,71 @@ class LSTMCellFn(torch.autograd.Function):
 
 def lstm_cell(gates: Tensor, c_prev: Tensor) -> Tuple[Tensor, Tensor]:
     return LSTMCellFn.apply(gates, c_prev)
+
+
+class _WgradDefer:
+    """One weight-gradient scratch per weight and optimiser step.  A weight of the time loop is used T - 1 times per step;
+    autograd would run, per use, a split-K weight-gradient launch, an unpack to OIHW and an accumulation kernel (1 765
+    accumulations per BAIR-256 step, round 1).  Between ``begin()`` and ``flush()`` the all-fp16 weight-gradient kernel of every
+    use adds its partial sums (already multiplied by that use's 1 / S) into ONE packed scratch; ``flush()`` unpacks each scratch
+    once, straight into ``weight.grad`` (leaf parameters: the flat gradient arena) or through ``torch.autograd.backward`` for
+    derived weights (the interleaved ConvLSTM gate weight).  Same sum as autograd's (trainer.py:584-587), fewer launches."""
+
+    def __init__(self):
+        self.active = False
+        self.entries = {}
+
+    def begin(self):
+        self.entries = {}
+        self.active = os.environ.get("PVG_NO_WGRAD_DEFER") != "1"
+
+    def scratch_for(self, weight, cin_p, cout_phys, r, s, device):
+        key = (weight.data_ptr(), tuple(weight.shape), cin_p, cout_phys)
+        e = self.entries.get(key)
+        if e is None:
+            e = dict(weight=weight, cin_p=cin_p, cout=cout_phys, r=r, s=s,
+                     scratch=zero_pool.zeros((cout_phys * r * s * _pad32(cin_p),), torch.float32, device))
+            self.entries[key] = e
+        return e["scratch"]
+
+    def flush(self, on_leaf_grad=None, resolve=None):
+        """Unpacks every scratch into its weight's gradient; ``on_leaf_grad(param)`` is called for each leaf parameter that
+        received one (what a post-accumulate hook would have seen); ``resolve(data_ptr)`` maps a weight's storage address to the
+        owning parameter object (the flat arena knows it), so the gradient lands in THE parameter's ``.grad`` whatever tensor
+        object autograd handed to the backward function."""
+        self.active = False
+        entries, self.entries = self.entries, {}
+        derived = []
+        for e in entries.values():
+            w = e["weight"]
+            if resolve is not None and w.is_leaf:
+                owner = resolve(w.data_ptr())
+                if owner is not None and tuple(owner.shape) == tuple(w.shape):
+                    w = owner
+            cout_log, cin_log, r, s = w.shape
+            st = _stream()
+            if w.is_leaf and e["cout"] == cout_log and w.grad is not None and w.grad.is_contiguous():
+                call("pvg_unpack_dw", e["scratch"].data_ptr(), cout_log, cin_log, r, s, e["cin_p"], w.grad.data_ptr(), 1, st)
+                if on_leaf_grad is not None:
+                    on_leaf_grad(w)
+                continue
+            dw = torch.empty((e["cout"], cin_log, r, s), dtype=torch.float32, device=w.device)
+            call("pvg_unpack_dw", e["scratch"].data_ptr(), e["cout"], cin_log, r, s, e["cin_p"], dw.data_ptr(), 0, st)
+            dw = dw[:cout_log]
+            if w.is_leaf:
+                if w.grad is None:
+                    w.grad = dw.contiguous()
+                else:
+                    w.grad.add_(dw)
+                if on_leaf_grad is not None:
+                    on_leaf_grad(w)
+            else:
+                derived.append((w, dw))
+        if derived:         # e.g. the interleaved gate weight of a ConvLSTM: its stack / reshape graph has not been walked yet
+            torch.autograd.backward([w for w, _ in derived], [g for _, g in derived])
+
+
+wgrad_defer = _WgradDefer()
 
 
 class _CtxShim:

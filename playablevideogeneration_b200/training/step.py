@@ -45,6 +45,17 @@ class FlatArena:
         for i, p in enumerate(self.params):
             p.register_post_accumulate_grad_hook(lambda _p, i=i: self.touched.add(i))
         self.steps = [0] * len(self.params)
+        self._index_of = {p.data_ptr(): i for i, p in enumerate(self.params)}
+
+    def param_at(self, data_ptr: int):
+        i = self._index_of.get(data_ptr)
+        return None if i is None else self.params[i]
+
+    def touch(self, param) -> None:
+        """A gradient was written into ``param``'s slice of the gradient arena outside autograd (ops.wgrad_defer.flush)."""
+        i = self._index_of.get(param.data_ptr())
+        if i is not None:
+            self.touched.add(i)
 
     def zero_grad(self):
         self.touched.clear()
@@ -334,7 +345,11 @@ class TrainStep:
         try:
             total, info, _ = self.compute_losses(batch_tuple, ground_truth_observations_count, gumbel_temperature, pretraining)
             self.arena.zero_grad()
-            total.backward()
+            ops.wgrad_defer.begin()                      # one weight-gradient scratch per weight for the whole backward pass
+            try:
+                total.backward()
+            finally:
+                ops.wgrad_defer.flush(self.arena.touch, self.arena.param_at)
             self.optimizer_step()
         finally:
             ops.zero_pool.end()
@@ -398,6 +413,8 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
             self._copy_done.record(self._copy_stream)
         self._staged = batch
+        # the next step's random numbers too: drawn now (same CPU RNG order), uploaded to a staging buffer on the side stream
+        self.step.module.noise.stage(self._copy_stream)
 
     def __call__(self, batch=None):
         if batch is not None:
@@ -409,7 +426,7 @@ class GraphedTrainStep:
             else:
                 for dst, src in zip(self.static_batch, batch):
                     dst.copy_(src, non_blocking=True)
-        self.step.module.noise.refill()
+        self.step.module.noise.commit()              # (draws +) staging -> live noise buffers, in front of the replay
         self.step.prepare_replay()
         self.graph.replay()
         # The replay re-packed the weights it USED (W_k) into its own pack buffers and then Adam wrote W_{k+1}: anything that
