@@ -82,7 +82,10 @@ int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo, con
  * y_planes (optional, Cout % 8 == 0): fp16 [2][N*H*W*Cout], the plane pair of y, written by the epilogue so that the next
  * convolution needs no separate split pass (vgg.py:48-52 conv -> relu -> conv chains, residual_block.py:52-57). */
 int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
-                          void* y_planes, const float* out_scale, void* stream);
+                          void* y_planes, const float* out_scale, double* bn_sums, int bn_groups, void* stream);
+/* bn_sums (optional; double[bn_groups][2][Cout], zero-initialised by the caller; d->act == PVG_ACT_NONE): the epilogue also
+ * accumulates the per-channel sum and sum of squares of y per batch group - the statistics of the BatchNorm that follows the
+ * convolution (residual_block.py:52-58, up_block.py:37-38), i.e. pvg_bn_stats without its pass over y. */
 /* out_scale (optional, one float in DEVICE memory): the accumulator is multiplied by it before bias / activation - the 1 / S of
  * a scaled gradient operand (pvg_split_16_scaled) when the call computes a data gradient (w_planes = the flipped pack). */
 /* Weight gradient from plane pairs only: x_planes = PVG_CORR_FP16_ALL planes of x [N,H,W,d->Cin] (the forward operand, reused),

@@ -144,6 +144,33 @@ def _conv(cin, cout, k, bias):
 _DEFAULT_NOISE = NoiseSource()
 
 
+def _fold_eval_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """Inference: BatchNorm (running statistics) folded into the preceding bias-free convolution - ``w' = w * s``, ``b' = beta -
+    mean * s`` with ``s = gamma / sqrt(var + eps)`` - so conv -> BN -> LeakyReLU is ONE launch (bias + activation in the conv
+    epilogue) instead of three.  Cached on the conv module; rebuilt when the weight, the BatchNorm parameters / statistics or
+    the optimiser epoch move."""
+    parts = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple(-1 if t is None else t._version for t in parts) + (ops.weights_epoch, conv.weight.data_ptr())
+    hit = getattr(conv, "_pvg_folded", None)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        s = torch.rsqrt(bn.running_var + bn.eps)
+        if bn.weight is not None:
+            s = s * bn.weight
+        w = (conv.weight * s[:, None, None, None]).contiguous()
+        b = -bn.running_mean * s
+        if bn.bias is not None:
+            b = b + bn.bias
+        b = b.contiguous()
+    conv._pvg_folded = (key, w, b)
+    return w, b
+
+
+def _can_fold(bn: nn.BatchNorm2d) -> bool:
+    return (not bn.training) and (not torch.is_grad_enabled()) and bn.running_mean is not None and ops.fold_eval_batchnorm
+
+
 class ResidualBlock(nn.Module):
     """model/layers/residual_block.py:14-68."""
 
@@ -172,12 +199,24 @@ class ResidualBlock(nn.Module):
         need = ops.conv_input_planes()
         cout = self.conv1.out_channels
         cphys = (cout + 7) // 8 * 8 if (cout % 8 and x.shape[1] % 8 == 0 and ops.supports_padded_cout()) else None
-        out = ops.conv2d(x, self.conv1.weight, cout_phys=cphys)
-        out = ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE, planes=need, groups=groups)
-        out = ops.conv2d(out, self.conv2.weight, cout_phys=cphys)
+        fold = cphys is None and not pool and _can_fold(self.bn1)
+        if fold:                # inference: conv1 -> bn1 -> LeakyReLU in one launch
+            w1, b1 = _fold_eval_bn(self.conv1, self.bn1)
+            out = ops.conv2d(x, w1, b1, act=ACT_LRELU, slope=SLOPE, out_planes=True)
+        else:
+            # training: the statistics of an un-pooled BatchNorm input are accumulated by the convolution's own epilogue
+            st = groups if self.bn1.training else 0
+            out = ops.conv2d(x, self.conv1.weight, cout_phys=cphys, bn_stats_groups=0 if pool else st)
+            out = ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE, planes=need, groups=groups)
+        out = ops.conv2d(out, self.conv2.weight, cout_phys=cphys, bn_stats_groups=groups if self.bn2.training else 0)
         if self.downsample is not None:
-            idn = ops.conv2d(x, self.downsample[0].weight, cout_phys=cphys)
-            idn = ops.pool_bn_act(idn, self.downsample[2], pool=pool, act=ACT_NONE, groups=groups)
+            if fold:
+                wd, bd = _fold_eval_bn(self.downsample[0], self.downsample[2])
+                idn = ops.conv2d(x, wd, bd)
+            else:
+                idn = ops.conv2d(x, self.downsample[0].weight, cout_phys=cphys,
+                                 bn_stats_groups=groups if (self.downsample[2].training and not pool) else 0)
+                idn = ops.pool_bn_act(idn, self.downsample[2], pool=pool, act=ACT_NONE, groups=groups)
         else:
             idn = x
         return ops.pool_bn_act(out, self.bn2, residual=idn, act=ACT_LRELU, slope=SLOPE, planes=need if out_planes else (),
@@ -194,8 +233,12 @@ class SameBlock(nn.Module):
         self.bn1 = nn.BatchNorm2d(out_planes)
 
     def forward(self, x):
-        out = ops.conv2d(x, self.conv1.weight)
-        return ops.pool_bn_act(out, self.bn1, pool=self.downsample_factor == 2, act=ACT_LRELU, slope=SLOPE)
+        if self.downsample_factor != 2 and _can_fold(self.bn1):
+            w, b = _fold_eval_bn(self.conv1, self.bn1)
+            return ops.conv2d(x, w, b, act=ACT_LRELU, slope=SLOPE)
+        pool = self.downsample_factor == 2
+        out = ops.conv2d(x, self.conv1.weight, bn_stats_groups=1 if (self.bn1.training and not pool) else 0)
+        return ops.pool_bn_act(out, self.bn1, pool=pool, act=ACT_LRELU, slope=SLOPE)
 
 
 class UpBlock(nn.Module):
@@ -210,8 +253,13 @@ class UpBlock(nn.Module):
     def forward(self, x, out_planes: bool = False, groups: int = 1):
         if not self.late_upscaling:
             x = ops.upsample2x(x, planes=ops.conv_input_planes())
-        x = ops.pool_bn_act(ops.conv2d(x, self.conv.weight), self.norm, act=ACT_LRELU, slope=SLOPE, groups=groups,
-                            planes=ops.conv_input_planes() if (out_planes and not self.late_upscaling) else ())
+        if _can_fold(self.norm):
+            w, b = _fold_eval_bn(self.conv, self.norm)
+            x = ops.conv2d(x, w, b, act=ACT_LRELU, slope=SLOPE, out_planes=out_planes and not self.late_upscaling)
+        else:
+            x = ops.pool_bn_act(ops.conv2d(x, self.conv.weight, bn_stats_groups=groups if self.norm.training else 0), self.norm,
+                                act=ACT_LRELU, slope=SLOPE, groups=groups,
+                                planes=ops.conv_input_planes() if (out_planes and not self.late_upscaling) else ())
         if self.late_upscaling:
             x = ops.upsample2x(x)
         return x

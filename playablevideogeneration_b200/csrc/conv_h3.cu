@@ -47,7 +47,8 @@ struct H3Cfg {
   static constexpr int kAccCols = 3 * BN;                           // [main0 | main1 | correction]
   static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
   static constexpr int kBarBytes = (2 * kASlots + 2 * kBSlots + 5) * 8 + 16;
-  static constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + 1024 + kBarBytes;
+  static constexpr int kStatBytes = 2 * 4 * BN * 2 * 4;            // BatchNorm partial sums: [tile parity][4 warps][BN][sum, sum^2]
+  static constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + 1024 + kBarBytes + kStatBytes + 16;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 128, "invalid N tile");
   static_assert(!PAIR || BN % 32 == 0, "a pair splits the weight rows in two MMA-legal halves");
   static_assert(kBSlots >= 3 && kASlots >= 2, "rings too shallow");
@@ -139,6 +140,38 @@ __device__ __forceinline__ void lstm_finish16(const float (&v)[16], const float*
   }
 }
 
+// Sum of 16 per-lane values over the 32 lanes of a warp with 16 shuffles (instead of 80): every step exchanges half of the
+// values a lane still holds with the lane `offset` away and keeps the other half, so after offsets 16, 8, 4, 2 each lane holds
+// ONE channel's partial sum, completed by the offset-1 step.  Returns the full warp sum of channel
+// ch = 8 * bit4 + 4 * bit3 + 2 * bit2 + bit1 of the lane index (lanes L and L ^ 1 return the same channel).
+__device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float send = h16 ? v[j] : v[j + 8];
+    const float keep = h16 ? v[j + 8] : v[j];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = h8 ? a[j] : a[j + 4];
+    const float keep = h8 ? a[j + 4] : a[j];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = h4 ? b[j] : b[j + 2];
+    const float keep = h4 ? b[j + 2] : b[j];
+    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = h2 ? c[0] : c[1];
+  const float keep = h2 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
 template <int BN, bool HALO, bool PAIR>
 __global__ void __launch_bounds__(kH3Threads, 1)
 conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
@@ -156,6 +189,7 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] main accumulator buffer drained
   uint64_t* cfree_bar = tempty_bar + 2;             // [1] correction accumulator folded into registers: next tile may overwrite it
   uint32_t* tmem_slot = (uint32_t*)(cfree_bar + 1);
+  float* stat_part = (float*)(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);     // [2][4][BN][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = PAIR ? (int)cluster_ctarank() : 0;
@@ -340,7 +374,8 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int periods = (k_iters + period - 1) / period;
     const float out_scale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;      // 1 / S of a scaled gradient operand
     uint32_t pg = 0;
-    for (int item = first_item; item < total_items; item += item_stride) {
+    int tile_it = 0;
+    for (int item = first_item; item < total_items; item += item_stride, ++tile_it) {
       const H3Tile t = h3_decode<PAIR>(item, rank, n_tiles, BN, p);
       const int ow = t.w0 + wi, oh = t.h0 + hi, on = t.n0 + ni;
       const bool valid = ow < p.W && oh < p.H && on < p.N;
@@ -388,6 +423,34 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint16_t* lo_row = p.y_planes + pix * p.Cout;          // Cout % 8 == 0 (checked by the host): 16-byte aligned rows
           store_planes16(v, lo_row, lo_row + p.y_numel, t.co0 + c, p.Cout);
         }
+        if (p.bn_sums != nullptr) {
+          // BatchNorm statistics of the output in the epilogue (no separate pass over y): per-channel sum and sum of squares
+          // of this warp's 32 pixels, 16 shuffles each
+          float sq[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = valid ? v[j] : 0.f; sq[j] = v[j] * v[j]; }
+          const float s1 = warp_sum16(v, lane), s2 = warp_sum16(sq, lane);
+          if ((lane & 1) == 0) {
+            const int ch = c + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            float* dst = stat_part + (((tile_it & 1) * 4 + q) * BN + ch) * 2;
+            dst[0] = s1; dst[1] = s2;
+          }
+        }
+      }
+      if (p.bn_sums != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+        if (row < BN && t.co0 + row < p.Cout) {
+          const float* src = stat_part + ((tile_it & 1) * 4 * BN + row) * 2;
+          const float s1 = src[0] + src[2 * BN] + src[4 * BN] + src[6 * BN];
+          const float s2 = src[1] + src[2 * BN + 1] + src[4 * BN + 1] + src[6 * BN + 1];
+          const int g = t.n0 / p.bn_samples_per_group;            // tiles never straddle groups (checked by the host)
+          if (g < p.bn_groups) {
+            double* o = p.bn_sums + (size_t)g * 2 * p.Cout + t.co0 + row;
+            atomicAdd(o, (double)s1);
+            atomicAdd(o + p.Cout, (double)s2);
+          }
+        }
+        // the partials of tile i + 2 reuse this parity's slots: by then every warp has passed the barrier of tile i + 1
       }
     }
   }
@@ -425,6 +488,10 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// BatchNorm statistics request of the current pvg_conv2d_fwd_planes call (see its bn_sums argument)
+struct BnStatsOut { double* sums; int groups; };
+static thread_local BnStatsOut g_bn = {nullptr, 0};
+
 template <int BN, bool HALO, bool PAIR>
 static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
                      void* y_planes, const float* out_scale, cudaStream_t st) {
@@ -435,11 +502,18 @@ static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = y; p.corr_fp16 = 1;
   p.y_planes = (uint16_t*)y_planes; p.y_numel = (int64_t)d->N * d->H * d->W * d->Cout; p.out_scale = out_scale;
   p.lstm_c_prev = g_lstm.c_prev; p.lstm_c_new = g_lstm.c_new; p.lstm_h_new = g_lstm.h_new;
+  p.bn_sums = nullptr; p.bn_groups = 0; p.bn_samples_per_group = 1;
   static const int dbg = env_int("PVG_H3_DBG", 0);      // timing experiment only (wrong results): haloed tile read without row offsets
   p.dbg = dbg;
   if (HALO) { p.tw = 8; p.th = 16; p.tn = 1; }
   else choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
+  bool stats_after = false;             // BatchNorm statistics requested but this tiling cannot produce them: separate pass
+  if (g_bn.sums != nullptr) {
+    const int spg = d->N / g_bn.groups;
+    if (spg % p.tn == 0) { p.bn_sums = g_bn.sums; p.bn_groups = g_bn.groups; p.bn_samples_per_group = spg; }   // tiles stay inside a group
+    else stats_after = true;
+  }
   CUtensorMap tmA, tmB;
   int rc;
   if (HALO) { if ((rc = encode_halo_map(&tmA, x_planes, d->N, d->H, d->W, d->Cin))) return rc; }
@@ -466,6 +540,7 @@ static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w
   cfg.attrs = attr; cfg.numAttrs = 1;
   PVG_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_h3_kernel<BN, HALO, PAIR>, tmA, tmB, p, items));
   PVG_LAUNCH_OK();
+  if (stats_after) return pvg_bn_stats(y, d->N, d->H * d->W, d->Cout, g_bn.groups, g_bn.sums, (void*)st);
   return 0;
 }
 
@@ -519,14 +594,19 @@ using namespace pvg;
 // y = act(bias + conv(x, w)) with x and w given ONLY as fp16 plane pairs (pvg_split_16 / pvg_pack_16x2 with PVG_CORR_FP16_ALL,
 // or the y_planes of a previous call); y_planes (optional): the plane pair of y for the next convolution.
 extern "C" int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias,
-                                     float* y, void* y_planes, const float* out_scale, void* stream) {
+                                     float* y, void* y_planes, const float* out_scale, double* bn_sums, int bn_groups, void* stream) {
+  PVG_CHECK_ARG(!bn_sums || (bn_groups >= 1 && d && d->N % bn_groups == 0 && d->act == PVG_ACT_NONE),
+                "BatchNorm statistics: N must be divisible by the group count and the epilogue must not apply an activation");
   PVG_CHECK_ARG(d && x_planes && w_planes && y, "null argument");
   PVG_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "empty problem");
   PVG_CHECK_ARG(d->R == d->S && d->pad == (d->R - 1) / 2 && (d->R & 1), "only odd 'same' kernels are supported");
   PVG_CHECK_ARG(d->Cin % 8 == 0, "16-bit planes need Cin % 8 == 0 (16-byte TMA strides)");
   PVG_CHECK_ARG((((uintptr_t)x_planes | (uintptr_t)w_planes | (uintptr_t)y | (uintptr_t)y_planes) & 15) == 0, "operands must be 16-byte aligned");
   PVG_CHECK_ARG(!y_planes || d->Cout % 8 == 0, "y_planes needs Cout % 8 == 0");
-  return conv2d_fwd_h3(d, x_planes, w_planes, bias, y, y_planes, out_scale, (cudaStream_t)stream);
+  g_bn.sums = bn_sums; g_bn.groups = bn_groups;
+  const int rc = conv2d_fwd_h3(d, x_planes, w_planes, bias, y, y_planes, out_scale, (cudaStream_t)stream);
+  g_bn.sums = nullptr; g_bn.groups = 0;
+  return rc;
 }
 
 // One ConvLSTM cell step: gates = conv3x3([inputs..., h]) as ONE implicit GEMM over interleaved gate columns, with the cell update

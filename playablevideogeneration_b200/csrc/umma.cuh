@@ -295,6 +295,8 @@ struct ConvParams {
   const float* lstm_c_prev;     // conv_h3.cu, act == PVG_ACT_LSTM: fused ConvLSTM cell operands [N][H][W][Cout / 4]
   float* lstm_c_new;
   float* lstm_h_new;
+  double* bn_sums;              // conv_h3.cu, optional: [groups][2][Cout] per-channel sum / sum of squares of y (BatchNorm statistics)
+  int bn_groups, bn_samples_per_group;
   int dbg;                      // conv_h3.cu timing experiments
 };
 

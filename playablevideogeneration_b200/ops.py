@@ -186,6 +186,7 @@ def flush_deferred() -> None:
 # ---------------------------------------------------------------------------------------------------------------
 # convolution
 # ---------------------------------------------------------------------------------------------------------------
+fold_eval_batchnorm = os.environ.get("PVG_NO_BN_FOLD") != "1"      # inference: BatchNorm folded into the preceding conv (caddy.py)
 weights_epoch = 0      # bumped by optimisers that update parameters through raw pointers (no autograd version bump)
 
 
@@ -389,9 +390,12 @@ class Conv2dFn(torch.autograd.Function):
     count (zero-padded concat buffers)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, slope, x_planes, out_planes, cout_phys=None):
+    def forward(ctx, x, weight, bias, act, slope, x_planes, out_planes, cout_phys=None, bn_groups=0):
         """``x_planes``: {format: planes} that came with x (may be empty); ``out_planes``: also return the forward-operand
         plane pair of y (all-fp16 forward kernel only)."""
+        # the auxiliary outputs (operand planes, BatchNorm sums) never receive a gradient: do not let autograd allocate and
+        # zero-fill stand-ins for them in the backward pass (298 fp16 fills = 6 GB of writes per BAIR-256 step, ncu launch list)
+        ctx.set_materialize_grads(False)
         x_in = x
         x = nhwc(x)
         if x is not x_in:
@@ -410,6 +414,7 @@ class Conv2dFn(torch.autograd.Function):
         flops = 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * cout * r * s * cin_log
         y_planes = None
         xp_used = None
+        bn_sums = None
         if algo == ALGO_UMMA and nprod == 2 and fmt == _lib.CORR_FP16_ALL:
             # all-fp16 forward conv straight from plane pairs (and, on request, to the plane pair of y)
             xp = xp_used = x_planes[fmt] if fmt in x_planes else _split(x, nprod, fmt)[1]
@@ -422,8 +427,10 @@ class Conv2dFn(torch.autograd.Function):
             if prof:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
+            if bn_groups and act == ACT_NONE and b is None:
+                bn_sums = zero_pool.zeros((bn_groups, 2, cphys), torch.float64, x.device)
             call("pvg_conv2d_fwd_planes", d, xp.data_ptr(), packs.lo(0, 2, fmt).data_ptr(), _p(b), y.data_ptr(), _p(y_planes), None,
-                 _stream())
+                 _p(bn_sums), int(bn_groups) if bn_sums is not None else 0, _stream())
             if prof:
                 e1.record()
                 conv_profile.append((e0, e1, flops, "h3"))
@@ -438,12 +445,15 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.x_wplanes is None and wm == (2, _lib.CORR_FP16_ALL) and xp_used is not None and weight.requires_grad:
             ctx.x_wplanes = xp_used          # the forward operand planes double as the weight-gradient operand
         ctx.x_wfmt = wm[1]
-        if y_planes is not None:
-            ctx.mark_non_differentiable(y_planes)
-        return y, y_planes
+        for t in (y_planes, bn_sums):
+            if t is not None:
+                ctx.mark_non_differentiable(t)
+        return y, y_planes, bn_sums
 
     @staticmethod
-    def backward(ctx, dy, _dy_planes=None):
+    def backward(ctx, dy, _dy_planes=None, _dsums=None):
+        if dy is None:
+            return (None,) * 9
         x, weight, y = ctx.saved_tensors
         act, slope, has_bias, cin_log = ctx.meta
         cout, _, r, s = weight.shape
@@ -546,7 +556,7 @@ class Conv2dFn(torch.autograd.Function):
             db = torch.empty((cout,), dtype=torch.float32, device=dy.device)
             scratch = torch.empty((cout,), dtype=torch.float64, device=dy.device)
             call("pvg_channel_sum", g.data_ptr(), n * h * w, cout, scratch.data_ptr(), db.data_ptr(), _stream())
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 def _backward_h3(ctx, dy, x, weight, y):
@@ -581,7 +591,7 @@ def _backward_h3(ctx, dy, x, weight, y):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         call("pvg_conv2d_fwd_planes", d, planes.data_ptr(), packs.lo(2, 2, _lib.CORR_FP16_ALL).data_ptr(), None, dx.data_ptr(), None,
-             inv.data_ptr(), st)
+             inv.data_ptr(), None, 0, st)
         if prof:
             e1.record()
             conv_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log, "h3"))
@@ -609,7 +619,7 @@ def _backward_h3(ctx, dy, x, weight, y):
         db = torch.empty((cout,), dtype=torch.float32, device=dev)
         scr = torch.empty((cout,), dtype=torch.float64, device=dev)
         call("pvg_channel_sum", g.data_ptr(), n * h * w, cout, scr.data_ptr(), db.data_ptr(), st)
-    return dx, dw, db, None, None, None, None, None
+    return dx, dw, db, None, None, None, None, None, None
 
 
 Conv2dFn._backward_h3 = staticmethod(_backward_h3)
@@ -623,15 +633,21 @@ def supports_padded_cout() -> bool:
 
 
 def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = ACT_NONE, slope: float = 0.0,
-           out_planes: bool = False, cout_phys: Optional[int] = None) -> Tensor:
+           out_planes: bool = False, cout_phys: Optional[int] = None, bn_stats_groups: int = 0) -> Tensor:
     """``out_planes``: the consumer of the result is another tensor-core convolution - have the epilogue write its operand planes.
     ``cout_phys``: write the result physically padded (zero channels) to this many channels - a multiple of 8 - so that a layer
     with an odd channel count (the 65-channel encoder tail, representation_network.py:28) and its consumers stay on the
-    tensor cores."""
+    tensor cores.
+    ``bn_stats_groups`` > 0: the result goes straight into a training-mode BatchNorm with that many batch groups - the conv
+    epilogue accumulates its per-channel statistics (no separate statistics pass over the result)."""
+    if os.environ.get("PVG_NO_EPILOGUE_STATS") == "1":
+        bn_stats_groups = 0
     want = bool(out_planes) and _lib.CORR_FP16_ALL in conv_input_planes(False)
-    y, yp = Conv2dFn.apply(x, weight, bias, act, slope, planes_of(x), want, cout_phys)
+    y, yp, sums = Conv2dFn.apply(x, weight, bias, act, slope, planes_of(x), want, cout_phys, int(bn_stats_groups))
     if yp is not None:
         y._pvg_planes = {_lib.CORR_FP16_ALL: yp}
+    if sums is not None:
+        y._pvg_bn_sums = (sums, int(bn_stats_groups))          # picked up by pool_bn_act (training mode, no pooling)
     return y
 
 
@@ -641,8 +657,12 @@ def conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: int = 
 class PoolBNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, pool, act, slope, eps, momentum,
-                groups, plane_fmts=()):
+                groups, plane_fmts=(), pre_sums=None):
+        ctx.set_materialize_grads(False)
+        x_in = x
         x = nhwc(x)
+        if x is not x_in:
+            pre_sums = None
         n, c, h, w = x.shape
         dev = x.device
         st = _stream()
@@ -655,13 +675,14 @@ class PoolBNActFn(torch.autograd.Function):
         padded = cp != c
         mean = (torch.zeros if padded else torch.empty)((groups, c), dtype=torch.float32, device=dev)
         invstd = (torch.zeros if padded else torch.empty)((groups, c), dtype=torch.float32, device=dev)
-        sums = zero_pool.zeros((groups, 2, c), torch.float64, dev) if (training or pool) else None
+        have_stats = pre_sums is not None and training and not pool and tuple(pre_sums.shape) == (groups, 2, c)
+        sums = pre_sums if have_stats else (zero_pool.zeros((groups, 2, c), torch.float64, dev) if (training or pool) else None)
         if pool:
             xp = empty_nhwc((n, c, oh, ow), dev)
             call("pvg_pool2_stats", x.data_ptr(), n, h, w, c, xp.data_ptr(), groups, sums.data_ptr(), st)
         else:
             xp = x
-            if training:
+            if training and not have_stats:           # else: accumulated by the producing convolution's epilogue
                 call("pvg_bn_stats", x.data_ptr(), n, h * w, c, groups, sums.data_ptr(), st)
         y = empty_nhwc((n, c, oh, ow), dev)
         pa, pb = _alloc_planes(plane_fmts, y.numel(), c, dev)
@@ -696,6 +717,8 @@ class PoolBNActFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dpa=None, _dpb=None):
+        if dy is None:
+            return (None,) * 15
         xp, weight, mean, invstd, y = ctx.saved_tensors
         training, pool, act, slope, groups, has_res, (n, c, h, w) = ctx.meta
         dy = nhwc(dy)
@@ -726,7 +749,7 @@ class PoolBNActFn(torch.autograd.Function):
             if ctx.cp != c:
                 raise _lib.PvgError("channel-padded BatchNorm backward needs the input gradient path")
             call("pvg_bn_bwd_params", sums2.data_ptr(), groups, c, dweight.data_ptr(), dbias.data_ptr(), st)
-        return (dx, dweight, dbias, g_out) + (None,) * 10
+        return (dx, dweight, dbias, g_out) + (None,) * 11
 
 
 def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, groups=1, planes: Sequence[int] = ()):
@@ -738,8 +761,10 @@ def pool_bn_act(x, bn, residual=None, pool=False, act=ACT_NONE, slope=0.2, group
     if training and bn.num_batches_tracked is not None:
         defer_count(bn.num_batches_tracked, groups)         # applied by flush_deferred() at the end of Model.forward
     planes = tuple(planes)[:2]
+    pre = getattr(x, "_pvg_bn_sums", None)
+    pre_sums = pre[0] if (pre is not None and pre[1] == groups and training and not pool) else None
     y, pa, pb = PoolBNActFn.apply(x, bn.weight, bias_or_none(bn), residual, bn.running_mean, bn.running_var, training, pool, act,
-                                  slope, bn.eps, bn.momentum if bn.momentum is not None else 0.1, groups, planes)
+                                  slope, bn.eps, bn.momentum if bn.momentum is not None else 0.1, groups, planes, pre_sums)
     return _attach_planes(y, planes, (pa, pb))
 
 
@@ -755,6 +780,7 @@ class Upsample2xFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, plane_fmts=()):
+        ctx.set_materialize_grads(False)
         x = nhwc(x)
         n, c, h, w = x.shape
         y = empty_nhwc((n, c, 2 * h, 2 * w), x.device)
@@ -769,6 +795,8 @@ class Upsample2xFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dpa=None, _dpb=None):
+        if dy is None:
+            return None, None
         n, c, h, w = ctx.shape
         dy = nhwc(dy)
         dx = empty_nhwc((n, c, h, w), dy.device)
@@ -796,6 +824,7 @@ class MaxPool2Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, plane_fmts=()):
+        ctx.set_materialize_grads(False)
         x = nhwc(x)
         n, c, h, w = x.shape
         y = empty_nhwc((n, c, h // 2, w // 2), x.device)
@@ -809,6 +838,8 @@ class MaxPool2Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dpa=None):
+        if dy is None:
+            return None, None
         x, y = ctx.saved_tensors
         n, c, h, w = x.shape
         dy = nhwc(dy)
@@ -992,6 +1023,7 @@ class ConcatPadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c_pad, plane_fmts, *parts):
+        ctx.set_materialize_grads(False)
         ref = next(p for p in parts if p.dim() == 4)
         n, _, h, w = ref.shape
         out = empty_nhwc((n, c_pad, h, w), ref.device)
@@ -1027,6 +1059,8 @@ class ConcatPadFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dpa=None, _dpb=None):
+        if dout is None:
+            return (None,) * (2 + len(ctx.spans))
         grads = []
         for i, (off, c, dim) in enumerate(ctx.spans):
             if not ctx.needs_input_grad[i + 2]:

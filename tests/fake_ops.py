@@ -20,7 +20,7 @@ def _act(x, act, slope):
     return x
 
 
-def conv2d(x, weight, bias=None, act=ACT_NONE, slope=0.0, out_planes=False, cout_phys=None):
+def conv2d(x, weight, bias=None, act=ACT_NONE, slope=0.0, out_planes=False, cout_phys=None, bn_stats_groups=0):
     cin = weight.shape[1]
     return _act(F.conv2d(x[:, :cin], weight, bias, padding=weight.shape[2] // 2), act, slope)
 
@@ -94,4 +94,5 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "conv_input_planes", lambda weight_grad=True: ())
     monkeypatch.setattr(ops, "supports_padded_cout", lambda: False)
     monkeypatch.setattr(ops, "supports_fused_lstm", lambda: False)
+    monkeypatch.setattr(ops, "fold_eval_batchnorm", False)
     monkeypatch.setattr(losses, "_global_l1", lambda gt, rec: F.l1_loss(rec, gt))

@@ -410,6 +410,29 @@ def test_producer_planes_equal_a_split_pass():
     assert torch.equal(z_planes, z_split)
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 128, 16, 24, 2), (6, 32, 64, 13, 10, 3), (8, 128, 72, 32, 32, 1), (12, 64, 32, 6, 16, 4)])
+def test_conv_epilogue_batchnorm_statistics(shape):
+    """BatchNorm statistics accumulated by the conv epilogue (per batch group) against sums over the conv's own output."""
+    ops = _ops()
+    n, cin, cout, h, w, groups = shape
+    x = _rand(n, cin, h, w, seed=1).to(DEV)
+    wt = _rand(cout if cout % 8 == 0 else 65, cin, 3, 3, seed=2, scale=(cin * 9) ** -0.5).to(DEV)
+    y = ops.conv2d(x, wt, bn_stats_groups=groups, cout_phys=cout if wt.shape[0] != cout else None)
+    sums, g = y._pvg_bn_sums
+    assert g == groups and tuple(sums.shape) == (groups, 2, y.shape[1])
+    yy = y.detach().double().reshape(groups, n // groups, y.shape[1], h * w)
+    ref = torch.stack([yy.sum(dim=(1, 3)), (yy * yy).sum(dim=(1, 3))], dim=1)
+    _close(f"epilogue_stats{shape}", sums.float(), ref.float().cpu(), 2e-6, 1e-5)
+    # and the BatchNorm that consumes them equals the one that computes its own statistics
+    bn = torch.nn.BatchNorm2d(wt.shape[0]).to(DEV).train()
+    import copy
+    bn2 = copy.deepcopy(bn)
+    a = ops.pool_bn_act(y, bn, act=ops.ACT_LRELU, groups=groups)
+    y_plain = y.detach().clone()
+    b = ops.pool_bn_act(y_plain, bn2, act=ops.ACT_LRELU, groups=groups)
+    _close(f"epilogue_stats_bn{shape}", a, b.cpu(), 2e-6, 2e-6)
+
+
 def test_concat_pad_strided_time_slices():
     """Maps handed to the concat as time slices of a (B, T, C, H, W) tensor (batch-strided, NHWC-dense per sample) are read in
     place."""
