@@ -549,6 +549,7 @@ static int dispatch_h3_bn(const pvg_conv_desc* d, const void* xp, const void* wp
                           const float* os, cudaStream_t st) {
   const int co = d->Cout;
   if constexpr (PAIR) {
+    if (co <= 32) return launch_h3<32, HALO, true>(d, xp, wp, bias, y, yp, os, st);
     if (co <= 64) return launch_h3<64, HALO, true>(d, xp, wp, bias, y, yp, os, st);
     return launch_h3<128, HALO, true>(d, xp, wp, bias, y, yp, os, st);
   } else {
@@ -579,8 +580,8 @@ int conv2d_fwd_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_pl
   // over the 74 clusters cost less than the 1-CTA rounds over the 148 SMs.
   const int64_t n_tiles = ceil_div(d->Cout, d->Cout <= 64 ? 64 : 128);
   const int64_t rounds1 = ceil_div64(m_tiles * n_tiles, kSMs), rounds2 = ceil_div64(ceil_div64(m_tiles, 2) * n_tiles, kSMs / 2);
-  bool pair = d->Cout > 32 && rounds2 * 4 <= rounds1 * 5;
-  if (force_pair >= 0) pair = force_pair == 1 && d->Cout > 32;
+  bool pair = d->Cout > 16 && rounds2 * 4 <= rounds1 * 5;          // N = 16 would leave 8-row weight tiles (below the 1 KB tile alignment)
+  if (force_pair >= 0) pair = force_pair == 1 && d->Cout > 16;
   if (halo) return pair ? dispatch_h3_bn<true, true>(d, x_planes, w_planes, bias, y, y_planes, out_scale, st)
                         : dispatch_h3_bn<true, false>(d, x_planes, w_planes, bias, y, y_planes, out_scale, st);
   return pair ? dispatch_h3_bn<false, true>(d, x_planes, w_planes, bias, y, y_planes, out_scale, st)

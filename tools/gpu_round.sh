@@ -83,6 +83,7 @@ case $s in
   ncu_h3b) PVG_H3_HALO=1 PVG_H3_PAIR=0 run ncu_h3b_10 400 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 2 -c 1 -f -o $OUT/prof_h3b_10 python tools/one_conv.py 120 256 64 64 64; PVG_H3_HALO=0 PVG_H3_PAIR=0 run ncu_h3b_00 400 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 2 -c 1 -f -o $OUT/prof_h3b_00 python tools/one_conv.py 120 256 64 64 64 ;;
   ncu_wgrad) run ncu_wgrad_a 400 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad_umma -s 2 -c 1 -f -o $OUT/prof_wgrad_a python tools/one_wgrad.py 8 64 32 256 256; run ncu_wgrad_b 400 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad_umma -s 2 -c 1 -f -o $OUT/prof_wgrad_b python tools/one_wgrad.py 8 128 128 64 64; run wgradb 300 python tools/wgrad_bench.py tf32x3 ;;
   ncu_list2) run ncu_list2 1700 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60000 --csv --log-file $OUT/launches_r02.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
+  ncu_r02) for spec in "vgg3_2 120 256 256 64 64" "enc_res0 128 16 16 128 128" "dec_up2 8 64 32 256 256" "lstm2_gates 8 288 512 32 32" "vgg1_2 120 64 64 256 256"; do set -- $spec; run ncu_$1 300 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 2 -c 1 -f -o $OUT/r02_$1 python tools/one_conv.py $2 $3 $4 $5 $6; python tools/ncu_extract.py $OUT/r02_$1.ncu-rep; done; for spec in "wgrad_dec_up2 8 64 32 256 256" "wgrad_dec_res0 8 128 128 64 64"; do set -- $spec; run ncu_$1 300 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad_umma -s 2 -c 1 -f -o $OUT/r02_$1 python tools/one_wgrad.py $2 $3 $4 $5 $6; python tools/ncu_extract.py $OUT/r02_$1.ncu-rep; done ;;
   h3_matrix) for hp in "0 0" "1 0" "0 1" "1 1"; do set -- $hp; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3_t_$1$2 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "umma_forward_tf32x3 and h3" -p no:cacheprovider; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3_tm_$1$2 200 python tools/tile_model.py tf32x3; PVG_H3_HALO=$1 PVG_H3_PAIR=$2 run h3_tm64_$1$2 200 python tools/tile_model.py tf32x3 64; done ;;
   t_umma) run t_umma 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "umma or conv_backward" -p no:cacheprovider ;;
   tm_h3) PVG_2CTA=0 PVG_PERSISTENT=0 run tm_h3 300 python tools/tile_model.py tf32x3; PVG_2CTA=0 PVG_PERSISTENT=0 run tm_h3_64 300 python tools/tile_model.py tf32x3 64; PVG_2CTA=0 PVG_PERSISTENT=0 PVG_CORR=fp16 run tm_fp16 300 python tools/tile_model.py tf32x3 ;;
