@@ -251,9 +251,13 @@ def _hbm_bytes(name, a):
         return "bn_apply", a[1] * a[2] * a[3] * f * (3 if a[15] else 2)
     if name == "pvg_bn_apply":                       # x, N, HW, C, groups, mean, invstd, w, b, residual
         return "bn_apply", a[1] * a[2] * a[3] * f * (3 if a[9] else 2)
+    if name == "pvg_bn_finalize_apply_ex":           # x, N, HW, C, groups, ..., residual at 15, y at 18, planes_a at 19, planes_b at 21
+        return "bn_apply", a[1] * a[2] * a[3] * (f * (3 if a[15] else 2) + (4 if a[19] else 0) + (4 if a[21] else 0))
+    if name == "pvg_bn_apply_ex":                    # x, N, HW, C, groups, mean, invstd, w, b, residual, act, slope, y, planes_a, fmt, planes_b
+        return "bn_apply", a[1] * a[2] * a[3] * (f * (3 if a[9] else 2) + (4 if a[13] else 0) + (4 if a[15] else 0))
     if name == "pvg_bn_bwd_reduce":                  # dy, y, x, N, HW, C, ..., act at 9
         return "bn_bwd", a[3] * a[4] * a[5] * f * (3 if a[9] else 2)
-    if name == "pvg_bn_bwd_apply":                   # dy, y, x, N, H, W, C, groups, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out
+    if name in ("pvg_bn_bwd_apply", "pvg_bn_bwd_apply_ex"):   # dy, y, x, N, H, W, C, groups, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out
         full = a[3] * a[4] * a[5] * a[6] * f
         small = full / 4 if a[15] else full
         return "bn_bwd", small * (3 if a[11] else 2) + full + (small if a[17] else 0)
@@ -261,6 +265,12 @@ def _hbm_bytes(name, a):
         return "split_16", a[2] * 8
     if name == "pvg_act_bwd_split_16":               # dy, y, act, slope, g, planes, n
         return "split_16", a[6] * 16
+    if name == "pvg_split_16_scaled":                # x, planes, n: read 4, write 2 x 2
+        return "split_16", a[2] * 8
+    if name == "pvg_act_bwd_split_16_scaled":        # dy, y, act, slope, g, planes, n: read 8, write 4 (+ 4 for g)
+        return "split_16", a[6] * (16 if a[4] else 12)
+    if name == "pvg_amax":                           # x, n
+        return "amax", a[1] * 4
     if name == "pvg_act_bwd":
         return "split_16", a[5] * 12
     if name == "pvg_absdiff_mean_fwd":               # a, b, N, count
@@ -275,6 +285,12 @@ def _hbm_bytes(name, a):
         return "resample", a[1] * a[4] * f * (a[2] * a[3] + a[6] * a[7])
     if name == "pvg_maxpool2_fwd":
         return "maxpool", a[1] * a[2] * a[3] * a[4] * f * 1.25
+    if name == "pvg_maxpool2_fwd_ex":                # ..., y, planes_a: + 4 bytes per output element
+        return "maxpool", a[1] * a[2] * a[3] * a[4] * (f * 1.25 + (1 if a[6] else 0))
+    if name == "pvg_resize_bilinear_ex":             # x, N, H, W, C, y, OH, OW, planes_a, fmt_a, planes_b
+        return "resample", a[1] * a[4] * (f * a[2] * a[3] + a[6] * a[7] * (f + (4 if a[8] else 0) + (4 if a[10] else 0)))
+    if name == "pvg_lstm_bwd_act":                   # gates_act, c_prev, c_new, dh, dc_new, M, C
+        return "lstm_pointwise", a[5] * a[6] * 52
     if name == "pvg_maxpool2_bwd":                   # dy, x, y, N, H, W, C
         return "maxpool", a[3] * a[4] * a[5] * a[6] * f * 2.5
     if name == "pvg_lstm_fwd":                       # gates, c_prev, M, C
@@ -506,8 +522,8 @@ def main():
         for a_, b_, f_, kind in prof:
             e = fams.setdefault(kind, [0, 0.0, 0.0])
             e[0] += 1; e[1] += a_.elapsed_time(b_); e[2] += f_
-        names = {"h3": "conv_h3_kernel (forward convs: 3 kind::f16 tcgen05 MMAs per product on fp16 plane pairs, halo-reuse, persistent)",
-                 "tf32": "conv_umma_persistent / conv_umma2_persistent (data gradients: kind::tf32 main product + 2 bf16 corrections)",
+        names = {"h3": "conv_h3_kernel (forward convs and data gradients: 3 kind::f16 tcgen05 MMAs per product on fp16 plane pairs, halo reuse, persistent, CTA pairs)",
+                 "tf32": "conv_umma_persistent / conv_umma2_persistent (legacy path: kind::tf32 main product + 2 bf16 corrections)",
                  "single": "conv_umma_kernel (single TF32 product)"}
         ceil_note = {"h3": "3 f16 MMAs per product: ceiling 1/3 of the bf16 peak", "tf32": "1 TF32 + 2 16-bit MMAs per product (2 TF32 MMA times): ceiling 1/4 of the bf16 peak",
                      "single": "TF32: ceiling 1/2 of the bf16 peak"}
@@ -525,7 +541,7 @@ def main():
         if wprof:
             wms = sum(a_.elapsed_time(b_) for a_, b_, _ in wprof)
             wfl = sum(f_ for _, _, f_ in wprof)
-            wg = dict(bound="tensor", kernel="conv_wgrad_umma_kernel (weight gradients: MN-major kind::tf32 + 2 bf16 corrections, split-K)",
+            wg = dict(bound="tensor", kernel="conv_wgrad_umma_kernel (weight gradients: MN-major fp16 plane pairs, 3 kind::f16 MMAs per product, split-K)" if args.precision == "tf32x3" else "conv_wgrad_umma_kernel (weight gradients, split-K)",
                       launches_per_step=len(wprof), ms_per_step=wms, achieved=wfl / (wms * 1e-3) / 1e12 if wms > 0 else 0.0,
                       peak=peaks["tflops"], unit="TFLOP/s", frac=(wfl / (wms * 1e-3) / 1e12 / peaks["tflops"]) if wms > 0 else 0.0,
                       traffic=tdata.get("wgrad", {}).get("traffic_bytes_per_launch"), share_of_step=wms / ms_dev)
@@ -550,16 +566,17 @@ def main():
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_step_time(w, args.cpu_sample_frames, 1, 0)
-    line = dict(metric=METRIC, value=frames_per_step / (ms_dev * 1e-3), unit="frames/s",
+    metric = METRIC if args.workload == "bair256_b8_t16" else f"frames/sec (train step, {w['H']}x{w['W']}x3, seq={w['T']})"
+    line = dict(metric=metric, value=frames_per_step / (ms_dev * 1e-3), unit="frames/s",
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype={"tf32x3": "f32 (fp32-equivalent split product on the tensor cores: TF32 main term + two correction terms, fp32 accumulate)", "tf32": "tf32",
+                vs_baseline=None, dtype={"tf32x3": "f32 (fp32-equivalent split product on the tensor cores: 22-bit fp16 plane pairs, 3 kind::f16 MMAs per product, fp32 accumulate)", "tf32": "tf32",
                                          "fp32": "f32"}[args.precision],
                 data="synthetic", impl="pvg_b200",
                 config=dict(workload=args.workload, per_gpu_batch=w["B"], seq_len=w["T"], frame=f"{w['H']}x{w['W']}x3",
                             gt_init=w["gt_init"], parallelism=f"dp{world}", precision=args.precision,
                             corrections=dict(ops._corr) if args.precision == "tf32x3" else None,
                             launch="cuda-graph replay of the whole step" if use_graph else "eager (one launch per kernel from Python)",
-                            l2="inputs (100.7 MB/step) and per-step activations (>10 GB) exceed the 126 MB L2; no explicit flush"),
+                            l2=f"per-step activations (>10 GB written and re-read) exceed the 126 MB L2 many times over; inputs are {h2d / 1e6:.1f} MB/step; no explicit flush"),
                 e2e=dict(value=frames_per_step / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d * world,
                          d2h_bytes_per_step=8 * world, ms_per_step=ms_e2e, last_loss=loss_host),
                 gpu_launches=launches, clocks=clocks, roofline=roof, roofline_hbm=roof_hbm, cpu_baseline=cpu_base,

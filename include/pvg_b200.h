@@ -82,7 +82,9 @@ int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo, con
  * y_planes (optional, Cout % 8 == 0): fp16 [2][N*H*W*Cout], the plane pair of y, written by the epilogue so that the next
  * convolution needs no separate split pass (vgg.py:48-52 conv -> relu -> conv chains, residual_block.py:52-57). */
 int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
-                          void* y_planes, const float* out_scale, double* bn_sums, int bn_groups, void* stream);
+                          void* y_planes, const float* out_scale, double* bn_sums, int bn_groups, uint32_t* amax_out, void* stream);
+/* amax_out (optional, one zero-initialised uint32): receives the bit pattern of max|y| - when y is a gradient, the next backward
+ * kernel up the chain takes its power-of-two scale from it and needs no pvg_amax pass over y. */
 /* bn_sums (optional; double[bn_groups][2][Cout], zero-initialised by the caller; d->act == PVG_ACT_NONE): the epilogue also
  * accumulates the per-channel sum and sum of squares of y per batch group - the statistics of the BatchNorm that follows the
  * convolution (residual_block.py:52-58, up_block.py:37-38), i.e. pvg_bn_stats without its pass over y. */
@@ -199,7 +201,7 @@ int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int
 int pvg_bn_bwd_apply_ex(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
                         const float* mean, const float* invstd, const float* weight, int act, float slope,
                         const double* sums2, int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias,
-                        int Cparams, void* stream);   /* Cparams: see pvg_bn_apply_ex */
+                        int Cparams, uint32_t* amax_out, void* stream);   /* Cparams: see pvg_bn_apply_ex; amax_out (optional): max|dx| bits */
 /* dweight[c] = sum_groups sum_gx ; dbias[c] = sum_groups sum_g */
 int pvg_bn_bwd_params(const double* sums2, int groups, int C, float* dweight, float* dbias, void* stream);
 

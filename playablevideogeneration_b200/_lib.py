@@ -31,7 +31,7 @@ P = c_void_p
 # name -> (argtypes); every function returns int (0 = ok) except pvg_last_error / pvg_version / pvg_has_umma
 _SIGNATURES = {
     "pvg_conv2d_fwd": [POINTER(ConvDesc), P, P, P, P, P, P, P],
-    "pvg_conv2d_fwd_planes": [POINTER(ConvDesc), P, P, P, P, P, P, P, c_int, P],
+    "pvg_conv2d_fwd_planes": [POINTER(ConvDesc), P, P, P, P, P, P, P, c_int, P, P],
     "pvg_conv2d_wgrad_planes": [POINTER(ConvDesc), c_int, P, P, P, P, P, c_int, P],
     "pvg_unpack_dw": [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P],
     "pvg_amax": [P, c_int64, P, P],
@@ -60,7 +60,7 @@ _SIGNATURES = {
     "pvg_concat_pad": [POINTER(ConcatDesc), P, P, c_int, P, c_int, P],
     "pvg_bn_bwd_reduce": [P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P],
     "pvg_bn_bwd_apply": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P, P, P],
-    "pvg_bn_bwd_apply_ex": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P, P, c_int, P],
+    "pvg_bn_bwd_apply_ex": [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, P, c_int, c_int, P, P, P, P, c_int, P, P],
     "pvg_pack_conv_weight_ex": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P],
     "pvg_bn_finalize_apply": [P, c_int, c_int, c_int, c_int, P, c_int64, c_float, c_float, P, P, P, P, P, P, P, c_int, c_float,
                               P, P],

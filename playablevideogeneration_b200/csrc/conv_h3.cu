@@ -382,6 +382,7 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t pix = ((int64_t)on * p.H + oh) * p.W + ow;
       float* yrow = p.y + pix * p.Cout;
       float acc[BN];
+      float tile_amax = 0.f;
 #pragma unroll
       for (int j = 0; j < BN; ++j) acc[j] = 0.f;
       for (int per = 0; per < periods; ++per, ++pg) {
@@ -423,6 +424,10 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint16_t* lo_row = p.y_planes + pix * p.Cout;          // Cout % 8 == 0 (checked by the host): 16-byte aligned rows
           store_planes16(v, lo_row, lo_row + p.y_numel, t.co0 + c, p.Cout);
         }
+        if (p.amax_out != nullptr) {             // largest magnitude of the tile's outputs (scale of the next backward kernel)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) tile_amax = fmaxf(tile_amax, valid && t.co0 + c + j < p.Cout ? fabsf(v[j]) : 0.f);
+        }
         if (p.bn_sums != nullptr) {
           // BatchNorm statistics of the output in the epilogue (no separate pass over y): per-channel sum and sum of squares
           // of this warp's 32 pixels, 16 shuffles each
@@ -436,6 +441,11 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             dst[0] = s1; dst[1] = s2;
           }
         }
+      }
+      if (p.amax_out != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tile_amax = fmaxf(tile_amax, __shfl_xor_sync(0xffffffffu, tile_amax, o));
+        if (lane == 0 && tile_amax == tile_amax) atomicMax(p.amax_out, __float_as_uint(tile_amax));
       }
       if (p.bn_sums != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
@@ -491,6 +501,7 @@ static int env_int(const char* name, int dflt) {
 // BatchNorm statistics request of the current pvg_conv2d_fwd_planes call (see its bn_sums argument)
 struct BnStatsOut { double* sums; int groups; };
 static thread_local BnStatsOut g_bn = {nullptr, 0};
+static thread_local uint32_t* g_amax_out = nullptr;      // amax_out argument of the current pvg_conv2d_fwd_planes call
 
 template <int BN, bool HALO, bool PAIR>
 static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
@@ -503,6 +514,7 @@ static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w
   p.y_planes = (uint16_t*)y_planes; p.y_numel = (int64_t)d->N * d->H * d->W * d->Cout; p.out_scale = out_scale;
   p.lstm_c_prev = g_lstm.c_prev; p.lstm_c_new = g_lstm.c_new; p.lstm_h_new = g_lstm.h_new;
   p.bn_sums = nullptr; p.bn_groups = 0; p.bn_samples_per_group = 1;
+  p.amax_out = g_amax_out;
   static const int dbg = env_int("PVG_H3_DBG", 0);      // timing experiment only (wrong results): haloed tile read without row offsets
   p.dbg = dbg;
   if (HALO) { p.tw = 8; p.th = 16; p.tn = 1; }
@@ -595,7 +607,8 @@ using namespace pvg;
 // y = act(bias + conv(x, w)) with x and w given ONLY as fp16 plane pairs (pvg_split_16 / pvg_pack_16x2 with PVG_CORR_FP16_ALL,
 // or the y_planes of a previous call); y_planes (optional): the plane pair of y for the next convolution.
 extern "C" int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias,
-                                     float* y, void* y_planes, const float* out_scale, double* bn_sums, int bn_groups, void* stream) {
+                                     float* y, void* y_planes, const float* out_scale, double* bn_sums, int bn_groups,
+                                     uint32_t* amax_out, void* stream) {
   PVG_CHECK_ARG(!bn_sums || (bn_groups >= 1 && d && d->N % bn_groups == 0 && d->act == PVG_ACT_NONE),
                 "BatchNorm statistics: N must be divisible by the group count and the epilogue must not apply an activation");
   PVG_CHECK_ARG(d && x_planes && w_planes && y, "null argument");
@@ -604,9 +617,9 @@ extern "C" int pvg_conv2d_fwd_planes(const pvg_conv_desc* d, const void* x_plane
   PVG_CHECK_ARG(d->Cin % 8 == 0, "16-bit planes need Cin % 8 == 0 (16-byte TMA strides)");
   PVG_CHECK_ARG((((uintptr_t)x_planes | (uintptr_t)w_planes | (uintptr_t)y | (uintptr_t)y_planes) & 15) == 0, "operands must be 16-byte aligned");
   PVG_CHECK_ARG(!y_planes || d->Cout % 8 == 0, "y_planes needs Cout % 8 == 0");
-  g_bn.sums = bn_sums; g_bn.groups = bn_groups;
+  g_bn.sums = bn_sums; g_bn.groups = bn_groups; g_amax_out = amax_out;
   const int rc = conv2d_fwd_h3(d, x_planes, w_planes, bias, y, y_planes, out_scale, (cudaStream_t)stream);
-  g_bn.sums = nullptr; g_bn.groups = 0;
+  g_bn.sums = nullptr; g_bn.groups = 0; g_amax_out = nullptr;
   return rc;
 }
 

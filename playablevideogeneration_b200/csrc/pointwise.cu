@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int act, float slope, const double* __restrict__ sums2, int eval,
                                                            int unpool, float* __restrict__ dx, float* __restrict__ g_out,
                                                            int groups, float* __restrict__ dweight, float* __restrict__ dbias,
-                                                           const int Cp) {
+                                                           const int Cp, uint32_t* __restrict__ amax_out) {
   if (blockIdx.x == 0 && (dweight || dbias)) {       // bn_bwd_params folded in: one launch less per BatchNorm backward
     for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
       double sg = 0.0, sgx = 0.0;
@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
   const int U = C / V;
   const int64_t total = M * U;
   const double inv_count = 1.0 / (double)rows_per_group;
+  float amax = 0.f;              // largest |dx| this thread writes (the 0.25 of the un-pooling is applied at the end)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / U;
     int c = (int)(i % U) * V;
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
         val = w * is * (gg - sg - xhat * sgx);
       }
       o.v[j] = val;
+      amax = fmaxf(amax, fabsf(val));
     }
     if (g_out) go.store(g_out + r * C + c);
     if (!unpool) {
@@ -377,6 +379,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       float* p = dx + ((n * H + 2 * oh) * W + 2 * ow) * C + c;
       o.store(p); o.store(p + C); o.store(p + (int64_t)W * C); o.store(p + (int64_t)W * C + C);
     }
+  }
+  if (amax_out != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0 && amax == amax) atomicMax(amax_out, __float_as_uint(unpool ? 0.25f * amax : amax));
   }
 }
 
@@ -1129,19 +1136,20 @@ int pvg_bn_bwd_apply(const float* dy, const float* y, const float* x, int N, int
                      const float* mean, const float* invstd, const float* weight, int act, float slope, const double* sums2,
                      int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias, void* stream) {
   return pvg_bn_bwd_apply_ex(dy, y, x, N, H, W, C, groups, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out, dweight,
-                             dbias, 0, stream);
+                             dbias, 0, nullptr, stream);
 }
 
 int pvg_bn_bwd_apply_ex(const float* dy, const float* y, const float* x, int N, int H, int W, int C, int groups,
                         const float* mean, const float* invstd, const float* weight, int act, float slope, const double* sums2,
-                        int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias, int Cparams, void* stream) {
+                        int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias, int Cparams, uint32_t* amax_out,
+                        void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
   const int Cp = (Cparams > 0 && Cparams < C) ? Cparams : C;
   int OH = unpool ? H / 2 : H, OW = unpool ? W / 2 : W;
   int64_t M = (int64_t)N * OH * OW, rpg = (int64_t)(N / groups) * OH * OW;
   DISPATCH_V(C, (bn_bwd_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
                     dy, y, x, M, rpg, OH, OW, C, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out, groups, dweight,
-                    dbias, Cp)));
+                    dbias, Cp, amax_out)));
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -297,6 +297,7 @@ struct ConvParams {
   float* lstm_h_new;
   double* bn_sums;              // conv_h3.cu, optional: [groups][2][Cout] per-channel sum / sum of squares of y (BatchNorm statistics)
   int bn_groups, bn_samples_per_group;
+  uint32_t* amax_out;           // conv_h3.cu, optional: atomicMax of the bit patterns of |y| (zero-initialised by the caller)
   int dbg;                      // conv_h3.cu timing experiments
 };
 

@@ -430,7 +430,7 @@ class Conv2dFn(torch.autograd.Function):
             if bn_groups and act == ACT_NONE and b is None:
                 bn_sums = zero_pool.zeros((bn_groups, 2, cphys), torch.float64, x.device)
             call("pvg_conv2d_fwd_planes", d, xp.data_ptr(), packs.lo(0, 2, fmt).data_ptr(), _p(b), y.data_ptr(), _p(y_planes), None,
-                 _p(bn_sums), int(bn_groups) if bn_sums is not None else 0, _stream())
+                 _p(bn_sums), int(bn_groups) if bn_sums is not None else 0, None, _stream())
             if prof:
                 e1.record()
                 conv_profile.append((e0, e1, flops, "h3"))
@@ -559,6 +559,25 @@ class Conv2dFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None, None, None
 
 
+# A gradient tensor can carry the largest magnitude of its elements, written by the kernel that produced it (conv data gradient,
+# BatchNorm backward) into a one-element device buffer: the consumer's power-of-two scale then needs no pass over the tensor.
+# The tag is only trusted while the tensor has not been modified (autograd may accumulate a second gradient INTO the buffer in
+# place: that bumps its version counter).
+track_amax = os.environ.get("PVG_NO_AMAX_TAGS") != "1"
+
+
+def tag_amax(t: Tensor, amax_bits: Tensor) -> Tensor:
+    t._pvg_amax = (amax_bits, t._version)
+    return t
+
+
+def known_amax(t: Tensor) -> Optional[Tensor]:
+    tag = getattr(t, "_pvg_amax", None)
+    if tag is None or not track_amax or tag[1] != t._version:
+        return None
+    return tag[0]
+
+
 def _backward_h3(ctx, dy, x, weight, y):
     """Data and weight gradient as all-fp16 split products (conv_h3.cu with the flipped pack; conv_wgrad_umma.cu NPROD = 4):
     dY is scaled by a power of two chosen from max|dY| so that its fp16 plane pair is exact to 22 bits, both kernels undo the
@@ -569,10 +588,12 @@ def _backward_h3(ctx, dy, x, weight, y):
     n, cin_p, h, w = x.shape
     dev = dy.device
     st = _stream()
-    amax = zero_pool.zeros((1,), torch.int32, dev)
     inv = torch.empty((1,), dtype=torch.float32, device=dev)
     planes = torch.empty((2 * dy.numel(),), dtype=torch.float16, device=dev)
-    call("pvg_amax", dy.data_ptr(), dy.numel(), amax.data_ptr(), st)
+    amax = known_amax(dy)                 # written by the kernel that produced dy (an upper bound of max|dy| is what is needed)
+    if amax is None:
+        amax = zero_pool.zeros((1,), torch.int32, dev)
+        call("pvg_amax", dy.data_ptr(), dy.numel(), amax.data_ptr(), st)
     need_g = has_bias and ctx.needs_input_grad[2]
     if act != ACT_NONE:
         g = torch.empty_like(dy) if need_g else None
@@ -590,8 +611,11 @@ def _backward_h3(ctx, dy, x, weight, y):
         if prof:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        dx_amax = zero_pool.zeros((1,), torch.int32, dev) if track_amax else None
         call("pvg_conv2d_fwd_planes", d, planes.data_ptr(), packs.lo(2, 2, _lib.CORR_FP16_ALL).data_ptr(), None, dx.data_ptr(), None,
-             inv.data_ptr(), None, 0, st)
+             inv.data_ptr(), None, 0, _p(dx_amax), st)
+        if dx_amax is not None:
+            tag_amax(dx, dx_amax)
         if prof:
             e1.record()
             conv_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log, "h3"))
@@ -741,10 +765,13 @@ class PoolBNActFn(torch.autograd.Function):
                 dx_buf = empty_nhwc((n, c, h, w), dev)
             else:
                 dx_buf = dx
+            dx_amax = zero_pool.zeros((1,), torch.int32, dev) if (track_amax and dx is not None) else None
             call("pvg_bn_bwd_apply_ex", dy.data_ptr(), _p(y), xp.data_ptr(), n, h, w, c, groups, mean.data_ptr(),
                  invstd.data_ptr(), _p(weight.detach() if weight is not None else None), act, float(slope),
                  sums2.data_ptr(), 0 if training else 1, 1 if pool else 0, dx_buf.data_ptr(), _p(g_out), _p(dweight), _p(dbias),
-                 ctx.cp, st)          # dweight / dbias: the parameter gradients ride along in the same launch
+                 ctx.cp, _p(dx_amax), st)          # dweight / dbias: the parameter gradients ride along in the same launch
+            if dx_amax is not None:
+                tag_amax(dx, dx_amax)
         elif need_params:
             if ctx.cp != c:
                 raise _lib.PvgError("channel-padded BatchNorm backward needs the input gradient path")
@@ -847,6 +874,9 @@ class MaxPool2Fn(torch.autograd.Function):
         if (h % 2) or (w % 2):
             dx.zero_()
         call("pvg_maxpool2_bwd", dy.data_ptr(), x.data_ptr(), y.data_ptr(), n, h, w, c, 0, dx.data_ptr(), _stream())
+        known = known_amax(dy)
+        if known is not None:              # every element of dx is an element of dy or zero
+            tag_amax(dx, known)
         return dx, None
 
 

@@ -433,6 +433,45 @@ def test_conv_epilogue_batchnorm_statistics(shape):
     _close(f"epilogue_stats_bn{shape}", a, b.cpu(), 2e-6, 2e-6)
 
 
+def test_gradient_amax_tags_replace_the_amax_pass_bit_for_bit(monkeypatch):
+    """conv data-gradient epilogue and BatchNorm backward write max|dx| next to dx; the conv backward above them takes its
+    power-of-two scale from that tag instead of a pvg_amax pass.  Same data gradient, bit for bit, and fewer amax launches;
+    a tag on a tensor that was modified afterwards is not trusted."""
+    ops = _ops()
+
+    def run(track):
+        monkeypatch.setattr(ops, "track_amax", track)
+        calls = []
+        real = ops.call
+        monkeypatch.setattr(ops, "call", lambda name, *a: (calls.append(name), real(name, *a))[1])
+        torch.manual_seed(0)
+        x = ops.nhwc(_rand(4, 32, 16, 24, seed=1).to(DEV)).requires_grad_(True)
+        w1 = _rand(64, 32, 3, 3, seed=2, scale=0.06).to(DEV).requires_grad_(True)
+        w2 = _rand(64, 64, 3, 3, seed=3, scale=0.04).to(DEV).requires_grad_(True)
+        w3 = _rand(32, 64, 3, 3, seed=4, scale=0.04).to(DEV).requires_grad_(True)
+        bn1 = torch.nn.BatchNorm2d(64).to(DEV).train()
+        bn2 = torch.nn.BatchNorm2d(64).to(DEV).train()
+        h = ops.pool_bn_act(ops.conv2d(x, w1), bn1, pool=True, act=ops.ACT_LRELU)
+        h = ops.maxpool2(ops.pool_bn_act(ops.conv2d(h, w2), bn2, act=ops.ACT_RELU))
+        y = ops.conv2d(h, w3, act=ops.ACT_TANH)
+        y.backward(_rand(*y.shape, seed=5).to(DEV))
+        monkeypatch.setattr(ops, "call", real)
+        return [t.grad.clone() for t in (x, w1, w2, w3, bn1.weight, bn2.bias)], calls.count("pvg_amax")
+
+    tagged, n_tagged = run(True)
+    plain, n_plain = run(False)
+    assert n_plain == 3 and n_tagged == 1, (n_plain, n_tagged)      # only the loss-side gradient still needs the pass
+    assert torch.equal(tagged[0], plain[0])            # same scale -> same operand planes -> the same data gradient
+    for i, (a, b) in enumerate(zip(tagged[1:], plain[1:])):     # split-K / statistics accumulate with atomics: order varies
+        _close(f"amax_tags_grad{i}", a, b.cpu(), 1e-6, 1e-6)
+    monkeypatch.setattr(ops, "track_amax", True)
+    t = torch.ones(8, device=DEV)
+    ops.tag_amax(t, torch.zeros(1, dtype=torch.int32, device=DEV))
+    assert ops.known_amax(t) is not None
+    t.add_(1.0)
+    assert ops.known_amax(t) is None
+
+
 def test_concat_pad_strided_time_slices():
     """Maps handed to the concat as time slices of a (B, T, C, H, W) tensor (batch-strided, NHWC-dense per sample) are read in
     place."""
