@@ -76,6 +76,11 @@ int pvg_has_umma(void);
  * y[n,h,w,co] = act(bias[co] + sum_{r,s,ci} x[n,h+r-pad,w+s-pad,ci] * w[co,r,s,ci]).   bias may be NULL. */
 int pvg_conv2d_fwd(const pvg_conv_desc* d, const float* x, const void* x_lo, const float* w, const void* w_lo,
                    const float* bias, float* y, void* stream);
+/* Image-facing 3 -> 64 channel 3x3 convolution (VGG19 conv1_1, vgg.py:48-52) in fp32 on the CUDA cores, output-bound: coalesced
+ * stores of y and, when y_planes != NULL, of the PVG_CORR_FP16_ALL plane pair of y that conv1_2 consumes.
+ * x: [N,H,W,3]; w: [64][3][3][3] (the K-major pack with CinK = 3); d->act / d->slope as for pvg_conv2d_fwd. */
+int pvg_conv2d_stem_planes(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* y_planes,
+                           void* stream);
 /* The same convolution with x and w given ONLY as fp16 plane pairs (PVG_CORR_FP16_ALL: pvg_split_16 / pvg_pack_16x2 with that
  * format, or the y_planes of a previous call): all three products of the split run as kind::f16 MMAs; 3x3 convolutions reuse
  * one haloed shared-memory tile for their 9 taps; persistent CTAs (CTA pairs on large problems).  d->Cin % 8 == 0.
@@ -145,6 +150,15 @@ int pvg_split_16_scaled(const float* x, void* planes, int64_t n, const uint32_t*
 /* g = dy * act'(y) (g may be NULL) and the scaled planes of g; *amax_bits = max|dy| bounds max|g| (|act'| <= 1) */
 int pvg_act_bwd_split_16_scaled(const float* dy, const float* y, int act, float slope, float* g, void* planes, int64_t n,
                                 const uint32_t* amax_bits, float* inv_scale, void* stream);
+/* The same two with a feature-matching L1 term folded in (vgg.py:41-56 taps + losses.py:465): the gradient that is pushed through
+ * the activation is dy + tap_gout[n] / count * sign(y - target), n = the sample ([N][count] layout) - i.e. what
+ * pvg_absdiff_mean_bwd(target, y, tap_gout) and an addition would have produced, without their passes over the feature map.
+ * The scaled variant takes its scale from the bound *amax_bits + max|tap_gout| / count. */
+int pvg_act_bwd_tap(const float* dy, const float* y, int act, float slope, float* g, int N, int64_t count, const float* target,
+                    const float* tap_gout, void* stream);
+int pvg_act_bwd_tap_split_16_scaled(const float* dy, const float* y, int act, float slope, float* g, void* planes, int N,
+                                    int64_t count, const uint32_t* amax_bits, float* inv_scale, const float* target,
+                                    const float* tap_gout, void* stream);
 /* g = dy * act'(y) and the 16-bit plane pair of g (pvg_split_16) in one pass */
 int pvg_act_bwd_split_16(const float* dy, const float* y, int act, float slope, float* g, void* planes, int64_t n, int fmt,
                          void* stream);

@@ -31,6 +31,7 @@ P = c_void_p
 # name -> (argtypes); every function returns int (0 = ok) except pvg_last_error / pvg_version / pvg_has_umma
 _SIGNATURES = {
     "pvg_conv2d_fwd": [POINTER(ConvDesc), P, P, P, P, P, P, P],
+    "pvg_conv2d_stem_planes": [POINTER(ConvDesc), P, P, P, P, P, P],
     "pvg_conv2d_fwd_planes": [POINTER(ConvDesc), P, P, P, P, P, P, P, c_int, P, P],
     "pvg_conv2d_wgrad_planes": [POINTER(ConvDesc), c_int, P, P, P, P, P, c_int, P],
     "pvg_unpack_dw": [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P],
@@ -46,6 +47,8 @@ _SIGNATURES = {
     "pvg_pack_16x2": [P, P, P, c_int64, c_int, P],
     "pvg_act_bwd_split_16": [P, P, c_int, c_float, P, P, c_int64, c_int, P],
     "pvg_act_bwd": [P, P, c_int, c_float, P, c_int64, P],
+    "pvg_act_bwd_tap": [P, P, c_int, c_float, P, c_int, c_int64, P, P, P],
+    "pvg_act_bwd_tap_split_16_scaled": [P, P, c_int, c_float, P, P, c_int, c_int64, P, P, P, P, P],
     "pvg_act_bwd_split": [P, P, c_int, c_float, P, P, P, c_int64, P],
     "pvg_bn_stats": [P, c_int, c_int, c_int, c_int, P, P],
     "pvg_pool2_stats": [P, c_int, c_int, c_int, c_int, P, c_int, P, P],

@@ -6,6 +6,7 @@
 //   conv_small_cout : Cout <= 4, Cin % 4 == 0             (tanh heads 128/64/32 -> 3 incl. the 7x7, data gradients of the
 //                     stems: 16 -> 3S, 64 -> 3)
 // Weights arrive in the common pack [Cout][R][S][Cin] (pvg_pack_conv_weight, unrounded fp32).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -492,6 +493,107 @@ int conv2d_wgrad_direct(const pvg_conv_desc* d, int Cin_logical, const float* x,
 }
 
 // returns 1 when a direct kernel took the problem, 0 when the caller should fall back, < 0 on error
+// ---------------------------------------------------------------------------------------------------------------
+// 3 -> 64 channels, 3x3 (VGG19 conv1_1, vgg.py:48-52 on the 256^2 frames: 240 frames per step per resolution).  The layer is
+// bound by its OUTPUT: 64 fp32 channels per pixel plus the fp16 plane pair conv1_2 consumes = 512 B per pixel against 1 728 FMAs.
+// 256 threads = 16 pixel groups x 16 channel quads; a thread keeps the 27 x 4 weights of its channel quad in registers and
+// walks the tile's pixels two at a time, so that every store instruction of a warp covers two whole pixels (2 x 256 B of y,
+// 2 x 128 B of each plane) instead of 32 different rows.  The haloed input tile (10 x 34 pixels x 3 channels) sits in shared
+// memory; the two pixels a warp works on read it as two broadcasts.
+// ---------------------------------------------------------------------------------------------------------------
+struct Stem3Cfg {
+  static constexpr int TH = 8, TW = 32, COUT = 64, THREADS = 256;
+  static constexpr int PH = TH + 2, PWF = (TW + 2) * 3;      // staged rows, floats per staged row
+};
+
+__global__ void __launch_bounds__(Stem3Cfg::THREADS) conv_stem3_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                       const float* __restrict__ bias, float* __restrict__ y,
+                                                                       uint16_t* __restrict__ planes, int64_t y_numel, int N,
+                                                                       int H, int W, int act, float slope) {
+  using C = Stem3Cfg;
+  __shared__ float xs[C::PH][C::PWF + 2];
+  const int tiles_w = ceil_div(W, C::TW), tiles_h = ceil_div(H, C::TH);
+  int t = blockIdx.x;
+  const int tile_w = t % tiles_w; t /= tiles_w;
+  const int tile_h = t % tiles_h;
+  const int n = t / tiles_h;
+  const int ow0 = tile_w * C::TW, oh0 = tile_h * C::TH;
+  for (int i = threadIdx.x; i < C::PH * C::PWF; i += C::THREADS) {
+    const int py = i / C::PWF, pf = i - py * C::PWF;
+    const int ih = oh0 + py - 1, f = (ow0 - 1) * 3 + pf;            // f: float index inside the image row
+    xs[py][pf] = (ih >= 0 && ih < H && f >= 0 && f < W * 3) ? __ldg(x + ((int64_t)n * H + ih) * W * 3 + f) : 0.f;
+  }
+  const int cq = threadIdx.x & 15, pg = threadIdx.x >> 4;
+  float wr[27][4];
+#pragma unroll
+  for (int k = 0; k < 27; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wr[k][j] = __ldg(w + (cq * 4 + j) * 27 + k);
+  float b4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b4[j] = bias != nullptr ? __ldg(bias + cq * 4 + j) : 0.f;
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < C::TH * C::TW / 32; ++it) {
+    float acc[2][4];
+    int pp[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      pp[u] = it * 32 + u * 16 + pg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[u][j] = b4[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float in[2][9];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float* row = &xs[pp[u] / C::TW + r][(pp[u] % C::TW) * 3];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) in[u][q] = row[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[u][j] = fmaf(in[u][q], wr[r * 9 + q][j], acc[u][j]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int oh = oh0 + pp[u] / C::TW, ow = ow0 + pp[u] % C::TW;
+      if (oh >= H || ow >= W) continue;
+      const float4 v = make_float4(act_fwd(acc[u][0], act, slope), act_fwd(acc[u][1], act, slope),
+                                   act_fwd(acc[u][2], act, slope), act_fwd(acc[u][3], act, slope));
+      const int64_t e = (((int64_t)n * H + oh) * W + ow) * C::COUT + cq * 4;
+      stg4(y + e, v);
+      if (planes != nullptr) {              // PVG_CORR_FP16_ALL pair: { f16((v - f16(v)) * 2^12), f16(v) }, see pointwise.cu
+        const float c0 = fminf(v.x, 65504.f), c1 = fminf(v.y, 65504.f), c2 = fminf(v.z, 65504.f), c3 = fminf(v.w, 65504.f);
+        const __half2 h01 = __floats2half2_rn(fmaxf(c0, -65504.f), fmaxf(c1, -65504.f));
+        const __half2 h23 = __floats2half2_rn(fmaxf(c2, -65504.f), fmaxf(c3, -65504.f));
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const float l0 = (v.x - f01.x) * 4096.f, l1 = (v.y - f01.y) * 4096.f, l2 = (v.z - f23.x) * 4096.f, l3 = (v.w - f23.y) * 4096.f;
+        const __half2 g01 = __floats2half2_rn(fminf(fmaxf(l0, -65504.f), 65504.f), fminf(fmaxf(l1, -65504.f), 65504.f));
+        const __half2 g23 = __floats2half2_rn(fminf(fmaxf(l2, -65504.f), 65504.f), fminf(fmaxf(l3, -65504.f), 65504.f));
+        *reinterpret_cast<uint2*>(planes + e) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
+        *reinterpret_cast<uint2*>(planes + y_numel + e) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      }
+    }
+  }
+}
+
+int conv2d_stem3_planes(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* y_planes,
+                        cudaStream_t st) {
+  using C = Stem3Cfg;
+  const unsigned tiles = (unsigned)(ceil_div(d->W, C::TW) * ceil_div(d->H, C::TH) * d->N);
+  conv_stem3_kernel<<<tiles, C::THREADS, 0, st>>>(x, w, bias, y, (uint16_t*)y_planes, (int64_t)d->N * d->H * d->W * C::COUT,
+                                                  d->N, d->H, d->W, d->act, d->slope);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
 int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
   const int64_t M = (int64_t)d->N * d->H * d->W;
   const unsigned grid = (unsigned)ceil_div64(M, kDThreads);
@@ -581,3 +683,13 @@ int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, co
 }
 
 }  // namespace pvg
+
+using namespace pvg;
+
+extern "C" int pvg_conv2d_stem_planes(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                                      void* y_planes, void* stream) {
+  PVG_CHECK_ARG(d && x && w && y, "null argument");
+  PVG_CHECK_ARG(d->Cin == 3 && d->Cout == 64 && d->R == 3 && d->S == 3 && d->pad == 1, "3 -> 64 channels, 3x3, 'same' padding only");
+  PVG_CHECK_ARG((((uintptr_t)y | (uintptr_t)y_planes) & 15) == 0, "y / y_planes must be 16-byte aligned");
+  return conv2d_stem3_planes(d, x, w, bias, y, y_planes, (cudaStream_t)stream);
+}

@@ -785,6 +785,64 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     g[i] = __ldg(dy + i) * act_bwd_from_out(__ldg(y + i), act, slope);
 }
 
+// ---- a feature-matching L1 term folded into the activation backward of the conv that produced the feature ----------------
+// The perceptual loss taps y = relu(conv(...)) (vgg.py:41-56) with mean|target - y| per sample (losses.py:465): y's gradient is
+// dy (from the layers above) + tap_gout[n] / count * sign(y - target).  Adding the second term here replaces the
+// absdiff backward kernel, autograd's accumulation of the two gradients and their three passes over the feature map each.
+__device__ __forceinline__ float tap_grad(float target, float y, float gn) {
+  const float d = target - y;                               // absdiff_mean_bwd_kernel: d|a-b|/db = -sign(a-b)
+  return d > 0.f ? -gn : (d < 0.f ? gn : 0.f);
+}
+__device__ __forceinline__ float block_max_abs(const float* __restrict__ v, int n) {       // every thread returns the maximum
+  __shared__ float part[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(v + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, part[i]);
+  return m;
+}
+// grid (x, N): sample n = blockIdx.y, count elements each (count % 4 == 0)
+__global__ void __launch_bounds__(256) act_bwd_tap_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act,
+                                                          float slope, float* __restrict__ g, int64_t count,
+                                                          const float* __restrict__ target, const float* __restrict__ tap_gout) {
+  const int n = blockIdx.y;
+  const float gn = __ldg(tap_gout + n) / (float)count;
+  const int64_t base = (int64_t)n * count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count / 4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 d = ldg4(dy + base + 4 * i), o = ldg4(y + base + 4 * i), t = ldg4(target + base + 4 * i);
+    stg4(g + base + 4 * i, make_float4((d.x + tap_grad(t.x, o.x, gn)) * act_bwd_from_out(o.x, act, slope),
+                                       (d.y + tap_grad(t.y, o.y, gn)) * act_bwd_from_out(o.y, act, slope),
+                                       (d.z + tap_grad(t.z, o.z, gn)) * act_bwd_from_out(o.z, act, slope),
+                                       (d.w + tap_grad(t.w, o.w, gn)) * act_bwd_from_out(o.w, act, slope)));
+  }
+}
+__global__ void __launch_bounds__(256) act_bwd_tap_split_16_scaled_kernel(
+    const float* __restrict__ dy, const float* __restrict__ y, int act, float slope, float* __restrict__ g,
+    uint16_t* __restrict__ planes, int64_t count, int N, const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
+    const float* __restrict__ target, const float* __restrict__ tap_gout) {
+  // scale from an upper bound of the sum: max|dy| + max_n |tap_gout[n]| / count (the same in every block)
+  const float bound = __uint_as_float(*amax_bits) + block_max_abs(tap_gout, N) / (float)count;
+  float inv;
+  const float S = grad_scale_from_amax(__float_as_uint(bound), &inv);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *inv_scale = inv;
+  const int n = blockIdx.y;
+  const float gn = __ldg(tap_gout + n) / (float)count;
+  const int64_t base = (int64_t)n * count, total = (int64_t)N * count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count / 4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 d = ldg4(dy + base + 4 * i), o = ldg4(y + base + 4 * i), t = ldg4(target + base + 4 * i);
+    const float4 v = make_float4((d.x + tap_grad(t.x, o.x, gn)) * act_bwd_from_out(o.x, act, slope),
+                                 (d.y + tap_grad(t.y, o.y, gn)) * act_bwd_from_out(o.y, act, slope),
+                                 (d.z + tap_grad(t.z, o.z, gn)) * act_bwd_from_out(o.z, act, slope),
+                                 (d.w + tap_grad(t.w, o.w, gn)) * act_bwd_from_out(o.w, act, slope));
+    if (g) stg4(g + base + 4 * i, v);
+    store_16_planes<2>(planes, total, base / 4 + i, make_float4(v.x * S, v.y * S, v.z * S, v.w * S));
+  }
+}
+
 // g = dy * act'(y) and, in the same pass, the 3xTF32 residual plane of g (lo = g - tf32(g); hi optional, see split)
 __global__ void __launch_bounds__(256) act_bwd_split_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act,
                                                             float slope, float* __restrict__ g, float* __restrict__ hi,
@@ -1346,6 +1404,36 @@ int pvg_act_bwd_split_16_scaled(const float* dy, const float* y, int act, float 
                 "n % 8 == 0, 16-byte aligned pointers and the amax / scale scalars are required");
   act_bwd_split_16_scaled_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, (uint16_t*)planes, n,
                                                                                         amax_bits, inv_scale);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+static dim3 tap_grid(int64_t count, int N) {
+  int64_t gx = (count / 4 + 255) / 256;
+  const int64_t cap = (148 * 16 + N - 1) / N;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)N);
+}
+
+int pvg_act_bwd_tap(const float* dy, const float* y, int act, float slope, float* g, int N, int64_t count, const float* target,
+                    const float* tap_gout, void* stream) {
+  PVG_CHECK_ARG(dy && y && g && target && tap_gout && N > 0 && N <= 65535 && count > 0 && count % 4 == 0 &&
+                    (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)g | (uintptr_t)target) & 15) == 0,
+                "count % 4 == 0, N <= 65535 and 16-byte aligned pointers required");
+  act_bwd_tap_kernel<<<tap_grid(count, N), 256, 0, (cudaStream_t)stream>>>(dy, y, act, slope, g, count, target, tap_gout);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_act_bwd_tap_split_16_scaled(const float* dy, const float* y, int act, float slope, float* g, void* planes, int N,
+                                    int64_t count, const uint32_t* amax_bits, float* inv_scale, const float* target,
+                                    const float* tap_gout, void* stream) {
+  PVG_CHECK_ARG(dy && y && planes && target && tap_gout && amax_bits && inv_scale && N > 0 && N <= 65535 && count > 0 &&
+                    count % 8 == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)g | (uintptr_t)planes | (uintptr_t)target) & 15) == 0,
+                "count % 8 == 0, N <= 65535, 16-byte aligned pointers and the amax / scale scalars are required");
+  act_bwd_tap_split_16_scaled_kernel<<<tap_grid(count, N), 256, 0, (cudaStream_t)stream>>>(
+      dy, y, act, slope, g, (uint16_t*)planes, count, N, amax_bits, inv_scale, target, tap_gout);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -382,6 +382,7 @@ def _conv_forward(x: Tensor, packs: _Packs, which: int, cout: int, ksize: int, b
 
 
 wgrad_profile = None    # like conv_profile, for the tensor-core weight-gradient kernel
+stem_kernel = os.environ.get("PVG_NO_STEM_KERNEL") != "1"      # pvg_conv2d_stem_planes for 3 -> 64 channel 3x3 layers
 
 
 class Conv2dFn(torch.autograd.Function):
@@ -434,6 +435,15 @@ class Conv2dFn(torch.autograd.Function):
             if prof:
                 e1.record()
                 conv_profile.append((e0, e1, flops, "h3"))
+        elif (algo == ALGO_SIMT and cin_p == 3 and cout == 64 and r == 3 and _precision != "fp32" and stem_kernel
+              and _is_nhwc_dense(x)):
+            # VGG19 conv1_1: output-bound CUDA-core kernel with coalesced stores that also writes the planes conv1_2 reads
+            n, _, h, w = x.shape
+            y = empty_nhwc((n, cout, h, w), x.device)
+            if out_planes:
+                y_planes = torch.empty((2 * y.numel(),), dtype=torch.float16, device=x.device)
+            d = ConvDesc(n, h, w, 3, cout, 3, 3, 1, act, float(slope), ALGO_SIMT, 1, 0)
+            call("pvg_conv2d_stem_planes", d, x.data_ptr(), packs.hi(0).data_ptr(), _p(b), y.data_ptr(), _p(y_planes), _stream())
         else:
             split = (x, x_planes[fmt]) if (algo == ALGO_UMMA and nprod == 2 and fmt in x_planes) else None
             y = _conv_forward(x, packs, 0, cout, r, b, act, slope, algo, nprod, fmt, flops, split=split)
@@ -458,6 +468,9 @@ class Conv2dFn(torch.autograd.Function):
         act, slope, has_bias, cin_log = ctx.meta
         cout, _, r, s = weight.shape
         n, cin_p, h, w = x.shape
+        tap = pending_tap(dy)             # a feature-matching L1 gradient still to be added to dy (TapL1Fn)
+        if tap is not None and (act == ACT_NONE or dy.numel() // dy.shape[0] % 8 != 0 or not _is_nhwc_dense(dy)):
+            dy, tap = _materialize_tap(dy, y, tap), None
         dy = nhwc(dy)
         dmode = _mode("dgrad")            # (nprod, fmt) of the data-gradient kernel (conv_umma.cu)
         wmode = _mode("wgrad")            # ... of the weight-gradient kernel (conv_wgrad_umma.cu)
@@ -467,19 +480,26 @@ class Conv2dFn(torch.autograd.Function):
         if dmode == H3 or wmode == H3:
             if (dmode == H3 and wmode == H3 and cin_p % _TC_CIN_MULTIPLE == 0 and ctx.cphys % 8 == 0 and _precision == "tf32x3"
                     and not (cin_p <= 4 and r <= 7) and not (r == 7 and cout <= 3)):
-                return Conv2dFn._backward_h3(ctx, dy, x, weight, y)
+                return Conv2dFn._backward_h3(ctx, dy, x, weight, y, tap)
             # shapes the all-fp16 kernels do not take (image-facing layers, channel counts that are not a multiple of 8):
             # TF32 main product + bf16 corrections
             BF = (2, _lib.CORR_BF16)
             dmode = BF if dmode == H3 else dmode
             wmode = BF if wmode == H3 else wmode
-        want_dx = ctx.needs_input_grad[0] and cout % _TC_CIN_MULTIPLE == 0 and dmode[0] >= 2
+        want_dx = (ctx.needs_input_grad[0] and cout % _TC_CIN_MULTIPLE == 0 and dmode[0] >= 2
+                   and _conv_algo(cout, cin_p, r, "dgrad")[0] == ALGO_UMMA)      # else: the planes of g would have no reader
         want_dw = ctx.needs_input_grad[1] and cin_p % _TC_CIN_MULTIPLE == 0 and cout % 4 == 0 and wmode[0] >= 2
         g_splits = {}                     # (nprod, fmt) -> (hi, lo) of g
         if act != ACT_NONE:
             g = torch.empty_like(dy)
             fused = dmode if want_dx else (wmode if want_dw else (0, 0))
-            if fused[0] == 2:            # activation backward and the 16-bit planes of g in one pass
+            if tap is not None and fused[0] in (2, 3):
+                dy, tap = _materialize_tap(dy, y, tap), None
+            if tap is not None:          # image-facing VGG conv1_1: activation backward with the tap gradient folded in
+                target, gl = tap
+                call("pvg_act_bwd_tap", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), dy.shape[0],
+                     dy.numel() // dy.shape[0], target.data_ptr(), gl.data_ptr(), _stream())
+            elif fused[0] == 2:          # activation backward and the 16-bit planes of g in one pass
                 planes = torch.empty((2 * dy.numel(),), dtype=_plane_dtype(fused[1]), device=dy.device)
                 call("pvg_act_bwd_split_16", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), planes.data_ptr(),
                      dy.numel(), fused[1], _stream())
@@ -578,7 +598,7 @@ def known_amax(t: Tensor) -> Optional[Tensor]:
     return tag[0]
 
 
-def _backward_h3(ctx, dy, x, weight, y):
+def _backward_h3(ctx, dy, x, weight, y, tap=None):
     """Data and weight gradient as all-fp16 split products (conv_h3.cu with the flipped pack; conv_wgrad_umma.cu NPROD = 4):
     dY is scaled by a power of two chosen from max|dY| so that its fp16 plane pair is exact to 22 bits, both kernels undo the
     scale; x is consumed through the very planes the forward convolution read."""
@@ -595,7 +615,12 @@ def _backward_h3(ctx, dy, x, weight, y):
         amax = zero_pool.zeros((1,), torch.int32, dev)
         call("pvg_amax", dy.data_ptr(), dy.numel(), amax.data_ptr(), st)
     need_g = has_bias and ctx.needs_input_grad[2]
-    if act != ACT_NONE:
+    if act != ACT_NONE and tap is not None:
+        target, gl = tap                   # dy + the feature-matching L1 gradient, activation backward and planes in one pass
+        g = torch.empty_like(dy) if need_g else None
+        call("pvg_act_bwd_tap_split_16_scaled", dy.data_ptr(), y.data_ptr(), act, float(slope), _p(g), planes.data_ptr(),
+             dy.shape[0], dy.numel() // dy.shape[0], amax.data_ptr(), inv.data_ptr(), target.data_ptr(), gl.data_ptr(), st)
+    elif act != ACT_NONE:
         g = torch.empty_like(dy) if need_g else None
         call("pvg_act_bwd_split_16_scaled", dy.data_ptr(), y.data_ptr(), act, float(slope), _p(g), planes.data_ptr(), dy.numel(),
              amax.data_ptr(), inv.data_ptr(), st)
@@ -1164,6 +1189,81 @@ class AbsDiffMeanFn(torch.autograd.Function):
 
 def absdiff_mean(a: Tensor, b: Tensor) -> Tensor:
     return AbsDiffMeanFn.apply(a.detach(), b)
+
+
+# A feature-matching L1 term on the output of a convolution that ALSO feeds deeper layers (the VGG taps of the perceptual loss,
+# model/layers/vgg.py:41-56 + training/losses.py:450-465) gives that output two gradients: autograd would materialise the L1
+# one (pvg_absdiff_mean_bwd) and add it to the deeper one - six passes over the largest feature maps of the step.  TapL1Fn
+# sits IN the chain instead (identity for the feature, the loss as a second output); in backward it hands the deeper gradient on
+# unchanged with the pending term attached, and the producing convolution's backward folds it into its activation-backward
+# pass (pvg_act_bwd_tap*).  Anything else that might receive the tagged tensor never does: tap_l1 only defers for a feature that
+# comes straight out of Conv2dFn, and Conv2dFn.backward materialises the sum itself whenever it cannot fuse it.
+fuse_taps = os.environ.get("PVG_NO_TAP_FUSION") != "1"
+
+
+def _is_nhwc_dense(t: Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def pending_tap(dy: Optional[Tensor]):
+    tag = getattr(dy, "_pvg_tap", None) if dy is not None else None
+    if tag is None:
+        return None
+    target, gl, version = tag
+    if version != dy._version:
+        raise _lib.PvgError("a gradient carrying a deferred feature-matching term was modified before its convolution saw it")
+    del dy._pvg_tap
+    return target, gl
+
+
+def _materialize_tap(dy: Tensor, y: Tensor, tap) -> Tensor:
+    target, gl = tap
+    n = y.shape[0]
+    db = torch.empty_like(y)
+    call("pvg_absdiff_mean_bwd", target.data_ptr(), y.data_ptr(), gl.data_ptr(), n, y.numel() // n, db.data_ptr(), _stream())
+    return db.add_(dy)
+
+
+class TapL1Fn(torch.autograd.Function):
+    """(feature, mean|target - feature| per sample): AbsDiffMeanFn for a feature that is also consumed by deeper layers."""
+
+    @staticmethod
+    def forward(ctx, x, target, defer):
+        _check_cuda(x); _check_cuda(target)
+        if x.shape != target.shape or not (_is_nhwc_dense(x) and _is_nhwc_dense(target)):
+            raise _lib.PvgError("tap_l1 needs two channels-last feature maps of one shape")
+        n = x.shape[0]
+        out = zero_pool.zeros((n,), torch.float64, x.device)
+        call("pvg_absdiff_mean_fwd", target.data_ptr(), x.data_ptr(), n, x.numel() // n, out.data_ptr(), _stream())
+        ctx.save_for_backward(target, x)
+        ctx.defer = defer
+        ctx.set_materialize_grads(False)
+        return x.view_as(x), out.float()
+
+    @staticmethod
+    def backward(ctx, g_x, g_loss):
+        if g_loss is None:
+            return g_x, None, None
+        target, x = ctx.saved_tensors
+        gl = g_loss.contiguous().float()
+        if g_x is not None and ctx.defer and _is_nhwc_dense(g_x):
+            g_x._pvg_tap = (target, gl, g_x._version)        # consumed by Conv2dFn.backward of the producing convolution
+            return g_x, None, None
+        n = x.shape[0]
+        db = torch.empty_like(x)
+        call("pvg_absdiff_mean_bwd", target.data_ptr(), x.data_ptr(), gl.data_ptr(), n, x.numel() // n, db.data_ptr(), _stream())
+        return (db if g_x is None else db.add_(g_x)), None, None
+
+
+def tap_l1(x: Tensor, target: Tensor) -> Tuple[Tensor, Tensor]:
+    """Returns (x, loss[n] = mean|target[n] - x[n]|): ``x`` (an alias carrying x's operand planes) is what deeper layers consume."""
+    fn = x.grad_fn
+    defer = bool(fuse_taps and fn is not None and type(fn).__name__ == "Conv2dFnBackward")
+    out, loss = TapL1Fn.apply(x, target.detach(), defer)
+    pl = planes_of(x)
+    if pl:
+        out._pvg_planes = pl
+    return out, loss
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -104,11 +104,10 @@ class UnmeanedPerceptualLoss(nn.Module):
         rec = _flatten(reconstructed_observations)
         with torch.no_grad():
             gt_feats = self.vgg(gt.detach())
-        rec_feats = self.vgg(rec)
+        dists = self.vgg(rec, l1_targets=gt_feats)          # |gt - rec|.mean(dim=[1,2,3]) per image and tap
         total = None
         singles = []
-        for fg, fr in zip(gt_feats, rec_feats):
-            cur = ops.absdiff_mean(fg, fr)                  # |gt - rec|.mean(dim=[1,2,3]) per image
+        for cur in dists:
             total = cur if total is None else total + cur
             singles.append(cur)
         # Reference quirk (losses.py:484-488): ``total_loss = current_loss`` followed by the in-place ``total_loss +=``

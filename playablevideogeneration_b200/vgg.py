@@ -64,7 +64,10 @@ class Vgg19(nn.Module):
                 self.convs[str(idx)].weight.copy_(sd[f"features.{idx}.weight"])
                 self.convs[str(idx)].bias.copy_(sd[f"features.{idx}.bias"])
 
-    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+    def forward(self, x: torch.Tensor, l1_targets: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """The five tapped features - or, with ``l1_targets`` (the features of the ground truth), the five per-sample L1
+        distances mean|target - feature| (losses.py:450-465), each computed where the feature is produced so that its
+        gradient is folded into the producing convolution's backward pass (ops.tap_l1)."""
         feats = []
         convs = [v for v in CFG if v != "M"]
         fwd_planes = ops.conv_input_planes(weight_grad=False)      # frozen weights: only the forward operand format
@@ -79,5 +82,9 @@ class Vgg19(nn.Module):
             # conv -> ReLU -> conv chains: the epilogue writes the next convolution's fp16 operand planes itself
             x = ops.conv2d(x, conv.weight, conv.bias, act=ACT_RELU, out_planes=next_is_conv)
             if idx in TAPS:
-                feats.append(x)
+                if l1_targets is not None:
+                    x, dist = ops.tap_l1(x, l1_targets[len(feats)])
+                    feats.append(dist)
+                else:
+                    feats.append(x)
         return feats

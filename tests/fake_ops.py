@@ -76,6 +76,10 @@ def absdiff_mean(a, b):
     return (a.detach() - b).abs().reshape(a.shape[0], -1).mean(dim=1)
 
 
+def tap_l1(x, target):
+    return x, absdiff_mean(target, x)
+
+
 def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
     with torch.no_grad():
         g = g * grad_scale + weight_decay * p
@@ -88,7 +92,7 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_dec
 def install(monkeypatch):
     from playablevideogeneration_b200.training import losses
     for name in ("conv2d", "pool_bn_act", "upsample2x", "resize_bilinear", "maxpool2", "lstm_cell", "concat_pad",
-                 "absdiff_mean", "sqdiff_mean", "adam_step"):
+                 "absdiff_mean", "tap_l1", "sqdiff_mean", "adam_step"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "nhwc", lambda x: x)
     monkeypatch.setattr(ops, "conv_input_planes", lambda weight_grad=True: ())

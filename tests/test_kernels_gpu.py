@@ -472,6 +472,82 @@ def test_gradient_amax_tags_replace_the_amax_pass_bit_for_bit(monkeypatch):
     assert ops.known_amax(t) is None
 
 
+def test_feature_tap_l1_folded_into_the_conv_backward(monkeypatch):
+    """ops.tap_l1 (the perceptual loss's L1 on a VGG feature that deeper layers also consume): same loss values as
+    absdiff_mean, and the gradient that reaches the image equals the one autograd assembles from the separate L1 backward and
+    the deeper gradient - on the image-facing CUDA-core conv (3 -> 64), on tensor-core convs, through a max-pool, and for the
+    last tap (no deeper consumer)."""
+    ops = _ops()
+    img = _rand(6, 3, 16, 24, seed=1).to(DEV)
+    ws = [_rand(64, 3, 3, 3, seed=2, scale=0.2), _rand(64, 64, 3, 3, seed=3, scale=0.05), _rand(128, 64, 3, 3, seed=4, scale=0.05),
+          _rand(128, 128, 3, 3, seed=5, scale=0.04)]
+    ws = [w.to(DEV) for w in ws]
+    bs = [_rand(w.shape[0], seed=10 + i, scale=0.1).to(DEV) for i, w in enumerate(ws)]
+    coef = _rand(6, seed=20).to(DEV)           # a different upstream gradient per sample and tap
+
+    def chain(x, targets, fused):
+        losses, feats = [], []
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            if i == 2:
+                x = ops.maxpool2(x, planes=ops.conv_input_planes(weight_grad=False))
+            x = ops.conv2d(x, w, b, act=ops.ACT_RELU, out_planes=i in (0, 2))
+            if i in (0, 2, 3):
+                feats.append(x)
+                if targets is None:
+                    continue
+                if fused:
+                    x, l = ops.tap_l1(x, targets[len(losses)])
+                else:
+                    l = ops.absdiff_mean(targets[len(losses)], x)
+                losses.append(l)
+        return feats, losses
+
+    with torch.no_grad():
+        targets, _ = chain(ops.nhwc(_rand(6, 3, 16, 24, seed=7).to(DEV)), None, False)
+    results = []
+    for fused in (True, False):
+        calls = []
+        real = ops.call
+        monkeypatch.setattr(ops, "call", lambda name, *a: (calls.append(name), real(name, *a))[1])
+        x = ops.nhwc(img.clone()).requires_grad_(True)
+        _, losses = chain(x, targets, fused)
+        total = sum((l * coef * (k + 1)).sum() for k, l in enumerate(losses))
+        total.backward()
+        monkeypatch.setattr(ops, "call", real)
+        results.append(([l.detach().clone() for l in losses], x.grad.clone(), calls))
+    (lf, gf, cf), (lu, gu, cu) = results
+    for a, b in zip(lf, lu):
+        assert torch.equal(a, b)
+    _close("tap_l1_image_grad", gf, gu.cpu(), 2e-6, 1e-9)
+    assert cf.count("pvg_act_bwd_tap") == 1 and cf.count("pvg_act_bwd_tap_split_16_scaled") == 1, cf
+    assert cf.count("pvg_absdiff_mean_bwd") == 1 and cu.count("pvg_absdiff_mean_bwd") == 3      # fused: only the last tap
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 32), (3, 13, 40), (1, 256, 256), (5, 9, 7)])
+def test_stem_conv_3_to_64_with_planes(shape):
+    """pvg_conv2d_stem_planes (VGG conv1_1): fp32 CUDA-core result against float64, and the plane pair it writes for
+    conv1_2 against a split pass over its own output; ragged tiles included."""
+    ops = _ops()
+    from playablevideogeneration_b200 import _lib
+    n, h, w = shape
+    x = _rand(n, 3, h, w, seed=1).to(DEV)
+    wt = _rand(64, 3, 3, 3, seed=2, scale=0.3).to(DEV)
+    b = _rand(64, seed=3, scale=0.2).to(DEV)
+    calls = []
+    real = ops.call
+    ops.call = lambda name, *a: (calls.append(name), real(name, *a))[1]
+    try:
+        y = ops.conv2d(ops.nhwc(x), wt, b, act=ops.ACT_RELU, out_planes=True)
+    finally:
+        ops.call = real
+    assert "pvg_conv2d_stem_planes" in calls
+    ref = F.relu(F.conv2d(x.double().cpu(), wt.double().cpu(), b.double().cpu(), padding=1))
+    _close(f"stem{shape}", y, ref.float(), 2e-6, 1e-6)
+    pl = ops.planes_of(y)[_lib.CORR_FP16_ALL]
+    want = ops._split(y.detach(), 2, _lib.CORR_FP16_ALL)[1]
+    assert torch.equal(pl.view(torch.int16), want.view(torch.int16))
+
+
 def test_concat_pad_strided_time_slices():
     """Maps handed to the concat as time slices of a (B, T, C, H, W) tensor (batch-strided, NHWC-dense per sample) are read in
     place."""
