@@ -506,7 +506,8 @@ struct Stem3Cfg {
   static constexpr int PH = TH + 2, PWF = (TW + 2) * 3;      // staged rows, floats per staged row
 };
 
-__global__ void __launch_bounds__(Stem3Cfg::THREADS) conv_stem3_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <int MINB>
+__global__ void __launch_bounds__(Stem3Cfg::THREADS, MINB) conv_stem3_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                        const float* __restrict__ bias, float* __restrict__ y,
                                                                        uint16_t* __restrict__ planes, int64_t y_numel, int N,
                                                                        int H, int W, int act, float slope) {
@@ -588,8 +589,13 @@ int conv2d_stem3_planes(const pvg_conv_desc* d, const float* x, const float* w, 
                         cudaStream_t st) {
   using C = Stem3Cfg;
   const unsigned tiles = (unsigned)(ceil_div(d->W, C::TW) * ceil_div(d->H, C::TH) * d->N);
-  conv_stem3_kernel<<<tiles, C::THREADS, 0, st>>>(x, w, bias, y, (uint16_t*)y_planes, (int64_t)d->N * d->H * d->W * C::COUT,
-                                                  d->N, d->H, d->W, d->act, d->slope);
+  static int minb = 0;               // resident blocks per SM the register allocation aims for (PVG_STEM_MINB=1: no spills, 8 warps)
+  if (minb == 0) { const char* e = getenv("PVG_STEM_MINB"); minb = (e && atoi(e) == 1) ? 1 : 2; }
+  const int64_t y_numel = (int64_t)d->N * d->H * d->W * C::COUT;
+  if (minb == 1)
+    conv_stem3_kernel<1><<<tiles, C::THREADS, 0, st>>>(x, w, bias, y, (uint16_t*)y_planes, y_numel, d->N, d->H, d->W, d->act, d->slope);
+  else
+    conv_stem3_kernel<2><<<tiles, C::THREADS, 0, st>>>(x, w, bias, y, (uint16_t*)y_planes, y_numel, d->N, d->H, d->W, d->act, d->slope);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -346,3 +346,18 @@ def test_input_pipeline_formula_is_the_reference_transform():
     u8 = torch.from_numpy(g["frames"])[:, top:bottom, left:right]                   # (N, H, W, 3)
     got = ((u8.float() / 255.0) - 0.5) / 0.5
     assert np.array_equal(got.permute(0, 3, 1, 2).numpy(), g["out"])
+
+
+def test_small_distribution_losses_match_the_reference():
+    """KLDivergence, EntropyLogitLoss, EntropyProbabilityLoss, KLGaussianDivergenceLoss, KLGeneralGaussianDivergenceLoss
+    (training/losses.py:121-209, 339-376) against values and input gradients of the unmodified reference classes
+    (tests/golden/small_losses.npz, generated by oracle/make_loss_golden.py)."""
+    import numpy as np
+    from oracle.make_loss_golden import evaluate
+    from playablevideogeneration_b200.training import losses as L
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "small_losses.npz"))
+    got = evaluate(L)
+    assert sorted(got) == sorted(golden.files)
+    for k in golden.files:
+        np.testing.assert_allclose(got[k], golden[k], rtol=2e-6, atol=1e-7, err_msg=k)
+

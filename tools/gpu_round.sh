@@ -24,6 +24,7 @@ case $s in
   model) run model 900 python -m pytest tests/test_model_gpu.py -q -m gpu -p no:cacheprovider ;;
   smoke) run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
   bench_small) run bench_small 600 python bench.py --workload bair64_b2_t4 --steps 3 --warmup 3 --no-cpu-baseline ;;
+  stem) run stem 300 python tools/stem_bench.py; PVG_STEM_MINB=1 run stem_minb1 300 python tools/stem_bench.py ;;
   benchq) run benchq 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
   benchq_notags) PVG_NO_AMAX_TAGS=1 run benchq_notags 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
   bench) run bench 600 python bench.py --steps 3 --warmup 3 ;;
