@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (rollout) measurements")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true", help="skip the PyTorch-eager + cuDNN leg (same box, same batch)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the pre-run loss check against the CPU oracle")
+    ap.add_argument("--layer-table", default=None, help="write a per-shape table of the tensor-core conv launches of one step (markdown)")
     return ap.parse_args()
 
 
@@ -302,6 +303,43 @@ def _hbm_bytes(name, a):
     return None, 0
 
 
+def _write_layer_table(path, prof, wprof, shapes, peaks, ms_step, workload):
+    """Per-shape aggregate of the tensor-core convolution launches of one (eager, event-timed) step: time, algorithmic TFLOP/s
+    and the two floors that bound the shape - HBM (operand planes in, fp32 result and its planes out, at the measured
+    bandwidth) and tensor (3 kind::f16 MMAs per product at the measured bf16 rate)."""
+    agg = {}
+    for ent in list(prof) + [(a, b, f, "wgrad") for a, b, f in wprof]:
+        a, b, fl = ent[0], ent[1], ent[2]
+        sh = shapes.get(id(a))
+        if sh is None:
+            continue
+        role, n, h, w, cin, cout, r, planes, sums = sh
+        px = n * h * w
+        if role == "wgrad":
+            nbytes = px * 4.0 * (cin + cout)
+        elif role == "lstm":
+            nbytes = px * (4.0 * cin + 4.0 * cout + 3 * 4.0 * (cout // 4))
+        else:
+            nbytes = px * (4.0 * cin + 4.0 * cout + (4.0 * cout if planes else 0.0))
+        e = agg.setdefault(sh, [0, 0.0, 0.0, 0.0])
+        e[0] += 1; e[1] += a.elapsed_time(b); e[2] += fl; e[3] += nbytes
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    tot = sum(v[1] for _, v in rows)
+    with open(path, "w") as f:
+        f.write(f"# Tensor-core convolution launches of one training step, by shape ({workload})\n\n")
+        f.write("`python bench.py --layer-table ...`: CUDA events around every launch of one eager step after the timed region "
+                f"(graph replay of the whole step: {ms_step:.1f} ms).  floor = max(HBM floor, tensor floor): HBM floor = operand planes read + "
+                f"fp32 result (+ its planes) written at {peaks['hbm_gbs']:.0f} GB/s; tensor floor = 3 x algorithmic FLOPs at "
+                f"{peaks['tflops']:.0f} TFLOP/s (measured bf16 cuBLAS).  {len(rows)} shapes, {sum(v[0] for _, v in rows)} launches, {tot:.1f} ms.\n\n")
+        f.write("| role | N | HxW | Cin | Cout | k | planes | BN sums | launches | ms | us/launch | TFLOP/s | HBM floor ms | tensor floor ms | floor / time |\n")
+        f.write("|---|---:|---|---:|---:|---:|---|---|---:|---:|---:|---:|---:|---:|---:|\n")
+        for (role, n, h, w, cin, cout, r, planes, sums), (cnt, ms, fl, nb) in rows:
+            hb = nb / (peaks["hbm_gbs"] * 1e9) * 1e3
+            tf = 3.0 * fl / (peaks["tflops"] * 1e12) * 1e3
+            f.write(f"| {role} | {n} | {h}x{w} | {cin} | {cout} | {r} | {'y' if planes else ''} | {'y' if sums else ''} | {cnt} | {ms:.3f} | "
+                    f"{ms * 1e3 / cnt:.1f} | {fl / (ms * 1e-3) / 1e12:.1f} | {hb:.3f} | {tf:.3f} | {max(hb, tf) / ms:.2f} |\n")
+
+
 def cpu_reference_step_time(w, frames, steps, warmup):
     """The reference algorithm (CPU oracle port: oracle/caddy_oracle.py, pinned against the unmodified reference) on
     all host cores: forward + all losses + backward + Adam on a B=1 slice of the workload."""
@@ -517,6 +555,8 @@ def main():
     peaks = load_peaks()
     roof = None
     roof_hbm = None
+    if args.layer_table and rank == 0 and (prof or wprof):
+        _write_layer_table(args.layer_table, prof or [], wprof or [], ops.profile_shapes, peaks, ms_dev, args.workload)
     if prof:
         fams = {}
         for a_, b_, f_, kind in prof:

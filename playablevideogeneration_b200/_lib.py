@@ -6,7 +6,7 @@ import os
 from ctypes import c_double, c_float, c_int, c_int32, c_int64, c_void_p, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpvg_b200.so")
+LIB_PATH = os.environ.get("PVG_LIB") or os.path.join(_HERE, "libpvg_b200.so")      # PVG_LIB: an alternative build (A/B timing)
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_LSTM = 0, 1, 2, 3, 4, 5
 ALGO_AUTO, ALGO_SIMT, ALGO_UMMA, ALGO_UMMA_PERSISTENT = 0, 1, 2, 3

@@ -496,34 +496,27 @@ int conv2d_wgrad_direct(const pvg_conv_desc* d, int Cin_logical, const float* x,
 // ---------------------------------------------------------------------------------------------------------------
 // 3 -> 64 channels, 3x3 (VGG19 conv1_1, vgg.py:48-52 on the 256^2 frames: 240 frames per step per resolution).  The layer is
 // bound by its OUTPUT: 64 fp32 channels per pixel plus the fp16 plane pair conv1_2 consumes = 512 B per pixel against 1 728 FMAs.
-// 256 threads = 16 pixel groups x 16 channel quads; a thread keeps the 27 x 4 weights of its channel quad in registers and
-// walks the tile's pixels two at a time, so that every store instruction of a warp covers two whole pixels (2 x 256 B of y,
-// 2 x 128 B of each plane) instead of 32 different rows.  The haloed input tile (10 x 34 pixels x 3 channels) sits in shared
-// memory; the two pixels a warp works on read it as two broadcasts.
+// Persistent blocks of 256 threads = 16 pixel groups x 16 channel quads.  A thread keeps the 27 x 4 weights of its channel quad
+// in registers for the whole launch and computes 4 horizontally adjacent pixels x 4 channels at a time from five aligned
+// float4 shared-memory reads per input row (r01/r02 captures: the per-pixel variant spent its issue slots on scalar LDS).
+// A warp's store instruction covers two whole pixels (2 x 256 B of y, 2 x 128 B of each plane).  The haloed input tile
+// (10 x 34 pixels x 3 channels) is double-buffered: the next tile is fetched into registers while the current one is computed.
 // ---------------------------------------------------------------------------------------------------------------
 struct Stem3Cfg {
   static constexpr int TH = 8, TW = 32, COUT = 64, THREADS = 256;
-  static constexpr int PH = TH + 2, PWF = (TW + 2) * 3;      // staged rows, floats per staged row
+  static constexpr int PH = TH + 2, PWF = (TW + 2) * 3, PWS = 104;     // staged rows, floats per staged row, row stride
+  static constexpr int STAGE = (PH * PWF + THREADS - 1) / THREADS;     // staged floats per thread
+  static_assert(PWS % 4 == 0 && PWS >= (TW - 4) * 3 + 20, "aligned float4 reads stay inside the row");
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(Stem3Cfg::THREADS, MINB) conv_stem3_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                                       const float* __restrict__ bias, float* __restrict__ y,
-                                                                       uint16_t* __restrict__ planes, int64_t y_numel, int N,
-                                                                       int H, int W, int act, float slope) {
+__global__ void __launch_bounds__(Stem3Cfg::THREADS, 1) conv_stem3_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                          const float* __restrict__ bias, float* __restrict__ y,
+                                                                          uint16_t* __restrict__ planes, int64_t y_numel, int N,
+                                                                          int H, int W, int act, float slope) {
   using C = Stem3Cfg;
-  __shared__ float xs[C::PH][C::PWF + 2];
+  __shared__ __align__(16) float xs[2][C::PH][C::PWS];
   const int tiles_w = ceil_div(W, C::TW), tiles_h = ceil_div(H, C::TH);
-  int t = blockIdx.x;
-  const int tile_w = t % tiles_w; t /= tiles_w;
-  const int tile_h = t % tiles_h;
-  const int n = t / tiles_h;
-  const int ow0 = tile_w * C::TW, oh0 = tile_h * C::TH;
-  for (int i = threadIdx.x; i < C::PH * C::PWF; i += C::THREADS) {
-    const int py = i / C::PWF, pf = i - py * C::PWF;
-    const int ih = oh0 + py - 1, f = (ow0 - 1) * 3 + pf;            // f: float index inside the image row
-    xs[py][pf] = (ih >= 0 && ih < H && f >= 0 && f < W * 3) ? __ldg(x + ((int64_t)n * H + ih) * W * 3 + f) : 0.f;
-  }
+  const int tiles = tiles_w * tiles_h * N;
   const int cq = threadIdx.x & 15, pg = threadIdx.x >> 4;
   float wr[27][4];
 #pragma unroll
@@ -533,69 +526,102 @@ __global__ void __launch_bounds__(Stem3Cfg::THREADS, MINB) conv_stem3_kernel(con
   float b4[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) b4[j] = bias != nullptr ? __ldg(bias + cq * 4 + j) : 0.f;
+
+  float stage[C::STAGE];
+  auto fetch = [&](int tile) {
+    int t = tile;
+    const int tile_w = t % tiles_w; t /= tiles_w;
+    const int tile_h = t % tiles_h;
+    const int n = t / tiles_h;
+#pragma unroll
+    for (int q = 0; q < C::STAGE; ++q) {
+      const int i = threadIdx.x + q * C::THREADS;
+      const int py = i / C::PWF, pf = i - py * C::PWF;
+      const int ih = tile_h * C::TH + py - 1, f = (tile_w * C::TW - 1) * 3 + pf;          // f: float index inside the image row
+      stage[q] = (i < C::PH * C::PWF && ih >= 0 && ih < H && f >= 0 && f < W * 3) ? __ldg(x + ((int64_t)n * H + ih) * W * 3 + f) : 0.f;
+    }
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < C::STAGE; ++q) {
+      const int i = threadIdx.x + q * C::THREADS;
+      const int py = i / C::PWF, pf = i - py * C::PWF;
+      if (i < C::PH * C::PWF) xs[buf][py][pf] = stage[q];
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < tiles) { fetch(tile); commit(0); }
   __syncthreads();
+  for (int buf = 0; tile < tiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < tiles) fetch(next);
+    int t = tile;
+    const int tile_w = t % tiles_w; t /= tiles_w;
+    const int tile_h = t % tiles_h;
+    const int n = t / tiles_h;
+    const int ow0 = tile_w * C::TW, oh0 = tile_h * C::TH;
 #pragma unroll 1
-  for (int it = 0; it < C::TH * C::TW / 32; ++it) {
-    float acc[2][4];
-    int pp[2];
+    for (int it = 0; it < C::TH * C::TW / 64; ++it) {
+      const int quad = it * 16 + pg;                       // 4 adjacent pixels of one tile row
+      const int ph = quad / (C::TW / 4), pw = (quad % (C::TW / 4)) * 4;
+      float acc[4][4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      pp[u] = it * 32 + u * 16 + pg;
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[u][j] = b4[j];
-    }
+        for (int j = 0; j < 4; ++j) acc[u][j] = b4[j];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      float in[2][9];
+      for (int r = 0; r < 3; ++r) {
+        float in[20];
+        const float4* row = reinterpret_cast<const float4*>(&xs[buf][ph + r][pw * 3]);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float* row = &xs[pp[u] / C::TW + r][(pp[u] % C::TW) * 3];
+        for (int q = 0; q < 5; ++q) {
+          const float4 v = row[q];
+          in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        }
 #pragma unroll
-        for (int q = 0; q < 9; ++q) in[u][q] = row[q];
+        for (int q = 0; q < 9; ++q)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[u][j] = fmaf(in[u * 3 + q], wr[r * 9 + q][j], acc[u][j]);
       }
+      const int oh = oh0 + ph;
 #pragma unroll
-      for (int q = 0; q < 9; ++q)
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[u][j] = fmaf(in[u][q], wr[r * 9 + q][j], acc[u][j]);
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int oh = oh0 + pp[u] / C::TW, ow = ow0 + pp[u] % C::TW;
-      if (oh >= H || ow >= W) continue;
-      const float4 v = make_float4(act_fwd(acc[u][0], act, slope), act_fwd(acc[u][1], act, slope),
-                                   act_fwd(acc[u][2], act, slope), act_fwd(acc[u][3], act, slope));
-      const int64_t e = (((int64_t)n * H + oh) * W + ow) * C::COUT + cq * 4;
-      stg4(y + e, v);
-      if (planes != nullptr) {              // PVG_CORR_FP16_ALL pair: { f16((v - f16(v)) * 2^12), f16(v) }, see pointwise.cu
-        const float c0 = fminf(v.x, 65504.f), c1 = fminf(v.y, 65504.f), c2 = fminf(v.z, 65504.f), c3 = fminf(v.w, 65504.f);
-        const __half2 h01 = __floats2half2_rn(fmaxf(c0, -65504.f), fmaxf(c1, -65504.f));
-        const __half2 h23 = __floats2half2_rn(fmaxf(c2, -65504.f), fmaxf(c3, -65504.f));
-        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-        const float l0 = (v.x - f01.x) * 4096.f, l1 = (v.y - f01.y) * 4096.f, l2 = (v.z - f23.x) * 4096.f, l3 = (v.w - f23.y) * 4096.f;
-        const __half2 g01 = __floats2half2_rn(fminf(fmaxf(l0, -65504.f), 65504.f), fminf(fmaxf(l1, -65504.f), 65504.f));
-        const __half2 g23 = __floats2half2_rn(fminf(fmaxf(l2, -65504.f), 65504.f), fminf(fmaxf(l3, -65504.f), 65504.f));
-        *reinterpret_cast<uint2*>(planes + e) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
-        *reinterpret_cast<uint2*>(planes + y_numel + e) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      for (int u = 0; u < 4; ++u) {
+        const int ow = ow0 + pw + u;
+        if (oh >= H || ow >= W) continue;
+        const float4 v = make_float4(act_fwd(acc[u][0], act, slope), act_fwd(acc[u][1], act, slope),
+                                     act_fwd(acc[u][2], act, slope), act_fwd(acc[u][3], act, slope));
+        const int64_t e = (((int64_t)n * H + oh) * W + ow) * C::COUT + cq * 4;
+        stg4(y + e, v);
+        if (planes != nullptr) {              // PVG_CORR_FP16_ALL pair: { f16((v - f16(v)) * 2^12), f16(v) }, see pointwise.cu
+          const __half2 h01 = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
+          const __half2 h23 = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const float l0 = (v.x - f01.x) * 4096.f, l1 = (v.y - f01.y) * 4096.f, l2 = (v.z - f23.x) * 4096.f, l3 = (v.w - f23.y) * 4096.f;
+          const __half2 g01 = __floats2half2_rn(fminf(fmaxf(l0, -65504.f), 65504.f), fminf(fmaxf(l1, -65504.f), 65504.f));
+          const __half2 g23 = __floats2half2_rn(fminf(fmaxf(l2, -65504.f), 65504.f), fminf(fmaxf(l3, -65504.f), 65504.f));
+          *reinterpret_cast<uint2*>(planes + e) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
+          *reinterpret_cast<uint2*>(planes + y_numel + e) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        }
       }
     }
+    if (next < tiles) commit(buf ^ 1);
+    __syncthreads();
   }
 }
 
 int conv2d_stem3_planes(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* y_planes,
                         cudaStream_t st) {
   using C = Stem3Cfg;
-  const unsigned tiles = (unsigned)(ceil_div(d->W, C::TW) * ceil_div(d->H, C::TH) * d->N);
-  static int minb = 0;               // resident blocks per SM the register allocation aims for (PVG_STEM_MINB=1: no spills, 8 warps)
-  if (minb == 0) { const char* e = getenv("PVG_STEM_MINB"); minb = (e && atoi(e) == 1) ? 1 : 2; }
-  const int64_t y_numel = (int64_t)d->N * d->H * d->W * C::COUT;
-  if (minb == 1)
-    conv_stem3_kernel<1><<<tiles, C::THREADS, 0, st>>>(x, w, bias, y, (uint16_t*)y_planes, y_numel, d->N, d->H, d->W, d->act, d->slope);
-  else
-    conv_stem3_kernel<2><<<tiles, C::THREADS, 0, st>>>(x, w, bias, y, (uint16_t*)y_planes, y_numel, d->N, d->H, d->W, d->act, d->slope);
+  const int tiles = ceil_div(d->W, C::TW) * ceil_div(d->H, C::TH) * d->N;
+  static int sms = 0;
+  if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int grid = tiles < sms ? tiles : sms;        // one persistent block per SM (160 registers x 256 threads)
+  conv_stem3_kernel<<<grid, C::THREADS, 0, st>>>(x, w, bias, y, (uint16_t*)y_planes, (int64_t)d->N * d->H * d->W * C::COUT, d->N,
+                                                 d->H, d->W, d->act, d->slope);
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -29,7 +29,6 @@
 
 namespace pvg {
 
-constexpr int kH3Threads = 192;
 constexpr int kH3Budget = 200 * 1024;       // bytes of shared memory for the two rings
 constexpr int kHaloW = 10, kHaloH = 18;     // haloed 8 x 16 tile
 
@@ -47,7 +46,16 @@ struct H3Cfg {
   static constexpr int kAccCols = 3 * BN;                           // [main0 | main1 | correction]
   static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
   static constexpr int kBarBytes = (2 * kASlots + 2 * kBSlots + 5) * 8 + 16;
-  static constexpr int kStatBytes = 2 * 4 * BN * 2 * 4;            // BatchNorm partial sums: [tile parity][4 warps][BN][sum, sum^2]
+  static constexpr int kStatBytes = 2 * 4 * BN * 2 * 4;            // BatchNorm partial sums: [tile parity][4 lane quarters][BN][sum, sum^2]
+  // Epilogue warps: four (one per TMEM lane quarter) or, from 64 columns on, eight - two per quarter, each taking about half of
+  // the columns.  The epilogue drains the accumulator every period AND stores the finished tile: with four warps the store phase of
+  // a 128-column tile with planes outlasted two periods of the next tile's main loop and stalled the MMA warp (r02 layer table:
+  // planes cost 15 %, bias + ReLU 8 % on K = 2304 layers; layers with K <= 1152 ran at the epilogue's pace).
+  static constexpr int kEpiWarps = BN >= 64 ? 8 : 4;
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + kEpiThreads;
+  static constexpr int kSplitCol = kEpiWarps == 8 ? ((BN / 16 + 1) / 2) * 16 : BN;     // columns [0, kSplitCol) | [kSplitCol, BN)
+  static constexpr int kHalfCols = kSplitCol;                       // the wider half: size of the register accumulator
   static constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + 1024 + kBarBytes + kStatBytes + 16;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 128, "invalid N tile");
   static_assert(!PAIR || BN % 32 == 0, "a pair splits the weight rows in two MMA-legal halves");
@@ -173,7 +181,7 @@ __device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane) {
 }
 
 template <int BN, bool HALO, bool PAIR>
-__global__ void __launch_bounds__(kH3Threads, 1)
+__global__ void __launch_bounds__(H3Cfg<BN, HALO, PAIR>::kThreads, 1)
 conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
                const int total_items) {
   using C = H3Cfg<BN, HALO, PAIR>;
@@ -200,7 +208,7 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int chunks = p.Cin / 32;
   const int taps = p.R * p.S;
   const int k_iters = taps * chunks;
-  constexpr uint32_t kEpiArrivals = PAIR ? 256 : 128;
+  constexpr uint32_t kEpiArrivals = (PAIR ? 2 : 1) * C::kEpiThreads;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -362,9 +370,13 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5; in a pair each CTA drains its own 128 TMEM lanes) =====================
+    // ===================== epilogue (warps 2..; in a pair each CTA drains its own 128 TMEM lanes) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    const int half = (warp - 2) >> 2;       // which column half of the tile this warp owns (0 when there are four epilogue warps)
+    const int c_begin = half ? C::kSplitCol : 0;
+    const int c_width = half ? BN - C::kSplitCol : C::kSplitCol;
+    const int e_idx = half * 128 + row;     // index among the epilogue threads
     const int wi = row % p.tw;
     const int hi = (row / p.tw) % p.th;
     const int ni = row / (p.tw * p.th);
@@ -381,45 +393,101 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = ow < p.W && oh < p.H && on < p.N;
       const int64_t pix = ((int64_t)on * p.H + oh) * p.W + ow;
       float* yrow = p.y + pix * p.Cout;
-      float acc[BN];
+      float acc[C::kHalfCols];
       float tile_amax = 0.f;
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int j = 0; j < C::kHalfCols; ++j) acc[j] = 0.f;
       for (int per = 0; per < periods; ++per, ++pg) {
         const uint32_t b = pg & 1;
         mbar_wait(&tfull_bar[b], (pg >> 1) & 1);
         tc_fence_after();
+        // TMEM -> registers 32 columns at a time: two loads in flight per wait (r02 capture of a K = 576 layer: the epilogue
+        // warps sat on the long scoreboard - one tcgen05.ld round trip per 16 columns and one bias load per stored chunk)
 #pragma unroll
-        for (int c = 0; c < BN; c += 16) {
-          float v[16];
-          tmem_ld16(tmem_acc + lane_base + (uint32_t)(b * BN + c), v);
+        for (int cc = 0; cc < C::kHalfCols; cc += 32) {
+          if (cc >= c_width) break;
+          uint32_t r0[16], r1[16];
+          const uint32_t ta = tmem_acc + lane_base + (uint32_t)(b * BN + c_begin + cc);
+          const bool two = cc + 16 < C::kHalfCols && cc + 16 < c_width;
+          tmem_ld16_nowait(ta, r0);
+          if (two) tmem_ld16_nowait(ta + 16, r1);
+          tmem_ld_wait();
+          tmem_ld_use(r0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c + j] += v[j];
+          for (int j = 0; j < 16; ++j) acc[cc + j] += __uint_as_float(r0[j]);
+          if (cc + 16 < C::kHalfCols) {
+            if (two) {
+              tmem_ld_use(r1);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[cc + 16 + j] += __uint_as_float(r1[j]);
+            }
+          }
         }
         tc_fence_before();
         if (PAIR) mbar_arrive_leader(&tempty_bar[b]); else mbar_arrive(&tempty_bar[b]);
       }
       // TMEM reads only: fold the corrections (accumulated at 2^12 x their value) into the registers, then hand the
-      // correction buffer back to the MMA warp; bias / activation / stores overlap the next tile's main loop
+      // correction buffer back to the MMA warp; activation / stores overlap the next tile's main loop.  The bias joins here:
+      // its loads overlap the TMEM round trips instead of waiting behind the stores of the previous chunk.
+      const bool bias_here = p.bias != nullptr && p.act != PVG_ACT_LSTM;
 #pragma unroll
-      for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        tmem_ld16(tmem_acc + lane_base + (uint32_t)(2 * BN + c), v);
+      for (int cc = 0; cc < C::kHalfCols; cc += 32) {
+        if (cc >= c_width) break;
+        uint32_t r0[16], r1[16];
+        const uint32_t ta = tmem_acc + lane_base + (uint32_t)(2 * BN + c_begin + cc);
+        const bool two = cc + 16 < C::kHalfCols && cc + 16 < c_width;
+        tmem_ld16_nowait(ta, r0);
+        if (two) tmem_ld16_nowait(ta + 16, r1);
+        float bv[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(v[j], 0x1p-12f, acc[c + j]) * out_scale;
+        for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+        if (bias_here) {
+          const int co = t.co0 + c_begin + cc;
+          if (vec_ok && co + 16 <= p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j >= 16 && !(two && co + 32 <= p.Cout)) break;
+              const float4 b4 = ldg4(p.bias + co + j);
+              bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+            }
+            if (two && co + 32 > p.Cout) {
+#pragma unroll
+              for (int j = 16; j < 32; ++j)
+                if (co + j < p.Cout) bv[j] = __ldg(p.bias + co + j);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (co + j < p.Cout) bv[j] = __ldg(p.bias + co + j);
+          }
+        }
+        tmem_ld_wait();
+        tmem_ld_use(r0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[cc + j] = fmaf(__uint_as_float(r0[j]), 0x1p-12f, acc[cc + j]) * out_scale + bv[j];
+        if (cc + 16 < C::kHalfCols) {
+          if (two) {
+            tmem_ld_use(r1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              acc[cc + 16 + j] = fmaf(__uint_as_float(r1[j]), 0x1p-12f, acc[cc + 16 + j]) * out_scale + bv[16 + j];
+          }
+        }
       }
       tc_fence_before();
       if (PAIR) mbar_arrive_leader(cfree_bar); else mbar_arrive(cfree_bar);
 #pragma unroll
-      for (int c = 0; c < BN; c += 16) {
+      for (int cc = 0; cc < C::kHalfCols; cc += 16) {
+        if (cc >= c_width) break;
+        const int c = c_begin + cc;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = acc[c + j];
+        for (int j = 0; j < 16; ++j) v[j] = acc[cc + j];
         if (p.act == PVG_ACT_LSTM) {          // fused ConvLSTM cell: p.y = activated gates (optional), Cout = 4 * hidden channels
           lstm_finish16(v, p.bias, t.co0 + c, p.Cout, valid, p.lstm_c_prev, p.lstm_c_new, p.lstm_h_new, p.y, pix);
           continue;
         }
-        finish16(v, p.bias, t.co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);
+        finish16(v, nullptr, t.co0 + c, p.Cout, p.act, p.slope, yrow, valid, vec_ok);       // the bias is already in
         if (p.y_planes != nullptr && valid && t.co0 + c < p.Cout) {
           uint16_t* lo_row = p.y_planes + pix * p.Cout;          // Cout % 8 == 0 (checked by the host): 16-byte aligned rows
           store_planes16(v, lo_row, lo_row + p.y_numel, t.co0 + c, p.Cout);
@@ -448,19 +516,42 @@ conv_h3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0 && tile_amax == tile_amax) atomicMax(p.amax_out, __float_as_uint(tile_amax));
       }
       if (p.bn_sums != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
-        if (row < BN && t.co0 + row < p.Cout) {
-          const float* src = stat_part + ((tile_it & 1) * 4 * BN + row) * 2;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");            // the epilogue warps
+        if (e_idx < BN && t.co0 + e_idx < p.Cout) {
+          const float* src = stat_part + ((tile_it & 1) * 4 * BN + e_idx) * 2;
           const float s1 = src[0] + src[2 * BN] + src[4 * BN] + src[6 * BN];
           const float s2 = src[1] + src[2 * BN + 1] + src[4 * BN + 1] + src[6 * BN + 1];
           const int g = t.n0 / p.bn_samples_per_group;            // tiles never straddle groups (checked by the host)
           if (g < p.bn_groups) {
-            double* o = p.bn_sums + (size_t)g * 2 * p.Cout + t.co0 + row;
+            double* o = (p.bn_replicas > 0 ? p.bn_ws + (size_t)(blockIdx.x % p.bn_replicas) * p.bn_groups * 2 * p.Cout : p.bn_sums) +
+                        (size_t)g * 2 * p.Cout + t.co0 + e_idx;
             atomicAdd(o, (double)s1);
             atomicAdd(o + p.Cout, (double)s2);
           }
         }
         // the partials of tile i + 2 reuse this parity's slots: by then every warp has passed the barrier of tile i + 1
+      }
+    }
+    if (p.bn_sums != nullptr && p.bn_replicas > 0) {
+      // last CTA of the launch: replica copies -> bn_sums, and the workspace goes back to all-zero for the next launch
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");              // this CTA's atomics have all been issued and fenced
+      uint32_t* flag = reinterpret_cast<uint32_t*>(stat_part);
+      if (e_idx == 0) *flag = atomicAdd(p.bn_ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+      asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiThreads) : "memory");
+      if (*flag != 0u) {
+        __threadfence();
+        const int per = p.bn_groups * 2 * p.Cout;
+        for (int i = e_idx; i < per; i += C::kEpiThreads) {
+          double acc = 0.0;
+          for (int r = 0; r < p.bn_replicas; ++r) {
+            double* src = p.bn_ws + (size_t)r * per + i;
+            acc += __ldcg(src);
+            __stcg(src, 0.0);
+          }
+          p.bn_sums[i] += acc;
+        }
+        if (e_idx == 0) *p.bn_ticket = 0u;
       }
     }
   }
@@ -503,6 +594,26 @@ struct BnStatsOut { double* sums; int groups; };
 static thread_local BnStatsOut g_bn = {nullptr, 0};
 static thread_local uint32_t* g_amax_out = nullptr;      // amax_out argument of the current pvg_conv2d_fwd_planes call
 
+// Zero-kept workspace of the replicated BatchNorm sums (+ the ticket counter behind it), one per device, allocated at first use
+// (an eager call: not inside a stream capture).  Launches that use it must be stream-ordered with respect to each other - every
+// caller in this package runs its convolutions on one stream (or one captured graph).
+constexpr int kBnReplicasMax = 32;
+constexpr size_t kBnWsDoubles = 1u << 20;             // 8 MB: e.g. 32 copies x 16 groups x 2 x 1024 channels
+static double* bn_workspace(cudaStream_t st) {
+  static double* ws[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (ws[dev] == nullptr) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+    double* pnew = nullptr;
+    if (cudaMalloc(&pnew, (kBnWsDoubles + 2) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(pnew, 0, (kBnWsDoubles + 2) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); cudaFree(pnew); return nullptr; }
+    ws[dev] = pnew;
+  }
+  return ws[dev];
+}
+
 template <int BN, bool HALO, bool PAIR>
 static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w_planes, const float* bias, float* y,
                      void* y_planes, const float* out_scale, cudaStream_t st) {
@@ -521,6 +632,7 @@ static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w
   else choose_patch(d->N, d->H, d->W, &p.tw, &p.th, &p.tn);
   p.tiles_w = ceil_div(d->W, p.tw); p.tiles_h = ceil_div(d->H, p.th); p.tiles_n = ceil_div(d->N, p.tn);
   bool stats_after = false;             // BatchNorm statistics requested but this tiling cannot produce them: separate pass
+  p.bn_ws = nullptr; p.bn_ticket = nullptr; p.bn_replicas = 0;
   if (g_bn.sums != nullptr) {
     const int spg = d->N / g_bn.groups;
     if (spg % p.tn == 0) { p.bn_sums = g_bn.sums; p.bn_groups = g_bn.groups; p.bn_samples_per_group = spg; }   // tiles stay inside a group
@@ -541,9 +653,21 @@ static int launch_h3(const pvg_conv_desc* d, const void* x_planes, const void* w
   const int items = (PAIR ? ceil_div(m_tiles, 2) : m_tiles) * n_tiles;
   const int max_ctas = PAIR ? kSMs / 2 : kSMs;
   const int groups = items < max_ctas ? items : max_ctas;
+  if (p.bn_sums != nullptr) {
+    // replica count: enough copies that a copy sees few CTAs, bounded by the workspace; tiny launches keep the direct path
+    const int ctas = PAIR ? groups * 2 : groups;
+    const size_t per = (size_t)p.bn_groups * 2 * d->Cout;
+    int rep = ctas >= 8 ? (ctas < kBnReplicasMax ? ctas : kBnReplicasMax) : 0;
+    while (rep > 1 && per * rep > kBnWsDoubles) rep >>= 1;
+    static const int no_rep = env_int("PVG_BN_NO_REPLICAS", 0);
+    if (rep > 1 && !no_rep) {
+      double* ws = bn_workspace(st);
+      if (ws != nullptr) { p.bn_ws = ws; p.bn_ticket = reinterpret_cast<uint32_t*>(ws + kBnWsDoubles); p.bn_replicas = rep; }
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(PAIR ? groups * 2 : groups));
-  cfg.blockDim = dim3(kH3Threads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

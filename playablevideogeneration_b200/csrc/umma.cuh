@@ -116,6 +116,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load without the wait: issue several, then tmem_ld_wait() once, then tmem_ld_use() on every register block before
+// its values are read (ties the uses to the wait: the compiler may otherwise schedule them ahead of it).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_use(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // K-major swizzled operand tile of fp32/tf32: rows of KC*4 bytes (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row
 // swizzle atoms stacked along M/N.
 template <int KC>
@@ -297,6 +315,12 @@ struct ConvParams {
   float* lstm_h_new;
   double* bn_sums;              // conv_h3.cu, optional: [groups][2][Cout] per-channel sum / sum of squares of y (BatchNorm statistics)
   int bn_groups, bn_samples_per_group;
+  // Same-address fp64 atomics serialise in L2 (measured: ~2 ns per atomic with one [2][Cout] target, i.e. 0.9 ms for a 48-image
+  // decoder launch): CTAs accumulate into one of bn_replicas copies [replica][groups][2][Cout] in a library-owned, zero-kept
+  // workspace; the last CTA to finish (bn_ticket) adds the copies into bn_sums and zeroes them again.  bn_replicas == 0: direct.
+  double* bn_ws;
+  uint32_t* bn_ticket;
+  int bn_replicas;
   uint32_t* amax_out;           // conv_h3.cu, optional: atomicMax of the bit patterns of |y| (zero-initialised by the caller)
   int dbg;                      // conv_h3.cu timing experiments
 };

@@ -382,6 +382,7 @@ def _conv_forward(x: Tensor, packs: _Packs, which: int, cout: int, ksize: int, b
 
 
 wgrad_profile = None    # like conv_profile, for the tensor-core weight-gradient kernel
+profile_shapes = {}     # id(start event) -> (role, N, H, W, Cin, Cout, R, writes planes, writes BN sums) of a profiled launch
 stem_kernel = os.environ.get("PVG_NO_STEM_KERNEL") != "1"      # pvg_conv2d_stem_planes for 3 -> 64 channel 3x3 layers
 
 
@@ -435,6 +436,7 @@ class Conv2dFn(torch.autograd.Function):
             if prof:
                 e1.record()
                 conv_profile.append((e0, e1, flops, "h3"))
+                profile_shapes[id(e0)] = ("fwd", n, h, w, cin_p, cphys, r, bool(y_planes is not None), bool(bn_sums is not None))
         elif (algo == ALGO_SIMT and cin_p == 3 and cout == 64 and r == 3 and _precision != "fp32" and stem_kernel
               and _is_nhwc_dense(x)):
             # VGG19 conv1_1: output-bound CUDA-core kernel with coalesced stores that also writes the planes conv1_2 reads
@@ -644,6 +646,7 @@ def _backward_h3(ctx, dy, x, weight, y, tap=None):
         if prof:
             e1.record()
             conv_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log, "h3"))
+            profile_shapes[id(e0)] = ("dgrad", n, h, w, cout, cin_p, r, False, False)
     if ctx.needs_input_grad[1]:
         xp = ctx.x_wplanes if ctx.x_wplanes is not None else _split(x, 2, _lib.CORR_FP16_ALL)[1]
         deferred = wgrad_defer.active
@@ -662,6 +665,7 @@ def _backward_h3(ctx, dy, x, weight, y, tap=None):
         if prof:
             e1.record()
             wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log))
+            profile_shapes[id(e0)] = ("wgrad", n, h, w, cin_p, cout, r, False, False)
         if dw is not None and cout != cout_log:
             dw = dw[:cout_log]
     if need_g:
@@ -1044,6 +1048,7 @@ class ConvLSTMStepFn(torch.autograd.Function):
         if prof:
             e1.record()
             conv_profile.append((e0, e1, 2.0 * n * h * w * cout * r * r * cin_log, "h3"))
+            profile_shapes[id(e0)] = ("lstm", n, h, w, z.shape[1], cout, r, False, False)
         ctx.save_for_backward(z, w_il, gates, c_prev, c_new)
         ctx.zp = zp if w_il.requires_grad else None
         return h_new, c_new

@@ -24,7 +24,12 @@ case $s in
   model) run model 900 python -m pytest tests/test_model_gpu.py -q -m gpu -p no:cacheprovider ;;
   smoke) run smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
   bench_small) run bench_small 600 python bench.py --workload bair64_b2_t4 --steps 3 --warmup 3 --no-cpu-baseline ;;
-  stem) run stem 300 python tools/stem_bench.py; PVG_STEM_MINB=1 run stem_minb1 300 python tools/stem_bench.py ;;
+  ncu_stem) run ncu_stem 300 ncu --set full --clock-control none --import-source on -k regex:conv_stem3 -s 2 -c 1 -f -o $OUT/r02_stem python tools/stem_bench.py 120; python tools/ncu_extract.py $OUT/r02_stem.ncu-rep ;;
+  stem) run stem 300 python tools/stem_bench.py; run stem_t 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "stem or producer_planes" -p no:cacheprovider ;;
+  layers) run layers 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check --layer-table $OUT/r02_layer_table.md ;;
+  ncu_epi) run ncu_epi 300 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 3 -c 1 -f -o $OUT/r02_epi python tools/conv_micro.py 120 64 128 128 128 planes; python tools/ncu_extract.py $OUT/r02_epi.ncu-rep ;;
+  micro) run micro 600 python tools/conv_micro.py ;;
+  micro_ab) PVG_LIB=$PWD/tools/ab/libpvg_b200_ew4.so run micro_ew4 600 python tools/conv_micro.py ;;
   benchq) run benchq 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
   benchq_notags) PVG_NO_AMAX_TAGS=1 run benchq_notags 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
   bench) run bench 600 python bench.py --steps 3 --warmup 3 ;;

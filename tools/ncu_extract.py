@@ -9,13 +9,17 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__cycles_elapsed.max", "sm__cycles_elapsed.max.per_second", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+PREFIXES = ("smsp__average_warps_issue_stalled", "smsp__average_warp_latency_issue_stalled", "sm__inst_executed_pipe_", "smsp__issue_active",
+            "sm__pipe_fma", "sm__pipe_alu", "l1tex__lsu_writeback", "l1tex__data_bank_conflicts", "smsp__inst_executed_op_",
+            "l1tex__t_sectors_pipe_lsu_mem_global_op_st", "l1tex__t_requests_pipe_lsu_mem_global_op_st", "lts__t_sectors_op_write",
+            "l1tex__data_pipe_lsu_wavefronts", "smsp__warps_eligible", "smsp__pcsamp_warps_issue_stalled")
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 out = {"kernel": vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else None}
 for h, u, v in zip(hdr, units, vals):
-    if h in WANT:
+    if h in WANT or h.startswith(PREFIXES):
         out[h] = {"value": v, "unit": u}
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
@@ -24,9 +28,17 @@ if len(srows) > 2:
     isrc, isamp = sh.index("Source"), sh.index("# Samples")
     data = srows[2:]
     tot = sum(int(r[isamp]) for r in data)
-    top = sorted(data, key=lambda r: -int(r[isamp]))[:12]
+    top = sorted(data, key=lambda r: -int(r[isamp]))[:40]
     out["warp_samples_total"] = tot
     out["top_sampled_instructions"] = [{"sass": r[isrc].strip()[:90], "samples": int(r[isamp])} for r in top]
+    out["source_columns"] = sh
+    keep = [i for i, h in enumerate(sh) if h.lower().startswith(("stall", "warp stall", "address", "#")) or "stall" in h.lower()]
+    out["top_sampled_detail"] = [{sh[i]: r[i] for i in keep if r[i] not in ("", "0")} for r in top[:25]]
+    # position in the program: index of each top instruction in the listing (tells main loop / epilogue apart)
+    pos = {id(r): k for k, r in enumerate(data)}
+    for d_, r in zip(out["top_sampled_instructions"], top):
+        d_["index"] = pos[id(r)]
+    out["instructions_total"] = len(data)
 json.dump(out, open(rep.replace(".ncu-rep", ".json"), "w"), indent=1)
 os.remove(rep)
 print(rep, "->", out.get("gpu__time_duration.sum"))
