@@ -321,8 +321,9 @@ def _write_layer_table(path, prof, wprof, shapes, peaks, ms_step, workload):
             nbytes = px * (4.0 * cin + 4.0 * cout + 3 * 4.0 * (cout // 4))
         else:
             nbytes = px * (4.0 * cin + 4.0 * cout + (4.0 * cout if planes else 0.0))
-        e = agg.setdefault(sh, [0, 0.0, 0.0, 0.0])
-        e[0] += 1; e[1] += a.elapsed_time(b); e[2] += fl; e[3] += nbytes
+        e = agg.setdefault(sh, [0, 0.0, 0.0, 0.0, 1e30, 0.0])
+        ms_ = a.elapsed_time(b)
+        e[0] += 1; e[1] += ms_; e[2] += fl; e[3] += nbytes; e[4] = min(e[4], ms_); e[5] = max(e[5], ms_)
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
     tot = sum(v[1] for _, v in rows)
     with open(path, "w") as f:
@@ -331,13 +332,13 @@ def _write_layer_table(path, prof, wprof, shapes, peaks, ms_step, workload):
                 f"(graph replay of the whole step: {ms_step:.1f} ms).  floor = max(HBM floor, tensor floor): HBM floor = operand planes read + "
                 f"fp32 result (+ its planes) written at {peaks['hbm_gbs']:.0f} GB/s; tensor floor = 3 x algorithmic FLOPs at "
                 f"{peaks['tflops']:.0f} TFLOP/s (measured bf16 cuBLAS).  {len(rows)} shapes, {sum(v[0] for _, v in rows)} launches, {tot:.1f} ms.\n\n")
-        f.write("| role | N | HxW | Cin | Cout | k | planes | BN sums | launches | ms | us/launch | TFLOP/s | HBM floor ms | tensor floor ms | floor / time |\n")
-        f.write("|---|---:|---|---:|---:|---:|---|---|---:|---:|---:|---:|---:|---:|---:|\n")
-        for (role, n, h, w, cin, cout, r, planes, sums), (cnt, ms, fl, nb) in rows:
+        f.write("| role | N | HxW | Cin | Cout | k | planes | BN sums | launches | ms | us/launch | min us | max us | TFLOP/s | HBM floor ms | tensor floor ms | floor / time |\n")
+        f.write("|---|---:|---|---:|---:|---:|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for (role, n, h, w, cin, cout, r, planes, sums), (cnt, ms, fl, nb, lo_, hi_) in rows:
             hb = nb / (peaks["hbm_gbs"] * 1e9) * 1e3
             tf = 3.0 * fl / (peaks["tflops"] * 1e12) * 1e3
             f.write(f"| {role} | {n} | {h}x{w} | {cin} | {cout} | {r} | {'y' if planes else ''} | {'y' if sums else ''} | {cnt} | {ms:.3f} | "
-                    f"{ms * 1e3 / cnt:.1f} | {fl / (ms * 1e-3) / 1e12:.1f} | {hb:.3f} | {tf:.3f} | {max(hb, tf) / ms:.2f} |\n")
+                    f"{ms * 1e3 / cnt:.1f} | {lo_ * 1e3:.1f} | {hi_ * 1e3:.1f} | {fl / (ms * 1e-3) / 1e12:.1f} | {hb:.3f} | {tf:.3f} | {max(hb, tf) / ms:.2f} |\n")
 
 
 def cpu_reference_step_time(w, frames, steps, warmup):
@@ -528,6 +529,7 @@ def main():
         if cls is None:
             return orig_call(name, *cargs)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.profile_spin()
         a.record()
         rc = orig_call(name, *cargs)
         b.record()
@@ -538,11 +540,15 @@ def main():
     from playablevideogeneration_b200.training import losses as _losses_mod
     _losses_mod.ops.call = timed_call
     launches0 = _lib.launch_count
-    torch.cuda._sleep(int(2.5e9))      # ~1.3 s of GPU spin: lets the host run ahead so that events bracket pure kernel time
+    # Events must bracket pure kernel time, but an eager step is host-bound (~17 k launches from Python): a 150 us spin kernel
+    # is queued in front of every bracketed launch, so that the start event, the kernel and the end event are all in the queue
+    # before the GPU reaches them.
+    ops.profile_spin_cycles = 300_000
     try:
         step.step(resident, w["gt_init"], 1.0)
     finally:
         _lib.call = ops.call = orig_call
+        ops.profile_spin_cycles = 0
     barrier()
     launches = (_lib.launch_count - launches0) * args.steps
     prof, ops.conv_profile = ops.conv_profile, None
@@ -588,7 +594,7 @@ def main():
         roof = dict(fam_rows[0])
         roof.update(peak_source=peaks["source"], other_tensor_kernels=fam_rows[1:], weight_gradient=wg,
                     traffic_source="profiles/r02_conv_traffic.json (ncu dram__bytes_read+write per launch, averaged over the step's launches of the family)" if roof.get("traffic") else None,
-                    measured="CUDA events around each launch in one extra eager (non-graph) step after the timed region",
+                    measured="CUDA events around each launch in one extra eager (non-graph) step after the timed region; a 150 us spin kernel in front of every bracketed launch keeps the host's launch latency out of the bracket",
                     note="achieved = algorithmic conv FLOPs (2*N*H*W*Cout*R*S*Cin, unpadded) / CUDA-event time of the family's launches; "
                          "peak is the measured bf16 cuBLAS figure; fp32-equivalent results need 3 tensor-core products per multiply")
     if hbm_events:

@@ -102,6 +102,11 @@ int pvg_conv2d_wgrad_planes(const pvg_conv_desc* d, int Cin_logical, const void*
                             const float* out_scale, float* scratch, float* dw_oihw, int accumulate, void* stream);
 /* dw_oihw == NULL defers the unpack: a weight that is used at every time step (autograd sums over its uses,
  * training/trainer.py:584-587) lets all its uses accumulate their split-K partials in ONE scratch and unpacks once: */
+/* Weight gradient of a 3x3 convolution with 16 / 32 channels on both sides, in fp32 on the CUDA cores (the GEMM is tiny, K is every
+ * pixel: the first encoder stage, residual_block.py:52-58).  x: [N,H,W,d->Cin], g = dY: [N,H,W,d->Cout], both fp32; scratch /
+ * dw_oihw / accumulate exactly as for pvg_conv2d_wgrad_planes (same packed scratch, so uses of one weight may mix both). */
+int pvg_conv2d_wgrad_small(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* g, float* scratch, float* dw_oihw,
+                           int accumulate, void* stream);
 int pvg_unpack_dw(const float* scratch, int Cout, int Cin_logical, int R, int S, int CinPhys, float* dw_oihw, int accumulate,
                   void* stream);
 /* OIHW [Cout][Cin][R][S] -> forward pack [Cout][R][S][CinK] and data-gradient pack [CinRows][R][S][CoutK] with flipped

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "pvg_conv2d_stem_planes": [POINTER(ConvDesc), P, P, P, P, P, P],
     "pvg_conv2d_fwd_planes": [POINTER(ConvDesc), P, P, P, P, P, P, P, c_int, P, P],
     "pvg_conv2d_wgrad_planes": [POINTER(ConvDesc), c_int, P, P, P, P, P, c_int, P],
+    "pvg_conv2d_wgrad_small": [POINTER(ConvDesc), c_int, P, P, P, P, c_int, P],
     "pvg_unpack_dw": [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P],
     "pvg_amax": [P, c_int64, P, P],
     "pvg_split_16_scaled": [P, P, c_int64, P, P, P],

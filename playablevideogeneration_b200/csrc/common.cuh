@@ -1,5 +1,6 @@
 // Shared helpers for the pvg_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -47,6 +48,18 @@ __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+// fp16 pair / scalar from fp32, round to nearest, saturating at +-65504 in ONE instruction (F2FP.SATFINITE...PACK_AB) - the
+// conversion every producer of fp16 operand planes uses (finite inputs: identical to clamp + cvt.rn)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_round_sat(float v) {         // the value f16(v) carries, as fp32
+  const uint32_t r = pack_f16x2_sat(v, 0.f);
+  return __half2float(__ushort_as_half((unsigned short)(r & 0xffffu)));
 }
 
 __device__ __forceinline__ float act_fwd(float v, int act, float slope) {

@@ -595,16 +595,12 @@ __global__ void __launch_bounds__(Stem3Cfg::THREADS, 1) conv_stem3_kernel(const 
         const int64_t e = (((int64_t)n * H + oh) * W + ow) * C::COUT + cq * 4;
         stg4(y + e, v);
         if (planes != nullptr) {              // PVG_CORR_FP16_ALL pair: { f16((v - f16(v)) * 2^12), f16(v) }, see pointwise.cu
-          const __half2 h01 = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
-          const __half2 h23 = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
-          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          const float l0 = (v.x - f01.x) * 4096.f, l1 = (v.y - f01.y) * 4096.f, l2 = (v.z - f23.x) * 4096.f, l3 = (v.w - f23.y) * 4096.f;
-          const __half2 g01 = __floats2half2_rn(fminf(fmaxf(l0, -65504.f), 65504.f), fminf(fmaxf(l1, -65504.f), 65504.f));
-          const __half2 g23 = __floats2half2_rn(fminf(fmaxf(l2, -65504.f), 65504.f), fminf(fmaxf(l3, -65504.f), 65504.f));
-          *reinterpret_cast<uint2*>(planes + e) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&g01), *reinterpret_cast<const uint32_t*>(&g23));
-          *reinterpret_cast<uint2*>(planes + y_numel + e) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          const uint32_t h01 = pack_f16x2_sat(v.x, v.y), h23 = pack_f16x2_sat(v.z, v.w);
+          const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01)), f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+          const uint32_t g01 = pack_f16x2_sat((v.x - f01.x) * 4096.f, (v.y - f01.y) * 4096.f);
+          const uint32_t g23 = pack_f16x2_sat((v.z - f23.x) * 4096.f, (v.w - f23.y) * 4096.f);
+          *reinterpret_cast<uint2*>(planes + e) = make_uint2(g01, g23);
+          *reinterpret_cast<uint2*>(planes + y_numel + e) = make_uint2(h01, h23);
         }
       }
     }
@@ -716,7 +712,121 @@ int conv2d_fwd_direct(const pvg_conv_desc* d, const float* x, const float* w, co
 
 }  // namespace pvg
 
+namespace pvg {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of 3x3 convolutions with 16 / 32 channels on both sides (the first encoder stage: 16 channels at 128 x 128
+// over all B*T frames, residual_block.py:52-58).  The GEMM is 144..288 x 16..32 with K = every pixel of the batch: the
+// tensor-core kernel spent 0.93 ms on 268 MB (r02 layer table: 10 TFLOP/s, 4 % of its floor).  Here a thread owns one
+// (input channel, output channel) pair - or 2 / 4 of them - and keeps its 9 taps in registers while persistent blocks walk
+// the image tiles; x slides through a 3 x 3 register window, so a pixel costs 3 + P shared-memory reads for 9 P FMAs.
+// fp32 products and sums; one atomicAdd per accumulator and block into the packed scratch of the tensor-core path.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+struct WgradSmallCfg {
+  static constexpr int TH = 4, TW = 32, THREADS = 256;
+  static constexpr int COG = THREADS / CIN;               // output channels covered by one pass over the threads
+  static constexpr int P = COUT / COG;                    // (ci, co) pairs per thread
+  static constexpr int XROW = (TW + 2) * CIN;
+  static_assert(COUT % COG == 0 && P >= 1, "thread mapping");
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                          float* __restrict__ scratch, int N, int H, int W) {
+  using C = WgradSmallCfg<CIN, COUT>;
+  __shared__ __align__(16) float xs[C::TH + 2][C::XROW];
+  __shared__ __align__(16) float gs[C::TH][C::TW * COUT];
+  const int ci = threadIdx.x % CIN, cb = threadIdx.x / CIN;
+  const int tiles_w = ceil_div(W, C::TW), tiles_h = ceil_div(H, C::TH);
+  const int tiles = tiles_w * tiles_h * N;
+  float acc[C::P][9];
+#pragma unroll
+  for (int k = 0; k < C::P; ++k)
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[k][q] = 0.f;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int t = tile;
+    const int tile_w = t % tiles_w; t /= tiles_w;
+    const int tile_h = t % tiles_h;
+    const int n = t / tiles_h;
+    const int ow0 = tile_w * C::TW, oh0 = tile_h * C::TH;
+    __syncthreads();                                   // the previous tile has been consumed
+    for (int i = threadIdx.x; i < (C::TH + 2) * (C::XROW / 4); i += C::THREADS) {
+      const int py = i / (C::XROW / 4), pf = (i - py * (C::XROW / 4)) * 4;
+      const int ih = oh0 + py - 1, iw = ow0 - 1 + pf / CIN;          // CIN % 4 == 0: a float4 stays inside one pixel
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = ldg4(x + (((int64_t)n * H + ih) * W + iw) * CIN + pf % CIN);
+      *reinterpret_cast<float4*>(&xs[py][pf]) = v;
+    }
+    for (int i = threadIdx.x; i < C::TH * (C::TW * COUT / 4); i += C::THREADS) {
+      const int py = i / (C::TW * COUT / 4), pf = (i - py * (C::TW * COUT / 4)) * 4;
+      const int oh = oh0 + py, ow = ow0 + pf / COUT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oh < H && ow < W) v = ldg4(g + (((int64_t)n * H + oh) * W + ow) * COUT + pf % COUT);
+      *reinterpret_cast<float4*>(&gs[py][pf]) = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ph = 0; ph < C::TH; ++ph) {
+      float win[3][3];                                 // x[ph + r][pw + s][ci]
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        win[r][1] = xs[ph + r][ci];
+        win[r][2] = xs[ph + r][CIN + ci];
+      }
+#pragma unroll 4
+      for (int pw = 0; pw < C::TW; ++pw) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          win[r][0] = win[r][1]; win[r][1] = win[r][2];
+          win[r][2] = xs[ph + r][(pw + 2) * CIN + ci];
+        }
+#pragma unroll
+        for (int k = 0; k < C::P; ++k) {
+          const float gv = gs[ph][pw * COUT + cb + k * C::COG];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[k][r * 3 + q] = fmaf(gv, win[r][q], acc[k][r * 3 + q]);
+        }
+      }
+    }
+  }
+  constexpr int CinP = (CIN + 31) & ~31;
+#pragma unroll
+  for (int k = 0; k < C::P; ++k)
+#pragma unroll
+    for (int q = 0; q < 9; ++q) atomicAdd(scratch + ((size_t)(cb + k * C::COG) * 9 + q) * CinP + ci, acc[k][q]);
+}
+
+template <int CIN, int COUT>
+static int launch_wgrad_small(const pvg_conv_desc* d, const float* x, const float* g, float* scratch, cudaStream_t st) {
+  using C = WgradSmallCfg<CIN, COUT>;
+  const int tiles = ceil_div(d->W, C::TW) * ceil_div(d->H, C::TH) * d->N;
+  const int grid = tiles < 148 * 2 ? tiles : 148 * 2;      // persistent: two blocks per SM, one flush of the accumulators each
+  wgrad_small_kernel<CIN, COUT><<<grid, C::THREADS, 0, st>>>(x, g, scratch, d->N, d->H, d->W);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace pvg
+
 using namespace pvg;
+
+extern "C" int pvg_conv2d_wgrad_small(const pvg_conv_desc* d, int Cin_logical, const float* x, const float* g, float* scratch,
+                                      float* dw_oihw, int accumulate, void* stream) {
+  PVG_CHECK_ARG(d && x && g && scratch, "null argument");
+  PVG_CHECK_ARG((d->Cin == 16 || d->Cin == 32) && (d->Cout == 16 || d->Cout == 32) && d->R == 3 && d->S == 3 && d->pad == 1,
+                "16 / 32 channels on both sides, 3x3, 'same' padding only");
+  PVG_CHECK_ARG((((uintptr_t)x | (uintptr_t)g) & 15) == 0, "x / g must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (d->Cin == 16) rc = d->Cout == 16 ? launch_wgrad_small<16, 16>(d, x, g, scratch, st) : launch_wgrad_small<16, 32>(d, x, g, scratch, st);
+  else rc = d->Cout == 16 ? launch_wgrad_small<32, 16>(d, x, g, scratch, st) : launch_wgrad_small<32, 32>(d, x, g, scratch, st);
+  if (rc || dw_oihw == nullptr) return rc;
+  return pvg_unpack_dw(scratch, d->Cout, Cin_logical, 3, 3, d->Cin, dw_oihw, accumulate, stream);
+}
 
 extern "C" int pvg_conv2d_stem_planes(const pvg_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
                                       void* y_planes, void* stream) {

@@ -89,8 +89,7 @@ __device__ __forceinline__ uint64_t h3_desc(uint32_t smem_addr, uint32_t sbo) {
 }
 
 __device__ __forceinline__ uint32_t h3_pack2(float a, float b) {
-  __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-  return *reinterpret_cast<uint32_t*>(&v);
+  return pack_f16x2_sat(a, b);
 }
 
 // fp16 plane pair of 16 finished output values (the PVG_CORR_FP16_ALL operand format of the next convolution)
@@ -98,8 +97,10 @@ __device__ __forceinline__ void store_planes16(const float (&v)[16], uint16_t* _
                                                int co, int Cout) {
   if (co + 16 > Cout) {                        // ragged tail of the last N tile (e.g. 72 channels)
     for (int j = 0; j < Cout - co; ++j) {
-      const __half h = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
-      const __half l = __float2half_rn(fminf(fmaxf((v[j] - __half2float(h)) * 4096.f, -65504.f), 65504.f));
+      const uint32_t hb = pack_f16x2_sat(v[j], 0.f);
+      const __half h = __ushort_as_half((unsigned short)(hb & 0xffffu));
+      const uint32_t lb = pack_f16x2_sat((v[j] - __half2float(h)) * 4096.f, 0.f);
+      const __half l = __ushort_as_half((unsigned short)(lb & 0xffffu));
       hi_row[co + j] = *reinterpret_cast<const uint16_t*>(&h);
       lo_row[co + j] = *reinterpret_cast<const uint16_t*>(&l);
     }

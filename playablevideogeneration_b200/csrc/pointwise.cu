@@ -46,8 +46,7 @@ __device__ __forceinline__ float tf32_part(float v, bool rna) {
 template <int FMT>
 __device__ __forceinline__ uint32_t f16x2_bits(float a, float b) {
   if (FMT != PVG_CORR_BF16) {
-    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t*>(&v);
+    return pack_f16x2_sat(a, b);
   }
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -56,7 +55,7 @@ __device__ __forceinline__ uint32_t f16x2_bits(float a, float b) {
 // operand) or, in the all-fp16 evaluation, f16(v)
 template <int FMT>
 __device__ __forceinline__ float hi_part(float v) {
-  if (FMT == PVG_CORR_FP16_ALL) return __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+  if (FMT == PVG_CORR_FP16_ALL) return f16_round_sat(v);
   return tf32_part(v, false);
 }
 template <int FMT>

@@ -343,6 +343,7 @@ def _run_conv(x, x_lo, w, w_lo, bias, y, ksize, pad, act, slope, algo, nprod, fm
     prof = conv_profile is not None and algo == ALGO_UMMA
     if prof:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        profile_spin()
         e0.record()
     call("pvg_conv2d_fwd", d, x.data_ptr(), _p(x_lo), w.data_ptr(), _p(w_lo), _p(bias), y.data_ptr(), _stream())
     if prof:
@@ -382,7 +383,17 @@ def _conv_forward(x: Tensor, packs: _Packs, which: int, cout: int, ksize: int, b
 
 
 wgrad_profile = None    # like conv_profile, for the tensor-core weight-gradient kernel
+profile_spin_cycles = 0  # > 0: a spin kernel of that many clocks is queued in front of every profiled launch
+
+
+def profile_spin() -> None:
+    """Keeps the GPU busy while the host queues [start event, kernel, end event] of a profiled launch.  Without it an eager,
+    host-bound step measures the host's launch latency: the start event is stamped by an idle GPU and the kernel arrives tens
+    of microseconds later (a 43 us conv read 96 us, a 178 us one 1 ms in the first round-2 layer table)."""
+    if profile_spin_cycles > 0:
+        torch.cuda._sleep(int(profile_spin_cycles))
 profile_shapes = {}     # id(start event) -> (role, N, H, W, Cin, Cout, R, writes planes, writes BN sums) of a profiled launch
+small_wgrad_kernel = os.environ.get("PVG_NO_SMALL_WGRAD") != "1"    # pvg_conv2d_wgrad_small for 16 / 32-channel 3x3 layers
 stem_kernel = os.environ.get("PVG_NO_STEM_KERNEL") != "1"      # pvg_conv2d_stem_planes for 3 -> 64 channel 3x3 layers
 
 
@@ -428,6 +439,7 @@ class Conv2dFn(torch.autograd.Function):
             prof = conv_profile is not None
             if prof:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                profile_spin()
                 e0.record()
             if bn_groups and act == ACT_NONE and b is None:
                 bn_sums = zero_pool.zeros((bn_groups, 2, cphys), torch.float64, x.device)
@@ -564,6 +576,7 @@ class Conv2dFn(torch.autograd.Function):
                 prof = wgrad_profile is not None
                 if prof:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    profile_spin()
                     e0.record()
                 call("pvg_conv2d_wgrad_umma", d, cin_log, x_hi.data_ptr(), _p(x_lo), g_hi.data_ptr(), _p(g_lo),
                      scratch.data_ptr(), dw4.data_ptr(), 0, _stream())
@@ -637,6 +650,7 @@ def _backward_h3(ctx, dy, x, weight, y, tap=None):
         prof = conv_profile is not None
         if prof:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            profile_spin()
             e0.record()
         dx_amax = zero_pool.zeros((1,), torch.int32, dev) if track_amax else None
         call("pvg_conv2d_fwd_planes", d, planes.data_ptr(), packs.lo(2, 2, _lib.CORR_FP16_ALL).data_ptr(), None, dx.data_ptr(), None,
@@ -648,7 +662,13 @@ def _backward_h3(ctx, dy, x, weight, y, tap=None):
             conv_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log, "h3"))
             profile_shapes[id(e0)] = ("dgrad", n, h, w, cout, cin_p, r, False, False)
     if ctx.needs_input_grad[1]:
-        xp = ctx.x_wplanes if ctx.x_wplanes is not None else _split(x, 2, _lib.CORR_FP16_ALL)[1]
+        # 16 / 32 channels on both sides: tiny GEMM, K = every pixel - fp32 CUDA-core kernel on x and dY themselves
+        # (measured, r02 layer table: 16 -> 16 over 128 frames 929 -> 445 us, 16 -> 32 951 -> 631 us; with 32 input channels the
+        #  tensor-core kernel is the faster one, so those stay there)
+        use_small = small_wgrad_kernel and act == ACT_NONE and r == 3 and cin_p == 16 and cout in (16, 32)
+        xp = None
+        if not use_small:
+            xp = ctx.x_wplanes if ctx.x_wplanes is not None else _split(x, 2, _lib.CORR_FP16_ALL)[1]
         deferred = wgrad_defer.active
         if deferred:
             dw, scratch = None, wgrad_defer.scratch_for(weight, cin_p, cout, r, s, dev)
@@ -659,9 +679,13 @@ def _backward_h3(ctx, dy, x, weight, y, tap=None):
         prof = wgrad_profile is not None
         if prof:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            profile_spin()
             e0.record()
-        call("pvg_conv2d_wgrad_planes", d, cin_log, xp.data_ptr(), planes.data_ptr(), inv.data_ptr(), scratch.data_ptr(),
-             _p(dw), 0, st)
+        if use_small:
+            call("pvg_conv2d_wgrad_small", d, cin_log, x.data_ptr(), dy.data_ptr(), scratch.data_ptr(), _p(dw), 0, st)
+        else:
+            call("pvg_conv2d_wgrad_planes", d, cin_log, xp.data_ptr(), planes.data_ptr(), inv.data_ptr(), scratch.data_ptr(),
+                 _p(dw), 0, st)
         if prof:
             e1.record()
             wgrad_profile.append((e0, e1, 2.0 * n * h * w * cout_log * r * s * cin_log))
@@ -1042,6 +1066,7 @@ class ConvLSTMStepFn(torch.autograd.Function):
         prof = conv_profile is not None
         if prof:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            profile_spin()
             e0.record()
         call("pvg_convlstm_step", d, zp.data_ptr(), packs.lo(0, 2, fmt).data_ptr(), b_il.detach().contiguous().data_ptr(),
              c_prev.data_ptr(), c_new.data_ptr(), h_new.data_ptr(), _p(gates), _stream())

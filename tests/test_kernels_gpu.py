@@ -548,6 +548,59 @@ def test_stem_conv_3_to_64_with_planes(shape):
     assert torch.equal(pl.view(torch.int16), want.view(torch.int16))
 
 
+@pytest.mark.parametrize("shape", [(3, 16, 16, 20, 40), (2, 16, 32, 13, 33), (4, 16, 32, 8, 8), (2, 16, 16, 37, 64), (128, 16, 16, 128, 128)])
+def test_small_channel_weight_gradient_kernel(shape):
+    """pvg_conv2d_wgrad_small (16 input channels, the first encoder stage) through conv2d's backward, against float64; the
+    data gradient of the same call still comes from the tensor-core kernel.  The 32-input-channel instantiations of the
+    kernel are exercised through the C ABI directly."""
+    ops = _ops()
+    n, cin, cout, h, w = shape
+    x = ops.nhwc(_rand(n, cin, h, w, seed=1).to(DEV)).requires_grad_(True)
+    wt = _rand(cout, cin, 3, 3, seed=2, scale=(cin * 9) ** -0.5).to(DEV).requires_grad_(True)
+    gy = _rand(n, cout, h, w, seed=3).to(DEV)
+    calls = []
+    real = ops.call
+    ops.call = lambda name, *a: (calls.append(name), real(name, *a))[1]
+    try:
+        y = ops.conv2d(x, wt)
+        y.backward(gy)
+    finally:
+        ops.call = real
+    assert "pvg_conv2d_wgrad_small" in calls and "pvg_conv2d_wgrad_planes" not in calls
+    if n * h * w <= 200000:
+        xd, wd = x.detach().double().cpu().requires_grad_(True), wt.detach().double().cpu().requires_grad_(True)
+        F.conv2d(xd, wd, padding=1).backward(gy.double().cpu())
+        _close(f"wgrad_small{shape}", wt.grad, wd.grad.float(), 2e-6, 1e-6)
+        _close(f"wgrad_small_dx{shape}", x.grad, xd.grad.float(), 2e-6, 1e-6)
+    else:                       # full encoder size: against the tensor-core kernel
+        small = wt.grad.clone()
+        wt.grad = None; x.grad = None
+        ops.small_wgrad_kernel = False
+        try:
+            ops.conv2d(x, wt).backward(gy)
+        finally:
+            ops.small_wgrad_kernel = True
+        _close(f"wgrad_small_vs_tc{shape}", small, wt.grad.cpu(), 1e-5, 1e-5)
+
+
+def test_small_channel_weight_gradient_kernel_32_inputs():
+    ops = _ops()
+    from playablevideogeneration_b200._lib import ConvDesc
+    from playablevideogeneration_b200 import _lib
+    for cout in (16, 32):
+        n, cin, h, w = 3, 32, 11, 40
+        x = ops.nhwc(_rand(n, cin, h, w, seed=1).to(DEV))
+        g = ops.nhwc(_rand(n, cout, h, w, seed=2).to(DEV))
+        scratch = torch.zeros(cout * 9 * 32, device=DEV)
+        dw = torch.empty(cout, cin, 3, 3, device=DEV)
+        d = ConvDesc(n, h, w, cin, cout, 3, 3, 1, 0, 0.0, _lib.ALGO_SIMT, 1, 0)
+        ops.call("pvg_conv2d_wgrad_small", d, cin, x.data_ptr(), g.data_ptr(), scratch.data_ptr(), dw.data_ptr(), 0,
+                 torch.cuda.current_stream().cuda_stream)
+        wd = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+        F.conv2d(x.double().cpu(), wd, padding=1).backward(g.double().cpu())
+        _close(f"wgrad_small_c32_{cout}", dw, wd.grad.float(), 2e-6, 1e-6)
+
+
 def test_concat_pad_strided_time_slices():
     """Maps handed to the concat as time slices of a (B, T, C, H, W) tensor (batch-strided, NHWC-dense per sample) are read in
     place."""

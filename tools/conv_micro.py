@@ -38,6 +38,36 @@ def run(n, cin, cout, h, w, bias, act, planes, groups):
     return sorted(ts)[1] * 1e3
 
 
+def run_lstm(n, cin, hidden, h, w):
+    cout = 4 * hidden
+    x = ops.empty_nhwc((n, cin, h, w), dev).normal_()
+    wt = torch.randn(cout, cin, 3, 3, device=dev) * (cin * 9) ** -0.5
+    b = torch.randn(cout, device=dev)
+    xp = ops._split(x, 2, FMT)[1]
+    wp = ops._get_packs(wt, cin, True, cout).lo(0, 2, FMT)
+    c_prev = ops.empty_nhwc((n, hidden, h, w), dev).normal_()
+    c_new, h_new = torch.empty_like(c_prev), torch.empty_like(c_prev)
+    gates = ops.empty_nhwc((n, cout, h, w), dev)
+    d = ConvDesc(n, h, w, cin, cout, 3, 3, 1, 0, 0.0, _lib.ALGO_UMMA, 2, FMT)
+    st = torch.cuda.current_stream().cuda_stream
+    ts = []
+    for it in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.call("pvg_convlstm_step", d, xp.data_ptr(), wp.data_ptr(), b.data_ptr(), c_prev.data_ptr(), c_new.data_ptr(),
+                 h_new.data_ptr(), gates.data_ptr(), st)
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[1] * 1e3
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "lstm":
+    for n, cin, hidden, h, w in ((8, 544, 256, 16, 16), (8, 288, 128, 32, 32), (8, 224, 128, 32, 32), (64, 544, 256, 16, 16)):
+        us = run_lstm(n, cin, hidden, h, w)
+        fl = 2.0 * n * h * w * 4 * hidden * 9 * cin
+        print(f"lstm N={n} {h}x{w} {cin}->{4 * hidden}: {us:8.1f} us ({fl / us / 1e6:6.1f} TF/s)", flush=True)
+    sys.exit(0)
 if len(sys.argv) > 6:          # one shape, one epilogue mode (for ncu): n cin cout h w mode[plain|bias+relu|planes|sums]
     n, cin, cout, h, w = (int(v) for v in sys.argv[1:6])
     mode = sys.argv[6]

@@ -29,6 +29,7 @@ case $s in
   layers) run layers 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check --layer-table $OUT/r02_layer_table.md ;;
   ncu_epi) run ncu_epi 300 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 3 -c 1 -f -o $OUT/r02_epi python tools/conv_micro.py 120 64 128 128 128 planes; python tools/ncu_extract.py $OUT/r02_epi.ncu-rep ;;
   micro) run micro 600 python tools/conv_micro.py ;;
+  micro_lstm) run micro_lstm 300 python tools/conv_micro.py lstm ;;
   micro_ab) PVG_LIB=$PWD/tools/ab/libpvg_b200_ew4.so run micro_ew4 600 python tools/conv_micro.py ;;
   benchq) run benchq 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
   benchq_notags) PVG_NO_AMAX_TAGS=1 run benchq_notags 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
