@@ -109,8 +109,15 @@ __device__ void channel_reduce(int64_t row_begin, int64_t row_end, int C, double
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[k][j] = 0.0;
   if (lane < lanes) {
-    for (int64_t r = row_begin + (int64_t)blockIdx.x * lanes + lane; r < row_end; r += (int64_t)gridDim.x * lanes)
+    const int64_t st = (int64_t)gridDim.x * lanes;
+    int64_t r = row_begin + (int64_t)blockIdx.x * lanes + lane;
+    for (; r + 3 * st < row_end; r += 4 * st) {      // four rows per trip: four times the loads in flight per thread
       f(r, unit, acc);
+      f(r + st, unit, acc);
+      f(r + 2 * st, unit, acc);
+      f(r + 3 * st, unit, acc);
+    }
+    for (; r < row_end; r += st) f(r, unit, acc);
   }
   // sum over lanes in shared memory, one (k, j) slice at a time to bound the footprint at 2 KB
   __shared__ double slice[kRedThreads];
@@ -126,6 +133,44 @@ __device__ void channel_reduce(int64_t row_begin, int64_t row_end, int C, double
         atomicAdd(&out[(size_t)k * C + threadIdx.x * V + j], s);
       }
       __syncthreads();
+    }
+  }
+}
+
+// Row walk of the element-wise BatchNorm kernels: a thread keeps ONE V-wide channel unit (so its per-channel constants live in
+// registers: `reload(g, c)` runs once per batch group the thread meets) and strides over the rows.  The first version decoded
+// (row, channel, group) from a flat index with three 64-bit divisions and re-read up to 16 per-channel constants for every
+// float4: the kernels ran at 1.5 - 2.2 TB/s (r02 launch list) while max-pool, with the same traffic pattern, reaches 6.
+template <int N_>
+struct RowCount { static constexpr int value = N_; };
+
+// `body(r, step, c, RowCount<R>{})` handles the R rows r, r + step, ... of one batch group: it issues the loads of all of them
+// before it computes and stores (R x the bytes in flight per thread; R = 1 for the tail and around group boundaries).
+template <int V, int ROWS, class Reload, class Body>
+__device__ __forceinline__ void walk_rows(int C, int64_t M, int64_t rows_per_group, Reload reload, Body body) {
+  const int U = C / V;
+  const int lanes = blockDim.x / U;
+  const int unit = threadIdx.x % U, lane = threadIdx.x / U;
+  if (lane >= lanes) return;
+  const int c = unit * V;
+  int64_t r = (int64_t)blockIdx.x * lanes + lane;
+  const int64_t step = (int64_t)gridDim.x * lanes;
+  if (r >= M) return;
+  int g = (int)(r / rows_per_group);
+  int64_t bound = (int64_t)(g + 1) * rows_per_group;
+  reload(g, c);
+  while (r < M) {
+    if (r >= bound) {
+      do { ++g; bound += rows_per_group; } while (r >= bound);
+      reload(g, c);
+    }
+    const int64_t last = r + (ROWS - 1) * step;
+    if (ROWS > 1 && last < M && last < bound) {
+      body(r, step, c, RowCount<ROWS>{});
+      r += ROWS * step;
+    } else {
+      body(r, step, c, RowCount<1>{});
+      r += step;
     }
   }
 }
@@ -210,26 +255,40 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const int Cp) {
   // Cp <= C: channels that HAVE parameters (a 65-channel BatchNorm on a tensor physically padded to 72 channels so that its
   // convolutions run on the tensor cores); the padding channels are zero in, zero out
-  const int U = C / V;
-  const int64_t total = M * U;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / U;
-    int c = (int)(i % U) * V;
-    int g = (int)(r / rows_per_group);
-    Vec<V> t = Vec<V>::load(x + r * C + c), o;
-    Vec<V> res;
-    if (residual) res = Vec<V>::load(residual + r * C + c);
+  float km[V], ki[V], kw[V], kb[V];
+  walk_rows<V, 4>(
+      C, M, rows_per_group,
+      [&](int g, int c) {
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const bool real = c + j < Cp;
-      float w = real ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f, b = (real && bias) ? __ldg(bias + c + j) : 0.f;
-      float v = (t.v[j] - __ldg(mean + (size_t)g * C + c + j)) * __ldg(invstd + (size_t)g * C + c + j) * w + b;
-      if (residual) v += res.v[j];
-      o.v[j] = act_fwd(v, act, slope);
-    }
-    o.store(y + r * C + c);
-    emit_planes<V>(po, r * C + c, o);
-  }
+        for (int j = 0; j < V; ++j) {
+          const bool real = c + j < Cp;
+          kw[j] = real ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f;
+          kb[j] = (real && bias) ? __ldg(bias + c + j) : 0.f;
+          km[j] = __ldg(mean + (size_t)g * C + c + j);
+          ki[j] = __ldg(invstd + (size_t)g * C + c + j);
+        }
+      },
+      [&](int64_t r, int64_t step, int c, auto rows) {
+        constexpr int R = decltype(rows)::value;
+        Vec<V> t[R], res[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          t[i] = Vec<V>::load(x + (r + i * step) * C + c);
+          if (residual) res[i] = Vec<V>::load(residual + (r + i * step) * C + c);
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          Vec<V> o;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float v = (t[i].v[j] - km[j]) * ki[j] * kw[j] + kb[j];
+            if (residual) v += res[i].v[j];
+            o.v[j] = act_fwd(v, act, slope);
+          }
+          o.store(y + (r + i * step) * C + c);
+          emit_planes<V>(po, (r + i * step) * C + c, o);
+        }
+      });
 }
 
 template <int V>
@@ -240,6 +299,12 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(const float*
                                                                     double* __restrict__ sums2) {
   const int g = blockIdx.y;
   const int64_t r0 = (int64_t)g * rows_per_group;
+  float km[V], ki[V];                     // this thread's channel unit is fixed (channel_reduce): its statistics live in registers
+  {
+    const int c = (int)(threadIdx.x % (C / V)) * V;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { km[j] = __ldg(mean + (size_t)g * C + c + j); ki[j] = __ldg(invstd + (size_t)g * C + c + j); }
+  }
   channel_reduce<V, 2>(r0, r0 + rows_per_group, C, sums2 + (size_t)g * 2 * C,
                        [&](int64_t r, int unit, double (*acc)[V]) {
                          int c = unit * V;
@@ -248,7 +313,7 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(const float*
 #pragma unroll
                          for (int j = 0; j < V; ++j) {
                            float gg = d.v[j] * (act != PVG_ACT_NONE ? act_bwd_from_out(yv.v[j], act, slope) : 1.f);
-                           float xhat = (xv.v[j] - __ldg(mean + (size_t)g * C + c + j)) * __ldg(invstd + (size_t)g * C + c + j);
+                           float xhat = (xv.v[j] - km[j]) * ki[j];
                            acc[0][j] += gg;
                            acc[1][j] += (double)gg * xhat;
                          }
@@ -297,26 +362,40 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* __r
     }
   }
   __syncthreads();
-  const int U = C / V;
-  const int64_t total = M * U;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / U;
-    int c = (int)(i % U) * V;
-    int g = (int)(r / rows_per_group);
-    Vec<V> t = Vec<V>::load(x + r * C + c), o;
-    Vec<V> res;
-    if (residual) res = Vec<V>::load(residual + r * C + c);
+  float km[V], ki[V], kw[V], kb[V];
+  walk_rows<V, 4>(
+      C, M, rows_per_group,
+      [&](int g, int c) {
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const bool real = c + j < Cp;
-      float w = real ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f, b = (real && bias) ? __ldg(bias + c + j) : 0.f;
-      float v = (t.v[j] - s_mean[(size_t)g * C + c + j]) * s_inv[(size_t)g * C + c + j] * w + b;
-      if (residual) v += res.v[j];
-      o.v[j] = act_fwd(v, act, slope);
-    }
-    o.store(y + r * C + c);
-    emit_planes<V>(po, r * C + c, o);
-  }
+        for (int j = 0; j < V; ++j) {
+          const bool real = c + j < Cp;
+          kw[j] = real ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f;
+          kb[j] = (real && bias) ? __ldg(bias + c + j) : 0.f;
+          km[j] = s_mean[(size_t)g * C + c + j];
+          ki[j] = s_inv[(size_t)g * C + c + j];
+        }
+      },
+      [&](int64_t r, int64_t step, int c, auto rows) {
+        constexpr int R = decltype(rows)::value;
+        Vec<V> t[R], res[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          t[i] = Vec<V>::load(x + (r + i * step) * C + c);
+          if (residual) res[i] = Vec<V>::load(residual + (r + i * step) * C + c);
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          Vec<V> o;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float v = (t[i].v[j] - km[j]) * ki[j] * kw[j] + kb[j];
+            if (residual) v += res[i].v[j];
+            o.v[j] = act_fwd(v, act, slope);
+          }
+          o.store(y + (r + i * step) * C + c);
+          emit_planes<V>(po, (r + i * step) * C + c, o);
+        }
+      });
 }
 
 template <int V>
@@ -336,49 +415,75 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       if (dbias) dbias[c] = (float)sg;
     }
   }
-  const int U = C / V;
-  const int64_t total = M * U;
   const double inv_count = 1.0 / (double)rows_per_group;
   float amax = 0.f;              // largest |dx| this thread writes (the 0.25 of the un-pooling is applied at the end)
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / U;
-    int c = (int)(i % U) * V;
-    int g = (int)(r / rows_per_group);
-    Vec<V> d = Vec<V>::load(dy + r * C + c), xv = Vec<V>::load(x + r * C + c), yv, o, go;
-    if (act != PVG_ACT_NONE) yv = Vec<V>::load(y + r * C + c);
+  float km[V], ki[V], kw[V], ksg[V], ksgx[V];
+  const bool small = M < (int64_t)0x7fffffff;          // 32-bit divisions for the un-pooling coordinates
+  walk_rows<V, 2>(
+      C, M, rows_per_group,
+      [&](int g, int c) {
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float gg = d.v[j] * (act != PVG_ACT_NONE ? act_bwd_from_out(yv.v[j], act, slope) : 1.f);
-      go.v[j] = gg;
-      float is = __ldg(invstd + (size_t)g * C + c + j);
-      float w = (c + j < Cp) ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f;
-      float val;
-      if (eval) {
-        val = w * is * gg;
-      } else {
-        float xhat = (xv.v[j] - __ldg(mean + (size_t)g * C + c + j)) * is;
-        float sg = (float)(sums2[((size_t)g * 2 + 0) * C + c + j] * inv_count);
-        float sgx = (float)(sums2[((size_t)g * 2 + 1) * C + c + j] * inv_count);
-        val = w * is * (gg - sg - xhat * sgx);
-      }
-      o.v[j] = val;
-      amax = fmaxf(amax, fabsf(val));
-    }
-    if (g_out) go.store(g_out + r * C + c);
-    if (!unpool) {
-      o.store(dx + r * C + c);
-    } else {
+        for (int j = 0; j < V; ++j) {
+          ki[j] = __ldg(invstd + (size_t)g * C + c + j);
+          kw[j] = (c + j < Cp) ? (weight ? __ldg(weight + c + j) : 1.f) : 0.f;
+          km[j] = __ldg(mean + (size_t)g * C + c + j);
+          ksg[j] = eval ? 0.f : (float)(sums2[((size_t)g * 2 + 0) * C + c + j] * inv_count);
+          ksgx[j] = eval ? 0.f : (float)(sums2[((size_t)g * 2 + 1) * C + c + j] * inv_count);
+        }
+      },
+      [&](int64_t r0, int64_t step, int c, auto rows) {
+        constexpr int R = decltype(rows)::value;
+        Vec<V> d[R], xv[R], yv[R];
 #pragma unroll
-      for (int j = 0; j < V; ++j) o.v[j] *= 0.25f;
-      int ow = (int)(r % OW);
-      int64_t t = r / OW;
-      int oh = (int)(t % OH);
-      int64_t n = t / OH;
-      const int W = OW * 2, H = OH * 2;
-      float* p = dx + ((n * H + 2 * oh) * W + 2 * ow) * C + c;
-      o.store(p); o.store(p + C); o.store(p + (int64_t)W * C); o.store(p + (int64_t)W * C + C);
-    }
-  }
+        for (int i = 0; i < R; ++i) {
+          const int64_t r = r0 + i * step;
+          d[i] = Vec<V>::load(dy + r * C + c);
+          xv[i] = Vec<V>::load(x + r * C + c);
+          if (act != PVG_ACT_NONE) yv[i] = Vec<V>::load(y + r * C + c);
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const int64_t r = r0 + i * step;
+          Vec<V> o, go;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float gg = d[i].v[j] * (act != PVG_ACT_NONE ? act_bwd_from_out(yv[i].v[j], act, slope) : 1.f);
+            go.v[j] = gg;
+            float val;
+            if (eval) {
+              val = kw[j] * ki[j] * gg;
+            } else {
+              float xhat = (xv[i].v[j] - km[j]) * ki[j];
+              val = kw[j] * ki[j] * (gg - ksg[j] - xhat * ksgx[j]);
+            }
+            o.v[j] = val;
+            amax = fmaxf(amax, fabsf(val));
+          }
+          if (g_out) go.store(g_out + r * C + c);
+          if (!unpool) {
+            o.store(dx + r * C + c);
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.v[j] *= 0.25f;
+            int ow, oh;
+            int64_t n;
+            if (small) {
+              const uint32_t r32 = (uint32_t)r, t32 = r32 / (uint32_t)OW;
+              ow = (int)(r32 - t32 * (uint32_t)OW);
+              n = t32 / (uint32_t)OH;
+              oh = (int)(t32 - (uint32_t)n * (uint32_t)OH);
+            } else {
+              ow = (int)(r % OW);
+              const int64_t t = r / OW;
+              oh = (int)(t % OH);
+              n = t / OH;
+            }
+            const int W = OW * 2, H = OH * 2;
+            float* p = dx + ((n * H + 2 * oh) * W + 2 * ow) * C + c;
+            o.store(p); o.store(p + C); o.store(p + (int64_t)W * C); o.store(p + (int64_t)W * C + C);
+          }
+        }
+      });
   if (amax_out != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -1135,10 +1240,11 @@ int pvg_bn_apply_ex(const float* x, int N, int HW, int C, int groups, const floa
                     void* planes_a, int fmt_a, void* planes_b, int fmt_b, int Cparams, void* stream) {
   const int Cp = (Cparams > 0 && Cparams < C) ? Cparams : C;
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  PVG_CHECK_ARG(((C % 4 == 0) ? C / 4 : C) <= 256, "unsupported channel count");
   if (!planes_ok(planes_a, planes_b, C)) return -1;
   int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
   const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, M * C);
-  DISPATCH_V(C, (bn_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_V(C, (bn_apply_kernel<V><<<ew_grid((M * (C / V) + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(
                     x, M, rpg, C, mean, invstd, weight, bias, residual, act, slope, y, po, Cp)));
   PVG_LAUNCH_OK();
   return 0;
@@ -1155,13 +1261,14 @@ int pvg_bn_finalize_apply_ex(const float* x, int N, int HW, int C, int groups, c
                              const float* weight, const float* bias, const float* residual, int act, float slope, float* y,
                              void* planes_a, int fmt_a, void* planes_b, int fmt_b, int Cparams, void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  PVG_CHECK_ARG(((C % 4 == 0) ? C / 4 : C) <= 256, "unsupported channel count");
   if (!planes_ok(planes_a, planes_b, C)) return -1;
   const int Cp = (Cparams > 0 && Cparams < C) ? Cparams : C;
   const size_t smem = (size_t)groups * C * 2 * sizeof(float);
   PVG_CHECK_ARG(smem <= 48 * 1024, "groups * C too large for the fused kernel: call pvg_bn_finalize + pvg_bn_apply");
   int64_t M = (int64_t)N * HW, rpg = (int64_t)(N / groups) * HW;
   const PlaneOut po = make_planes(planes_a, fmt_a, planes_b, fmt_b, M * C);
-  DISPATCH_V(C, (bn_finalize_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, smem, (cudaStream_t)stream>>>(
+  DISPATCH_V(C, (bn_finalize_apply_kernel<V><<<ew_grid((M * (C / V) + 3) / 4, 256), 256, smem, (cudaStream_t)stream>>>(
                     x, M, rpg, C, groups, sums, (double)count, eps, momentum, running_mean, running_var, mean, invstd, weight,
                     bias, residual, act, slope, y, po, Cp)));
   PVG_LAUNCH_OK();
@@ -1201,10 +1308,11 @@ int pvg_bn_bwd_apply_ex(const float* dy, const float* y, const float* x, int N, 
                         int eval, int unpool, float* dx, float* g_out, float* dweight, float* dbias, int Cparams, uint32_t* amax_out,
                         void* stream) {
   PVG_CHECK_ARG(groups >= 1 && N % groups == 0, "N must be divisible by groups");
+  PVG_CHECK_ARG(((C % 4 == 0) ? C / 4 : C) <= 256, "unsupported channel count");
   const int Cp = (Cparams > 0 && Cparams < C) ? Cparams : C;
   int OH = unpool ? H / 2 : H, OW = unpool ? W / 2 : W;
   int64_t M = (int64_t)N * OH * OW, rpg = (int64_t)(N / groups) * OH * OW;
-  DISPATCH_V(C, (bn_bwd_apply_kernel<V><<<ew_grid(M * (C / V), 256), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_V(C, (bn_bwd_apply_kernel<V><<<ew_grid((M * (C / V) + 1) / 2, 256), 256, 0, (cudaStream_t)stream>>>(
                     dy, y, x, M, rpg, OH, OW, C, mean, invstd, weight, act, slope, sums2, eval, unpool, dx, g_out, groups, dweight,
                     dbias, Cp, amax_out)));
   PVG_LAUNCH_OK();

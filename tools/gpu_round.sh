@@ -28,6 +28,7 @@ case $s in
   stem) run stem 300 python tools/stem_bench.py; run stem_t 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "stem or producer_planes" -p no:cacheprovider ;;
   layers) run layers 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check --layer-table $OUT/r02_layer_table.md ;;
   ncu_epi) run ncu_epi 300 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 3 -c 1 -f -o $OUT/r02_epi python tools/conv_micro.py 120 64 128 128 128 planes; python tools/ncu_extract.py $OUT/r02_epi.ncu-rep ;;
+  bn_micro) run bn_micro 300 python tools/bn_micro.py; PVG_LIB=$PWD/tools/ab/libpvg_b200_oldbn.so run bn_micro_old 300 python tools/bn_micro.py ;;
   micro) run micro 600 python tools/conv_micro.py ;;
   micro_lstm) run micro_lstm 300 python tools/conv_micro.py lstm ;;
   micro_ab) PVG_LIB=$PWD/tools/ab/libpvg_b200_ew4.so run micro_ew4 600 python tools/conv_micro.py ;;
