@@ -96,7 +96,9 @@ __device__ __forceinline__ uint32_t h3_pack2(float a, float b) {
 __device__ __forceinline__ void store_planes16(const float (&v)[16], uint16_t* __restrict__ lo_row, uint16_t* __restrict__ hi_row,
                                                int co, int Cout) {
   if (co + 16 > Cout) {                        // ragged tail of the last N tile (e.g. 72 channels)
-    for (int j = 0; j < Cout - co; ++j) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {             // static indices: a run-time trip count would push v[] into local memory
+      if (j >= Cout - co) break;
       const uint32_t hb = pack_f16x2_sat(v[j], 0.f);
       const __half h = __ushort_as_half((unsigned short)(hb & 0xffffu));
       const uint32_t lb = pack_f16x2_sat((v[j] - __half2float(h)) * 4096.f, 0.f);
