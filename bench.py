@@ -517,6 +517,15 @@ def main():
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3) / args.steps)
+    if use_graph and world == 1:
+        # the captured graph's private memory pool (104 GB at Breakout B=16 x T=32) is not needed any more: the eager profiling
+        # step below allocates its activations from the ordinary pool and would not fit next to it on the largest workloads
+        del total
+        gstep = run_resident = run_host = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
     # ---- one more step launched kernel by kernel with CUDA events around EVERY C-ABI call: the per-kernel durations behind
     #      `roofline` (tensor-core convs, from their algorithmic FLOPs) and `roofline_hbm` (bandwidth-bound kernel classes,
     #      from their algorithmic bytes); events cannot be timed inside a graph replay.  Also counts launches. ----------------

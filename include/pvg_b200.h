@@ -229,6 +229,14 @@ int pvg_bn_bwd_params(const double* sums2, int groups, int C, float* dweight, fl
  *      dst: [N][H][W][3] fp32 = ((u8 / 255) - mean) / std of the box at (left, top); bit-identical to the CPU transform. */
 int pvg_frames_u8_to_nhwc(const uint8_t* src, int N, int Hs, int Ws, int left, int top, int H, int W, float mean, float std,
                           float* dst, void* stream);
+/* One pass of PIL's Image.resize(size, BILINEAR) on 8-bit RGB frames (dataset/transforms.py:28: the resize applied when the
+ * cropped frame does not have the model's input size; antialiased, 22-bit fixed point): src [N,Hs,Ws,3], input box
+ * (left, top, Hin, Win), resampled along the width (vertical == 0: dst [N,Hin,out_size,3]) or the height (vertical != 0: dst
+ * [N,out_size,Win,3]).  bounds [out_size][2] = (first input position, count), kk [out_size][ksize] = Pillow's integer
+ * coefficients (device arrays; the host side computes them as precompute_coeffs + normalize_coeffs_8bpc do).  Horizontal pass
+ * first, then vertical, as in ImagingResample: bit-identical to Pillow. */
+int pvg_resample_u8(const uint8_t* src, int N, int Hs, int Ws, int left, int top, int Hin, int Win, int vertical, int out_size,
+                    const int* bounds, const int* kk, int ksize, uint8_t* dst, void* stream);
 
 /* ---- resampling: F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) at up_block.py:35,43;
  *      F.interpolate(size, 'bilinear') of the ground truth at losses.py:92,450; nn.MaxPool2d(2) of VGG19 -------- */

@@ -84,5 +84,35 @@ def input_pipeline_golden():
     print("input pipeline golden", out.shape, float(out.min()), float(out.max()))
 
 
+def input_resize_golden():
+    """dataset/transforms.py:15-32 + 90-108 when the cropped frame does NOT have the target size: PIL crop, PIL
+    ``resize(BILINEAR)`` (antialiased, 8-bit fixed point), ToTensor, Normalize -> tests/golden/input_resize.npz."""
+    from PIL import Image
+    R.install_shims()
+    sys.path.insert(0, R.REF_ROOT)
+    from dataset.transforms import TransformsGenerator
+    rng = np.random.RandomState(11)
+    out = {}
+    cases = {"down": ((2, 60, 90, 3), [10, 5, 74, 53], [32, 20]),        # 64 x 48 crop -> 32 x 20 (w, h): both axes shrink
+             "up": ((2, 30, 40, 3), None, [64, 48]),                      # no crop, both axes grow
+             "mixed": ((2, 50, 70, 3), [3, 1, 67, 49], [48, 48]),         # 64 x 48 crop -> 48 x 48: width shrinks, height kept
+             "bair": ((1, 64, 64, 3), None, [256, 256])}                  # BAIR's native 64 x 64 frames to the 256 x 256 model input
+    for name, (shape, crop, size) in cases.items():
+        frames = rng.randint(0, 256, size=shape, dtype=np.uint8)
+        cfg = {"data": {"crop": crop}, "model": {"representation_network": {"target_input_size": size}}}
+        tf = TransformsGenerator.get_final_transforms(cfg)["train"]
+        res = np.stack([tf(Image.fromarray(f)).numpy() for f in frames])
+        rs = TransformsGenerator.check_and_resize(crop, size)
+        out[f"{name}.frames"] = frames
+        out[f"{name}.crop"] = np.array(crop if crop is not None else [-1, -1, -1, -1])
+        out[f"{name}.size"] = np.array(size)
+        out[f"{name}.u8"] = np.stack([np.asarray(rs(Image.fromarray(f))) for f in frames])
+        out[f"{name}.out"] = res
+    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "input_resize.npz")
+    np.savez_compressed(path, **out)
+    print({k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__" and "--input-pipeline" in sys.argv:
     input_pipeline_golden()
+    input_resize_golden()

@@ -80,6 +80,7 @@ _SIGNATURES = {
     "pvg_lstm_bwd": [P, P, P, P, P, c_int64, c_int, P, P, P],
     "pvg_absdiff_mean_fwd": [P, P, c_int, c_int64, P, P],
     "pvg_absdiff_mean_bwd": [P, P, P, c_int, c_int64, P, P],
+    "pvg_resample_u8": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P],
     "pvg_frames_u8_to_nhwc": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, P, P],
     "pvg_sqdiff_mean": [P, P, c_int, c_int, c_int, c_int64, c_int, c_int, P, P],
     "pvg_frames_to_u8": [P, c_int64, P, P, P],

@@ -1179,6 +1179,32 @@ __global__ void __launch_bounds__(256) frames_u8_kernel(const uint8_t* __restric
   }
 }
 
+// One pass of PIL's two-pass ``Image.resize(size, BILINEAR)`` on 8-bit RGB (dataset/transforms.py:28; Pillow's
+// ImagingResampleHorizontal_8bpc / Vertical_8bpc): out = clip8((2^21 + sum_k in[first + k] * coeff[k]) >> 22) with the 22-bit
+// fixed-point coefficient table and the (first, count) bounds of every output position, both computed on the host exactly as
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc do (ops.pil_bilinear_coeffs).  `axis_stride` = elements between
+// consecutive input positions along the resampled axis; the other axis and the channels are walked through (row, col) strides.
+__global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t total,
+                                                          int out_axis, int other, int64_t src_img, int64_t src_axis_stride,
+                                                          int64_t src_other_stride, int64_t dst_img, int64_t dst_axis_stride,
+                                                          int64_t dst_other_stride, const int* __restrict__ bounds,
+                                                          const int* __restrict__ kk, int ksize) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 3);
+    int64_t t = i / 3;
+    const int o = (int)(t % other); t /= other;
+    const int a = (int)(t % out_axis);
+    const int64_t n = t / out_axis;
+    const int first = __ldg(bounds + 2 * a), count = __ldg(bounds + 2 * a + 1);
+    const uint8_t* p = src + n * src_img + (int64_t)first * src_axis_stride + (int64_t)o * src_other_stride + c;
+    const int* k = kk + (int64_t)a * ksize;
+    int ss = 1 << 21;
+    for (int x = 0; x < count; ++x) ss += (int)p[(int64_t)x * src_axis_stride] * __ldg(k + x);
+    ss >>= 22;
+    dst[n * dst_img + (int64_t)a * dst_axis_stride + (int64_t)o * dst_other_stride + c] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+  }
+}
+
 extern "C" {
 
 const char* pvg_last_error(void) { return pvg::g_last_error.c_str(); }
@@ -1593,6 +1619,27 @@ int pvg_frames_u8_to_nhwc(const uint8_t* src, int N, int Hs, int Ws, int left, i
   PVG_CHECK_ARG(stdv != 0.f, "std must not be zero");
   const int64_t total = (int64_t)N * H * W;
   frames_u8_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, total, Hs, Ws, left, top, H, W, mean, stdv, dst);
+  PVG_LAUNCH_OK();
+  return 0;
+}
+
+int pvg_resample_u8(const uint8_t* src, int N, int Hs, int Ws, int left, int top, int Hin, int Win, int vertical, int out_size,
+                    const int* bounds, const int* kk, int ksize, uint8_t* dst, void* stream) {
+  PVG_CHECK_ARG(src && dst && bounds && kk && N > 0 && Hin > 0 && Win > 0 && out_size > 0 && ksize > 0, "bad argument");
+  PVG_CHECK_ARG(left >= 0 && top >= 0 && left + Win <= Ws && top + Hin <= Hs, "input box outside the source frame");
+  const uint8_t* s0 = src + ((int64_t)top * Ws + left) * 3;
+  const int64_t src_img = (int64_t)Hs * Ws * 3;
+  if (!vertical) {                 // [N][Hin][Win][3] -> [N][Hin][out_size][3]
+    const int64_t total = (int64_t)N * Hin * out_size * 3;
+    resample_u8_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(s0, dst, total, out_size, Hin, src_img, 3, (int64_t)Ws * 3,
+                                                                               (int64_t)Hin * out_size * 3, 3, (int64_t)out_size * 3,
+                                                                               bounds, kk, ksize);
+  } else {                         // [N][Hin][Win][3] -> [N][out_size][Win][3]
+    const int64_t total = (int64_t)N * out_size * Win * 3;
+    resample_u8_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(s0, dst, total, out_size, Win, src_img, (int64_t)Ws * 3, 3,
+                                                                               (int64_t)out_size * Win * 3, (int64_t)Win * 3, 3, bounds,
+                                                                               kk, ksize);
+  }
   PVG_LAUNCH_OK();
   return 0;
 }

@@ -1168,17 +1168,103 @@ def concat_pad(parts: Sequence[Tensor], multiple: int = 32, planes: Sequence[int
 # ---------------------------------------------------------------------------------------------------------------
 # input pipeline
 # ---------------------------------------------------------------------------------------------------------------
-def frames_from_uint8(frames: Tensor, crop: Optional[Sequence[int]] = None, mean: float = 0.5, std: float = 0.5) -> Tensor:
-    """PIL ``crop`` + ``ToTensor`` + ``Normalize(mean, std)`` of dataset/transforms.py:15-32,90-108 on the device.
-    frames: (N, Hs, Ws, 3) uint8 CUDA tensor (decoded RGB frames); crop = [left, upper, right, lower] as in the YAML
-    (``data.crop``).  Returns the (N, 3, H, W) fp32 observation tensor (channels_last storage, what the kernels consume),
-    bit-identical to the reference's CPU transform for frames that already have the target size."""
+def pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Pillow's ``precompute_coeffs`` (box = the whole axis, BILINEAR: triangle filter, support 1, widened by the scale when
+    shrinking) followed by ``normalize_coeffs_8bpc`` (22-bit fixed point), in the same double-precision operation order
+    (src/libImaging/Resample.c): (bounds int32 [out_size, 2] = (first, count), coefficients int32 [out_size, ksize], ksize)."""
+    import math
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = [[0, 0] for _ in range(out_size)]
+    kk = [[0] * ksize for _ in range(out_size)]
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)                # C's (int): truncation toward zero, like Python's int()
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        ws = []
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            if a < 0.0:
+                a = -a
+            wv = 1.0 - a if a < 1.0 else 0.0
+            ws.append(wv)
+            ww += wv
+        for x in range(xmax):
+            v = ws[x] / ww if ww != 0.0 else ws[x]
+            kk[xx][x] = int(-0.5 + v * (1 << 22)) if v < 0 else int(0.5 + v * (1 << 22))
+        bounds[xx] = [xmin, xmax]
+    return bounds, kk, ksize
+
+
+_resample_tables = {}
+
+
+def _resample_table(in_size: int, out_size: int, device):
+    key = (in_size, out_size, str(device))
+    hit = _resample_tables.get(key)
+    if hit is None:
+        b, k, ks = pil_bilinear_coeffs(in_size, out_size)
+        hit = (torch.tensor(b, dtype=torch.int32, device=device), torch.tensor(k, dtype=torch.int32, device=device), ks)
+        _resample_tables[key] = hit
+    return hit
+
+
+def resize_frames_uint8(frames: Tensor, crop: Optional[Sequence[int]], size: Sequence[int]) -> Tensor:
+    """PIL ``crop`` + ``resize(size, Image.BILINEAR)`` of dataset/transforms.py:15-32 on uint8 frames on the device, bit-identical
+    to Pillow (antialiased two-pass resampling in 22-bit fixed point: horizontal pass, then vertical).  frames: (N, Hs, Ws, 3)
+    uint8 CUDA tensor; crop = [left, upper, right, lower] or None; size = (width, height) as in ``target_input_size``."""
+    if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+        raise _lib.PvgError("resize_frames_uint8 takes a (N, H, W, 3) uint8 CUDA tensor")
+    frames = frames.contiguous()
+    n, hs, ws, _ = frames.shape
+    left, top, right, bottom = (0, 0, ws, hs) if crop is None else (int(v) for v in crop)
+    hin, win = bottom - top, right - left
+    ow, oh = int(size[0]), int(size[1])
+    cur, cur_h, cur_w, box = frames, hs, ws, (left, top, hin, win)
+    if ow != win:                                          # horizontal pass first (ImagingResample)
+        b, k, ks = _resample_table(win, ow, frames.device)
+        tmp = torch.empty((n, hin, ow, 3), dtype=torch.uint8, device=frames.device)
+        call("pvg_resample_u8", cur.data_ptr(), n, cur_h, cur_w, box[0], box[1], hin, win, 0, ow, b.data_ptr(), k.data_ptr(), ks,
+             tmp.data_ptr(), _stream())
+        cur, cur_h, cur_w, box = tmp, hin, ow, (0, 0, hin, ow)
+    if oh != hin:
+        b, k, ks = _resample_table(hin, oh, frames.device)
+        out = torch.empty((n, oh, ow, 3), dtype=torch.uint8, device=frames.device)
+        call("pvg_resample_u8", cur.data_ptr(), n, cur_h, cur_w, box[0], box[1], hin, ow, 1, oh, b.data_ptr(), k.data_ptr(), ks,
+             out.data_ptr(), _stream())
+        cur, cur_h, cur_w, box = out, oh, ow, (0, 0, oh, ow)
+    if cur is frames:                                      # nothing to resample: the crop itself
+        cur = frames[:, top:bottom, left:right].contiguous()
+    return cur
+
+
+def frames_from_uint8(frames: Tensor, crop: Optional[Sequence[int]] = None, mean: float = 0.5, std: float = 0.5,
+                      size: Optional[Sequence[int]] = None) -> Tensor:
+    """PIL ``crop`` (+ ``resize(size, BILINEAR)``) + ``ToTensor`` + ``Normalize(mean, std)`` of dataset/transforms.py:15-32,90-108
+    on the device.  frames: (N, Hs, Ws, 3) uint8 CUDA tensor (decoded RGB frames); crop = [left, upper, right, lower] as in the
+    YAML (``data.crop``); size = (width, height) = ``target_input_size`` (None: the crop already has it, as in every shipped
+    config).  Returns the (N, 3, H, W) fp32 observation tensor (channels_last storage, what the kernels consume), bit-identical
+    to the reference's CPU transform."""
     if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
         raise _lib.PvgError("frames_from_uint8 takes a (N, H, W, 3) uint8 CUDA tensor")
     frames = frames.contiguous()
     n, hs, ws, _ = frames.shape
     left, top, right, bottom = (0, 0, ws, hs) if crop is None else (int(v) for v in crop)
     h, w = bottom - top, right - left
+    if size is not None and (int(size[0]), int(size[1])) != (w, h):
+        frames = resize_frames_uint8(frames, crop, size)
+        n, hs, ws, _ = frames.shape
+        left, top, h, w = 0, 0, hs, ws
     out = empty_nhwc((n, 3, h, w), frames.device)
     call("pvg_frames_u8_to_nhwc", frames.data_ptr(), n, hs, ws, left, top, h, w, float(mean), float(std), out.data_ptr(), _stream())
     return out

@@ -361,3 +361,39 @@ def test_small_distribution_losses_match_the_reference():
     for k in golden.files:
         np.testing.assert_allclose(got[k], golden[k], rtol=2e-6, atol=1e-7, err_msg=k)
 
+
+def _numpy_resample(img, bounds, kk, axis):
+    """Integer restatement of Pillow's 8-bit resampling pass (test infrastructure): img (H, W, 3) uint8."""
+    import numpy as np
+    src = np.moveaxis(img.astype(np.int64), axis, 0)
+    out = np.empty((len(bounds),) + src.shape[1:], dtype=np.uint8)
+    for a, ((first, count), k) in enumerate(zip(bounds, kk)):
+        ss = np.full(src.shape[1:], 1 << 21, dtype=np.int64)
+        for x in range(count):
+            ss = ss + src[first + x] * k[x]
+        out[a] = np.clip(ss >> 22, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+def test_pil_resize_coefficients_reproduce_pillow():
+    """ops.pil_bilinear_coeffs (the host half of pvg_resample_u8) + an integer restatement of the two passes against what the
+    reference's own transform (PIL crop + resize(BILINEAR), dataset/transforms.py:15-32) produced:
+    tests/golden/input_resize.npz from oracle/make_metric_golden.py --input-pipeline.  Bit-exact."""
+    import numpy as np
+    from playablevideogeneration_b200 import ops
+    g = np.load(os.path.join(ROOT, "tests", "golden", "input_resize.npz"))
+    for name in ("down", "up", "mixed", "bair"):
+        frames, crop, size, want = g[f"{name}.frames"], g[f"{name}.crop"], g[f"{name}.size"], g[f"{name}.u8"]
+        if crop[0] >= 0:
+            frames = frames[:, crop[1]:crop[3], crop[0]:crop[2]]
+        ow, oh = int(size[0]), int(size[1])
+        for f, w in zip(frames, want):
+            cur = f
+            if ow != cur.shape[1]:
+                b, k, _ = ops.pil_bilinear_coeffs(cur.shape[1], ow)
+                cur = _numpy_resample(cur, b, k, 1)
+            if oh != cur.shape[0]:
+                b, k, _ = ops.pil_bilinear_coeffs(cur.shape[0], oh)
+                cur = _numpy_resample(cur, b, k, 0)
+            assert np.array_equal(cur, w), name
+

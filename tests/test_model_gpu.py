@@ -429,3 +429,20 @@ def test_input_pipeline_kernel_matches_reference_transform():
     assert torch.equal(full.cpu(), want.permute(0, 3, 1, 2))
     with pytest.raises(Exception):
         ops.frames_from_uint8(frames, crop=[0, 0, 1000, 10])
+
+
+def test_input_pipeline_resize_matches_pillow_bit_for_bit():
+    """PIL crop + resize(BILINEAR) + ToTensor + Normalize on the device (pvg_resample_u8 x 2 + pvg_frames_u8_to_nhwc) against the
+    unmodified reference transform (tests/golden/input_resize.npz): the resized uint8 frames and the normalised tensors are
+    bit-identical - shrinking (antialiased), growing, one axis only, and BAIR's 64 x 64 -> 256 x 256."""
+    from playablevideogeneration_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_resize.npz"))
+    for name in ("down", "up", "mixed", "bair"):
+        frames = torch.from_numpy(g[f"{name}.frames"]).to(DEV)
+        crop = None if g[f"{name}.crop"][0] < 0 else [int(v) for v in g[f"{name}.crop"]]
+        size = [int(v) for v in g[f"{name}.size"]]
+        u8 = ops.resize_frames_uint8(frames, crop, size)
+        assert np.array_equal(u8.cpu().numpy(), g[f"{name}.u8"]), name
+        out = ops.frames_from_uint8(frames, crop=crop, size=size)
+        assert np.array_equal(out.cpu().numpy(), g[f"{name}.out"]), name
+
