@@ -510,7 +510,7 @@ class Conv2dFn(torch.autograd.Function):
             if tap is not None and fused[0] in (2, 3):
                 dy, tap = _materialize_tap(dy, y, tap), None
             if tap is not None:          # image-facing VGG conv1_1: activation backward with the tap gradient folded in
-                target, gl = tap
+                target, gl, _ = tap
                 call("pvg_act_bwd_tap", dy.data_ptr(), y.data_ptr(), act, float(slope), g.data_ptr(), dy.shape[0],
                      dy.numel() // dy.shape[0], target.data_ptr(), gl.data_ptr(), _stream())
             elif fused[0] == 2:          # activation backward and the 16-bit planes of g in one pass
@@ -631,7 +631,7 @@ def _backward_h3(ctx, dy, x, weight, y, tap=None):
         call("pvg_amax", dy.data_ptr(), dy.numel(), amax.data_ptr(), st)
     need_g = has_bias and ctx.needs_input_grad[2]
     if act != ACT_NONE and tap is not None:
-        target, gl = tap                   # dy + the feature-matching L1 gradient, activation backward and planes in one pass
+        target, gl, _ = tap                # dy + the feature-matching L1 gradient, activation backward and planes in one pass
         g = torch.empty_like(dy) if need_g else None
         call("pvg_act_bwd_tap_split_16_scaled", dy.data_ptr(), y.data_ptr(), act, float(slope), _p(g), planes.data_ptr(),
              dy.shape[0], dy.numel() // dy.shape[0], amax.data_ptr(), inv.data_ptr(), target.data_ptr(), gl.data_ptr(), st)
@@ -1325,15 +1325,16 @@ def pending_tap(dy: Optional[Tensor]):
     tag = getattr(dy, "_pvg_tap", None) if dy is not None else None
     if tag is None:
         return None
-    target, gl, version = tag
+    target, gl, version, feature = tag
     if version != dy._version:
         raise _lib.PvgError("a gradient carrying a deferred feature-matching term was modified before its convolution saw it")
     del dy._pvg_tap
-    return target, gl
+    return target, gl, feature
 
 
-def _materialize_tap(dy: Tensor, y: Tensor, tap) -> Tensor:
-    target, gl = tap
+def _materialize_tap(dy: Tensor, y: Optional[Tensor], tap) -> Tensor:
+    target, gl, feature = tap
+    y = feature if y is None else y           # a convolution without activation does not save its output: the tap node did
     n = y.shape[0]
     db = torch.empty_like(y)
     call("pvg_absdiff_mean_bwd", target.data_ptr(), y.data_ptr(), gl.data_ptr(), n, y.numel() // n, db.data_ptr(), _stream())
@@ -1363,7 +1364,7 @@ class TapL1Fn(torch.autograd.Function):
         target, x = ctx.saved_tensors
         gl = g_loss.contiguous().float()
         if g_x is not None and ctx.defer and _is_nhwc_dense(g_x):
-            g_x._pvg_tap = (target, gl, g_x._version)        # consumed by Conv2dFn.backward of the producing convolution
+            g_x._pvg_tap = (target, gl, g_x._version, x)     # consumed by Conv2dFn.backward of the producing convolution
             return g_x, None, None
         n = x.shape[0]
         db = torch.empty_like(x)

@@ -521,6 +521,20 @@ def test_feature_tap_l1_folded_into_the_conv_backward(monkeypatch):
     _close("tap_l1_image_grad", gf, gu.cpu(), 2e-6, 1e-9)
     assert cf.count("pvg_act_bwd_tap") == 1 and cf.count("pvg_act_bwd_tap_split_16_scaled") == 1, cf
     assert cf.count("pvg_absdiff_mean_bwd") == 1 and cu.count("pvg_absdiff_mean_bwd") == 3      # fused: only the last tap
+    # a tapped convolution WITHOUT activation cannot fold the term into an activation-backward pass: its backward adds it itself
+    grads = []
+    for fused in (True, False):
+        x = ops.nhwc(_rand(2, 64, 8, 16, seed=30).to(DEV)).requires_grad_(True)
+        f = ops.conv2d(x, ws[1])
+        tgt = _rand(2, 64, 8, 16, seed=31).to(DEV)
+        tgt = ops.nhwc(tgt)
+        if fused:
+            f, l = ops.tap_l1(f, tgt)
+        else:
+            l = ops.absdiff_mean(tgt, f)
+        (ops.conv2d(f, ws[1], bs[1], act=ops.ACT_RELU).sum() * 1e-3 + l.sum()).backward()
+        grads.append(x.grad.clone())
+    _close("tap_l1_no_activation", grads[0], grads[1].cpu(), 2e-6, 1e-9)
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 32), (3, 13, 40), (1, 256, 256), (5, 9, 7)])
