@@ -28,11 +28,10 @@ case $s in
   stem) run stem 300 python tools/stem_bench.py; run stem_t 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "stem or producer_planes" -p no:cacheprovider ;;
   layers) run layers 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check --layer-table $OUT/r02_layer_table.md ;;
   ncu_epi) run ncu_epi 300 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 3 -c 1 -f -o $OUT/r02_epi python tools/conv_micro.py 120 64 128 128 128 planes; python tools/ncu_extract.py $OUT/r02_epi.ncu-rep ;;
-  bn_micro) run bn_micro 300 python tools/bn_micro.py; PVG_LIB=$PWD/tools/ab/libpvg_b200_oldbn.so run bn_micro_old 300 python tools/bn_micro.py ;;
+  bn_micro) run bn_micro 300 python tools/bn_micro.py ;;      # A/B against another build: PVG_LIB=/path/to/libpvg_b200_other.so
   ncu_final) for spec in "vgg2_1_planes 120 64 128 128 128 planes" "vgg3_2_planes 120 256 256 64 64 planes" "dec_res_sums 8 128 128 64 64 sums" "enc_res_sums 128 64 64 32 32 sums" "vgg1_2_relu 120 64 64 256 256 bias+relu"; do set -- $spec; run ncu_$1 200 ncu --set full --clock-control none --import-source on -k regex:conv_h3 -s 3 -c 1 -f -o $OUT/r02f_$1 python tools/conv_micro.py $2 $3 $4 $5 $6 $7; python tools/ncu_extract.py $OUT/r02f_$1.ncu-rep; done ;;
   micro) run micro 600 python tools/conv_micro.py ;;
   micro_lstm) run micro_lstm 300 python tools/conv_micro.py lstm ;;
-  micro_ab) PVG_LIB=$PWD/tools/ab/libpvg_b200_ew4.so run micro_ew4 600 python tools/conv_micro.py ;;
   benchq) run benchq 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
   benchq_notags) PVG_NO_AMAX_TAGS=1 run benchq_notags 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline --no-secondary --no-parity-check ;;
   bench) run bench 600 python bench.py --steps 3 --warmup 3 ;;
