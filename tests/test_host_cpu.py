@@ -397,3 +397,26 @@ def test_pil_resize_coefficients_reproduce_pillow():
                 cur = _numpy_resample(cur, b, k, 0)
             assert np.array_equal(cur, w), name
 
+
+def test_pil_resize_restatement_against_pillow_on_random_sizes():
+    """Wider pin of ops.pil_bilinear_coeffs than the four committed goldens: when Pillow is importable, 60 random (input size,
+    output size) pairs - shrinking by up to 7x, growing by up to 5x, prime sizes - must reproduce Image.resize(BILINEAR)."""
+    import numpy as np
+    PIL = pytest.importorskip("PIL")
+    from PIL import Image
+    from playablevideogeneration_b200 import ops
+    rng = np.random.RandomState(5)
+    for _ in range(60):
+        h, w = int(rng.randint(3, 97)), int(rng.randint(3, 97))
+        oh, ow = int(rng.randint(1, 120)), int(rng.randint(1, 120))
+        img = rng.randint(0, 256, size=(h, w, 3), dtype=np.uint8)
+        want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        cur = img
+        if ow != w:
+            b, k, _ = ops.pil_bilinear_coeffs(w, ow)
+            cur = _numpy_resample(cur, b, k, 1)
+        if oh != h:
+            b, k, _ = ops.pil_bilinear_coeffs(h, oh)
+            cur = _numpy_resample(cur, b, k, 0)
+        assert np.array_equal(cur, want), (h, w, oh, ow)
+
